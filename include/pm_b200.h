@@ -1,0 +1,181 @@
+/*
+ * pm_b200.h -- C-ABI of the B200-native dictionary-matching engine (libpm_b200.so).
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference repository yehonatan145/PatternMatching).
+ * The product has NO CPU fallback: every scan entry point fails (non-zero return / pm_last_error)
+ * when no CUDA device is usable.
+ *
+ * Pattern identity.  The reference identifies a pattern by a PatternsTreeNode* whose payload is
+ * PatternInternalID{file_number, line_number} of the FIRST occurrence of the byte string
+ * (Core/src/PatternsTree.h:25-28, 90-106; PatternsTree.c:193-196, 274-283).  On the device a pattern
+ * is a dense "pid": 0 = no pattern (null_pattern_id), 1..P in order of first occurrence, which is
+ * the (file,line)-sorted order.  pm_dict_pattern() maps pid -> (file, line, user id).
+ */
+#ifndef PM_B200_H
+#define PM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pm_dict pm_dict;     /* host side: patterns + compiled tables */
+typedef struct pm_engine pm_engine; /* device side: tables resident in HBM + scan state */
+
+/* last error message of the calling thread ("" if none) */
+const char* pm_last_error(void);
+int pm_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dictionary compilation on the host
+ * ---------------------------------------------------------------------------------------------- */
+/* replaces: ac_create (Core/src/mpac.c:236-247) + the PatternsTree ingest state */
+pm_dict* pm_dict_create(void);
+void pm_dict_free(pm_dict* d);
+/* One .dict line -> raw bytes; grammar of parse_pattern_from_line (Core/src/parser.c:63-99) incl.
+ * its rejection rules.  Returns 1 and the pattern in out[0..*out_len) (capacity >= n), 0 if rejected. */
+int pm_parse_pattern_line(const uint8_t* line, size_t n, uint8_t* out, size_t* out_len);
+/* replaces: fpt_fill_with_dict_file (Core/src/PatternsTree.c:260-291) for the next -d file;
+ * file_number = number of previous pm_dict_add_file/_mem calls.  Returns 0, or -1 (cannot read). */
+int pm_dict_add_file(pm_dict* d, const char* path);
+int pm_dict_add_mem(pm_dict* d, const uint8_t* data, size_t n);
+/* replaces: MpsElem.add_pattern (Core/src/mps.h:74; ac_add_pattern mpac.c:257-273).  The bytes are
+ * copied (they are binary and may contain 0x00, Core/src/README.md:85-89).  `user_id` is an opaque
+ * 64-bit value returned by pm_dict_pattern (the shim stores the pattern_id_t pointer there).
+ * Returns the pid, or the pid of the identical pattern added earlier (de-dup keeps the first). */
+uint32_t pm_dict_add_pattern(pm_dict* d, const uint8_t* pat, size_t len, uint32_t file, uint32_t line, uint64_t user_id);
+/* replaces: MpsElem.compile (Core/src/mps.h:75; ac_compile mpac.c:282-291, add_failure_links :187-210)
+ * and convert_fpt_to_patterns_tree (PatternsTree.c:416-428) for the suffix-parent relation. */
+int pm_dict_compile(pm_dict* d);
+
+typedef struct {
+    uint64_t n_lines, n_rejected, n_duplicates; /* ingest accounting */
+    uint32_t n_patterns;                        /* unique patterns P */
+    uint32_t max_pat_len;                       /* conf->max_pat_len, PatternsTree.c:310 */
+    uint64_t total_pat_bytes;
+    uint32_t n_ac_states;                       /* forward trie states incl. root == reference n_states */
+    uint32_t n_sfx_nodes;                       /* nodes of the reversed-pattern (suffix) trie incl. root */
+    uint32_t n_sfx_rows;                        /* suffix-trie nodes that own a transition row */
+    uint32_t n_classes;                         /* byte equivalence classes (alphabet compression) */
+    uint32_t n_hot2_cont;                       /* 2-byte suffixes that continue below the shared-memory table */
+    uint64_t table_bytes;                       /* bytes of all device tables */
+} pm_dict_info;
+int pm_dict_get_info(const pm_dict* d, pm_dict_info* info);
+/* pid in 1..P -> identity; parent_pid = longest proper suffix that is itself a pattern (0 = none),
+ * i.e. PatternsTreeNode.parent (Core/src/PatternsTree.h:90-94). */
+int pm_dict_pattern(const pm_dict* d, uint32_t pid, uint32_t* file, uint32_t* line, uint64_t* user_id,
+                    uint32_t* parent_pid, uint32_t* len, const uint8_t** bytes);
+/* replaces: is_pattern_suffix (Core/src/PatternsTree.c:485-494) on pids */
+int pm_dict_is_pattern_suffix(const pm_dict* d, uint32_t first_pid, uint32_t second_pid);
+
+/* ------------------------------------------------------------------------------------------------
+ * Engine: tables in HBM, scan kernels
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+    PM_ALGO_SFX = 0, /* exact: per-position backward walk of the reversed-pattern trie (default) */
+    PM_ALGO_DFA = 1, /* exact: per-thread forward walk of the flat Aho-Corasick DFA */
+    PM_ALGO_KR  = 2  /* randomized: Karp-Rabin suffix-stage fingerprints (mpbg/bgps/kmprt style) */
+};
+enum {
+    PM_STREAM_UNIFORM = 0, /* uniform bytes (splitmix64 counter generator) */
+    PM_STREAM_PLANTED = 1, /* uniform background + one planted pattern per 4096-byte block */
+    PM_STREAM_ALMOST  = 2, /* concatenated random-length pattern prefixes (write_first_lines.py semantics) */
+    PM_STREAM_AB      = 3  /* {a,b} with P(a)=0.75 (adversarial small alphabet) */
+};
+
+/* Upload the compiled tables to CUDA device `device`.  NULL (and pm_last_error) when there is no
+ * usable device: there is no CPU fallback. */
+pm_engine* pm_engine_create(const pm_dict* d, int device);
+void pm_engine_free(pm_engine* e);
+/* replaces: MpsElem.total_mem (Core/src/mps.h:77): bytes of all device-resident tables */
+size_t pm_engine_total_mem(const pm_engine* e);
+/* KR variant parameters: r is drawn from `seed` (the reference draws it from rand(), bgps.c:469-475) */
+int pm_engine_set_kr_seed(pm_engine* e, uint64_t seed);
+
+/* Scan n bytes that are already in device memory.
+ *   d_stream   : device pointer, 16-byte aligned, first byte to report on
+ *   hist_valid : how many bytes directly BEFORE d_stream belong to the same stream and are readable
+ *                (0 = d_stream is the start of the stream / of the allocation).  With
+ *                hist_valid >= max_pat_len-1 the result equals the continuous scan.
+ *   d_out      : device pointer to n uint16 pids: d_out[i] = pid of the LONGEST pattern that is a
+ *                suffix of stream[..i] (what read_char returns, Core/src/mps.h:41-42), 0 = none
+ *   cuda_stream: a cudaStream_t (0 = default stream); the call is asynchronous on it.
+ * replaces: the per-byte loop `algo_results[j] = read_char_func(obj, stream_buffer[j])`
+ *           (Core/src/measure.c:292-294) over ac_read_char (Core/src/mpac.c:304-319). */
+int pm_engine_scan_device(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid,
+                          uint16_t* d_out, void* cuda_stream);
+
+/* Scan a HOST buffer: pinned double-buffered H2D copy, scan, D2H of the dense uint16 result,
+ * synchronous.  State is carried across calls exactly like consecutive read_char calls until
+ * pm_engine_reset().  replaces: the chunk loop of measure_single_instance_stats (measure.c:281-304). */
+int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n, uint16_t* out);
+/* replaces: MpsElem.reset (Core/src/mps.h:78; ac_reset mpac.c:339-342) */
+void pm_engine_reset(pm_engine* e);
+
+/* Device-side reduction of a dense result: positions with a match, matches including PatternsTree
+ * ancestors, and the order-independent digest sums of (global position, file, line) defined in
+ * oracle/pm_oracle.h (match_digest).  pos_base = global position of d_out[0].  Synchronous.
+ * out4 = {positions, matches, hsum_longest, hsum_all}. */
+int pm_engine_summarize(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t pos_base, uint64_t out4[4],
+                        void* cuda_stream);
+
+/* Compact a dense result into position-sorted (pos, pid) records (pos = pos_base + i, 40 bits;
+ * pid 24 bits; record = pos << 24 | pid), longest match per position; with expand_ancestors != 0
+ * one record per match incl. PatternsTree ancestors (longest first).  d_records has capacity `cap`
+ * records; *n_records receives the number produced (may exceed cap: nothing is written past cap).
+ * Synchronous. */
+int pm_engine_compact(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t pos_base, int expand_ancestors,
+                      uint64_t* d_records, size_t cap, uint64_t* n_records, void* cuda_stream);
+
+/* Seeded synthetic streams generated directly in HBM (definitions: SURVEY.md 8d, oracle/pm_oracle.c):
+ * writes bytes [off, off+n) of stream `kind` to d_dst.  off and n multiples of 4096. */
+int pm_engine_generate(pm_engine* e, int kind, uint64_t off, size_t n, uint8_t* d_dst, void* cuda_stream);
+
+/* Timing helper used by bench.py: runs pm_engine_scan_device `iters` times on `cuda_stream`
+ * bracketed by CUDA events recorded ON THAT STREAM and returns the mean milliseconds per scan. */
+int pm_engine_time_scan(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid,
+                        uint16_t* d_out, int iters, float* ms_per_scan, void* cuda_stream);
+/* number of kernel launches issued by this engine since creation (bench.py's gpu_launches) */
+uint64_t pm_engine_launch_count(const pm_engine* e);
+
+/* ------------------------------------------------------------------------------------------------
+ * The reference plugin surface (Core/src/mps.h:71-80) -- implemented in mps_gpu_shim.c on top of
+ * the calls above.  Types are spelled with void* / char* exactly as in MpsElem so that the
+ * reference can register it unchanged.
+ * ---------------------------------------------------------------------------------------------- */
+void* gpu_create(void);                                                   /* MpsElem.create      */
+void gpu_add_pattern(void* obj, char* pat, size_t len, void* pattern_id); /* MpsElem.add_pattern */
+void gpu_compile(void* obj);                                              /* MpsElem.compile     */
+void* gpu_read_char(void* obj, char c);                                   /* MpsElem.read_char   */
+size_t gpu_total_mem(void* obj);                                          /* MpsElem.total_mem   */
+void gpu_reset(void* obj);                                                /* MpsElem.reset       */
+void gpu_free(void* obj);                                                 /* MpsElem.free        */
+/* batched extension: out[j] = what read_char would have returned for buf[j]; returns n */
+size_t gpu_read_block(void* obj, const char* buf, size_t n, void** out);
+/* same object, other kernels behind it */
+void* gpu_dfa_create(void);
+void* gpu_kr_create(void);
+
+/* Layout-compatible with MpsElem (Core/src/mps.h:71-80); pattern_id_t spelled void*. */
+typedef struct {
+    char* name;
+    void* (*create)(void);
+    void (*add_pattern)(void*, char*, size_t, void*);
+    void (*compile)(void*);
+    void* (*read_char)(void*, char);
+    size_t (*total_mem)(void*);
+    void (*reset)(void*);
+    void (*free)(void*);
+} pm_mps_elem;
+/* fill one mps_table slot: the body of a mps_gpu_register() added to mps_table_setup
+ * (Core/src/mps.c:120-124, recipe Core/src/README.md:119-130) */
+void mps_gpu_register_into(pm_mps_elem* slot);     /* exact, suffix-trie scan   */
+void mps_gpu_dfa_register_into(pm_mps_elem* slot); /* exact, forward DFA walker */
+void mps_gpu_kr_register_into(pm_mps_elem* slot);  /* randomized Karp-Rabin     */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PM_B200_H */

@@ -1,0 +1,260 @@
+// aux_kernels.cu -- kernels around the scan: seeded stream generators in HBM, the device-side
+// reduction of a dense result (counts + order-independent digests), and compaction of a dense
+// result into position-sorted (pos, pid) records with optional PatternsTree-ancestor expansion
+// (Core/src/PatternsTree.c:485-494 semantics: all matches at a position = longest + its ancestors).
+#include "aux_kernels.cuh"
+#include "pm_dev.cuh"
+
+namespace pm {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Stream generators.  Definitions are SURVEY.md 8d / oracle/pm_oracle.c; every byte is a pure
+// function of its absolute offset so that shards are generated independently.
+// ------------------------------------------------------------------------------------------------
+__global__ void gen_uniform_kernel(uint64_t off, uint64_t n, uint8_t* __restrict__ dst) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;  // 8-byte word index
+    if (i * 8 >= n) return;
+    reinterpret_cast<uint64_t*>(dst)[i] = splitmix64_d(0x5EED0001ull + (off >> 3) + i);
+}
+
+__global__ void gen_ab_kernel(uint64_t off, uint64_t n, uint8_t* __restrict__ dst) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i * 8 >= n) return;
+    const uint64_t w = splitmix64_d(0xADE50004ull + (off >> 3) + i);
+    uint64_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o |= uint64_t(((w >> (8 * k)) & 0xFF) < 192 ? 'a' : 'b') << (8 * k);
+    reinterpret_cast<uint64_t*>(dst)[i] = o;
+}
+
+// one planted pattern per 4096-byte block, on top of the uniform background
+__global__ void gen_plant_kernel(uint64_t off, uint64_t n, uint8_t* __restrict__ dst, PatTables t) {
+    const uint64_t bi = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (bi * 4096 >= n || t.n_patterns == 0) return;
+    const uint64_t b = (off >> 12) + bi;
+    const uint64_t h = splitmix64_d(0xD1C70002ull + b);
+    const uint32_t k = uint32_t(h % t.n_patterns);
+    const uint32_t len = t.len[k];
+    if (len > 4096) return;
+    const uint32_t o = uint32_t((h >> 32) % (4096 - len + 1));
+    const uint8_t* src = t.bytes + t.off[k];
+    uint8_t* d = dst + bi * 4096 + o;
+    for (uint32_t u = 0; u < len; ++u) d[u] = src[u];
+}
+
+// every 4096-byte block = concatenated random-length prefixes of random patterns
+__global__ void gen_almost_kernel(uint64_t off, uint64_t n, uint8_t* __restrict__ dst, PatTables t) {
+    const uint64_t bi = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (bi * 4096 >= n) return;
+    uint8_t* d = dst + bi * 4096;
+    if (t.n_patterns == 0) { for (int u = 0; u < 4096; ++u) d[u] = 0; return; }
+    const uint64_t b = (off >> 12) + bi;
+    uint32_t fill = 0;
+    for (uint64_t piece = 0; fill < 4096; ++piece) {
+        const uint64_t h = splitmix64_d(0xA1A50005ull + (b << 12) + piece);
+        const uint32_t k = uint32_t(h % t.n_patterns);
+        const uint32_t plen = 1 + uint32_t((h >> 32) % t.len[k]);
+        const uint8_t* src = t.bytes + t.off[k];
+        for (uint32_t u = 0; u < plen && fill < 4096; ++u, ++fill) d[fill] = src[u];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Summary of a dense result
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) summarize_kernel(const uint16_t* __restrict__ out, uint64_t n, uint64_t pos_base,
+                                                       PatTables t, unsigned long long* __restrict__ acc) {
+    uint64_t positions = 0, matches = 0, h0 = 0, h1 = 0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+        uint32_t pid = out[i];
+        if (!pid) continue;
+        const uint64_t pos = pos_base + i;
+        ++positions;
+        h0 += splitmix64_d(pos ^ t.pidhash[pid]);
+        for (; pid; pid = t.parent[pid]) {
+            h1 += splitmix64_d(pos ^ t.pidhash[pid]);
+            ++matches;
+        }
+    }
+    __shared__ uint64_t sh[4][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t v[4] = {warp_sum(positions), warp_sum(matches), warp_sum(h0), warp_sum(h1)};
+    if (lane == 0) for (int k = 0; k < 4; ++k) sh[k][wid] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        uint64_t s = 0;
+        for (int w = 0; w < 8; ++w) s += sh[threadIdx.x][w];
+        atomicAdd(&acc[threadIdx.x], (unsigned long long)s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Compaction: dense -> position-sorted records, deterministic (count, scan, scatter)
+// ------------------------------------------------------------------------------------------------
+constexpr int kCompactChunk = 2048;  // positions per CTA
+constexpr int kCompactThreads = 256;
+
+__device__ __forceinline__ uint32_t recs_at(uint32_t pid, bool expand, const PatTables& t) {
+    return pid ? (expand ? 1u + t.chain[pid] : 1u) : 0u;
+}
+
+__global__ void __launch_bounds__(kCompactThreads) compact_count_kernel(const uint16_t* __restrict__ out, uint64_t n,
+                                                                         bool expand, PatTables t,
+                                                                         unsigned long long* __restrict__ block_counts) {
+    const uint64_t base = uint64_t(blockIdx.x) * kCompactChunk;
+    uint32_t c = 0;
+    for (int k = threadIdx.x; k < kCompactChunk; k += kCompactThreads) {
+        const uint64_t i = base + k;
+        if (i < n) c += recs_at(out[i], expand, t);
+    }
+    __shared__ uint32_t sh[kCompactThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int w = 0; w < kCompactThreads / 32; ++w) s += sh[w];
+        block_counts[blockIdx.x] = s;
+    }
+}
+
+// exclusive scan of the per-CTA counts by ONE CTA (the array has n/2048 entries)
+__global__ void __launch_bounds__(1024) compact_scan_kernel(unsigned long long* __restrict__ counts, uint64_t nb,
+                                                            unsigned long long* __restrict__ total) {
+    __shared__ unsigned long long sh[32];
+    __shared__ unsigned long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint64_t base = 0; base < nb; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        unsigned long long v = i < nb ? counts[i] : 0ull, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) sh[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long w = sh[lane], z = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, z, o);
+                if (lane >= o) z += y;
+            }
+            sh[lane] = z - w;  // exclusive per-warp offsets
+        }
+        __syncthreads();
+        const unsigned long long carry = carry_s;
+        if (i < nb) counts[i] = carry + sh[wid] + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + sh[wid] + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry_s;
+}
+
+__global__ void __launch_bounds__(kCompactThreads) compact_write_kernel(const uint16_t* __restrict__ out, uint64_t n,
+                                                                         uint64_t pos_base, bool expand, PatTables t,
+                                                                         const unsigned long long* __restrict__ block_offs,
+                                                                         unsigned long long* __restrict__ recs, uint64_t cap) {
+    // each thread owns 8 consecutive positions so that records stay position-sorted
+    constexpr int kPer = kCompactChunk / kCompactThreads;
+    const uint64_t base = uint64_t(blockIdx.x) * kCompactChunk + uint64_t(threadIdx.x) * kPer;
+    uint32_t pid[kPer], c = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        pid[k] = (base + k < n) ? out[base + k] : 0;
+        c += recs_at(pid[k], expand, t);
+    }
+    // exclusive scan of c over the CTA
+    __shared__ uint32_t sh[kCompactThreads / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) sh[wid] = x;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < wid; ++w) woff += sh[w];
+    uint64_t dst = block_offs[blockIdx.x] + woff + x - c;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        uint32_t q = pid[k];
+        if (!q) continue;
+        const uint64_t pos = pos_base + base + k;
+        do {
+            if (dst < cap) recs[dst] = (pos << 24) | q;
+            ++dst;
+            q = expand ? t.parent[q] : 0;
+        } while (q);
+    }
+}
+
+}  // namespace
+
+cudaError_t generate_launch(int kind, uint64_t off, uint64_t n, uint8_t* dst, const PatTables& t, cudaStream_t st,
+                            uint64_t* launches) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t words = uint32_t((n + 7) / 8), blocks4k = uint32_t((n + 4095) / 4096);
+    switch (kind) {
+        case 0:
+        case 1:
+            gen_uniform_kernel<<<(words + 255) / 256, 256, 0, st>>>(off, n, dst);
+            ++*launches;
+            if (kind == 1) {
+                gen_plant_kernel<<<(blocks4k + 127) / 128, 128, 0, st>>>(off, n, dst, t);
+                ++*launches;
+            }
+            break;
+        case 2:
+            gen_almost_kernel<<<(blocks4k + 63) / 64, 64, 0, st>>>(off, n, dst, t);
+            ++*launches;
+            break;
+        case 3:
+            gen_ab_kernel<<<(words + 255) / 256, 256, 0, st>>>(off, n, dst);
+            ++*launches;
+            break;
+        default:
+            return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t summarize_launch(const uint16_t* out, uint64_t n, uint64_t pos_base, const PatTables& t,
+                             unsigned long long* d_acc4, int n_sms, cudaStream_t st, uint64_t* launches) {
+    cudaError_t e = cudaMemsetAsync(d_acc4, 0, 4 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess || n == 0) return e;
+    uint64_t want = (n + 255) / 256;
+    const uint32_t grid = uint32_t(want < uint64_t(n_sms) * 8 ? want : uint64_t(n_sms) * 8);
+    summarize_kernel<<<grid, 256, 0, st>>>(out, n, pos_base, t, d_acc4);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+size_t compact_blocks(uint64_t n) { return size_t((n + kCompactChunk - 1) / kCompactChunk); }
+
+cudaError_t compact_launch(const uint16_t* out, uint64_t n, uint64_t pos_base, bool expand, const PatTables& t,
+                           unsigned long long* d_block_counts, unsigned long long* d_total, unsigned long long* recs,
+                           uint64_t cap, cudaStream_t st, uint64_t* launches) {
+    const uint64_t nb = compact_blocks(n);
+    if (nb == 0) return cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st);
+    compact_count_kernel<<<uint32_t(nb), kCompactThreads, 0, st>>>(out, n, expand, t, d_block_counts);
+    compact_scan_kernel<<<1, 1024, 0, st>>>(d_block_counts, nb, d_total);
+    compact_write_kernel<<<uint32_t(nb), kCompactThreads, 0, st>>>(out, n, pos_base, expand, t, d_block_counts, recs, cap);
+    *launches += 3;
+    return cudaGetLastError();
+}
+
+}  // namespace pm

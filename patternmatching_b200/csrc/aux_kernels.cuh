@@ -1,0 +1,29 @@
+// aux_kernels.cuh -- launch interfaces of the generator / summary / compaction kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pm {
+
+// Device-resident pattern tables.  off/len/bytes are indexed by the canonical pattern index
+// (pid - 1); parent/chain/pidhash by pid (entry 0 = "no pattern").
+struct PatTables {
+    uint32_t n_patterns;
+    const uint32_t* off;
+    const uint32_t* len;
+    const uint8_t* bytes;
+    const uint16_t* parent;   // PatternsTree parent pid (Core/src/PatternsTree.h:90-94), 0 = root
+    const uint16_t* chain;    // number of ancestors
+    const uint64_t* pidhash;  // splitmix64(((file+1) << 32) | line), see oracle/pm_oracle.h match_digest
+};
+
+cudaError_t generate_launch(int kind, uint64_t off, uint64_t n, uint8_t* dst, const PatTables& t, cudaStream_t st,
+                            uint64_t* launches);
+cudaError_t summarize_launch(const uint16_t* out, uint64_t n, uint64_t pos_base, const PatTables& t,
+                             unsigned long long* d_acc4, int n_sms, cudaStream_t st, uint64_t* launches);
+size_t compact_blocks(uint64_t n);
+cudaError_t compact_launch(const uint16_t* out, uint64_t n, uint64_t pos_base, bool expand, const PatTables& t,
+                           unsigned long long* d_block_counts, unsigned long long* d_total, unsigned long long* recs,
+                           uint64_t cap, cudaStream_t st, uint64_t* launches);
+
+}  // namespace pm

@@ -1,0 +1,368 @@
+// dict.cpp -- host dictionary compiler.  See dict.hpp for the reference lines each part restates.
+#include "dict.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <unordered_map>
+
+namespace pm {
+
+uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+uint64_t kr_pow(uint64_t a, uint64_t e) {
+    uint64_t r = 1;
+    a %= kKrP;
+    while (e) {
+        if (e & 1) r = kr_mul(r, a);
+        a = kr_mul(a, a);
+        e >>= 1;
+    }
+    return r;
+}
+uint64_t kr_inv(uint64_t a) { return kr_pow(a, kKrP - 2); }  // Fermat; same value as field.c's Euclid
+uint64_t kr_fp(const uint8_t* s, size_t n, uint64_t r) {
+    uint64_t acc = 0, rn = 1;
+    for (size_t i = 0; i < n; ++i) {
+        acc = (acc + s[i] * rn) % kKrP;
+        rn = kr_mul(rn, r);
+    }
+    return acc;
+}
+
+// --------------------------------------------------------------------------------------------
+// A byte trie built by hashing (node, byte) -> child, then renumbered breadth-first with children
+// in byte order (deterministic, shallow nodes get the small ids).
+// --------------------------------------------------------------------------------------------
+struct Dict::Trie {
+    std::unordered_map<uint64_t, uint32_t> edge;
+    std::vector<uint32_t> term;  // pid ending at the node, 0 = none
+    Trie() { term.push_back(0); edge.reserve(1 << 16); }
+    uint32_t child(uint32_t node, uint8_t b) const {
+        auto it = edge.find((uint64_t(node) << 8) | b);
+        return it == edge.end() ? 0 : it->second;
+    }
+    uint32_t child_or_add(uint32_t node, uint8_t b) {
+        auto ins = edge.emplace((uint64_t(node) << 8) | b, uint32_t(term.size()));
+        if (ins.second) term.push_back(0);
+        return ins.first->second;
+    }
+    size_t size() const { return term.size(); }
+};
+
+namespace {
+// Breadth-first CSR view of a Trie.
+struct Bfs {
+    uint32_t n = 0;
+    std::vector<uint32_t> off, child, parent, depth, term;
+    std::vector<uint8_t> byte, in_byte;
+    explicit Bfs(const std::unordered_map<uint64_t, uint32_t>& edge, const std::vector<uint32_t>& term_old) {
+        n = uint32_t(term_old.size());
+        // edges sorted by (old parent, byte)
+        std::vector<std::pair<uint64_t, uint32_t>> es(edge.begin(), edge.end());
+        std::sort(es.begin(), es.end());
+        std::vector<uint32_t> old_off(n + 1, 0);
+        for (auto& e : es) old_off[(e.first >> 8) + 1]++;
+        for (uint32_t i = 0; i < n; ++i) old_off[i + 1] += old_off[i];
+        std::vector<uint32_t> order;  // bfs position -> old id
+        order.reserve(n);
+        std::vector<uint32_t> new_id(n, 0);
+        order.push_back(0);
+        parent.assign(n, 0); depth.assign(n, 0); in_byte.assign(n, 0);
+        for (size_t h = 0; h < order.size(); ++h) {
+            uint32_t o = order[h];
+            for (uint32_t k = old_off[o]; k < old_off[o + 1]; ++k) {
+                uint32_t c = es[k].second;
+                new_id[c] = uint32_t(order.size());
+                parent[new_id[c]] = uint32_t(h);
+                depth[new_id[c]] = depth[h] + 1;
+                in_byte[new_id[c]] = uint8_t(es[k].first & 0xFF);
+                order.push_back(c);
+            }
+        }
+        off.assign(n + 1, 0); child.resize(n ? n - 1 : 0); byte.resize(n ? n - 1 : 0); term.resize(n);
+        uint32_t k2 = 0;
+        for (uint32_t h = 0; h < n; ++h) {
+            uint32_t o = order[h];
+            term[h] = term_old[o];
+            off[h] = k2;
+            for (uint32_t k = old_off[o]; k < old_off[o + 1]; ++k) {
+                child[k2] = new_id[es[k].second];
+                byte[k2] = uint8_t(es[k].first & 0xFF);
+                ++k2;
+            }
+        }
+        off[n] = k2;
+    }
+    bool internal(uint32_t v) const { return off[v + 1] > off[v]; }
+};
+}  // namespace
+
+Dict::Dict() : fwd_(new Trie()) {}
+Dict::~Dict() { delete fwd_; }
+
+// Core/src/parser.c:63-99.  Reads at or past the end of the line see the getline terminator, which
+// is neither ' ' nor a hex digit; a space right before the closing bar therefore rejects the line.
+bool Dict::parse_line(const uint8_t* line, size_t n, uint8_t* out, size_t* out_len) {
+    auto hex = [](int ch) -> int {
+        if (ch >= '0' && ch <= '9') return ch - '0';
+        if (ch >= 'a' && ch <= 'f') return ch - 'a' + 10;
+        if (ch >= 'A' && ch <= 'F') return ch - 'A' + 10;
+        return -1;
+    };
+    auto at = [&](size_t p) -> int { return p < n ? line[p] : '\n'; };
+    size_t len = 0, pos = 0;
+    *out_len = 0;
+    while (pos < n) {
+        if (line[pos] != '|') { out[len++] = line[pos++]; continue; }
+        ++pos;
+        while (pos < n && line[pos] != '|') {
+            while (at(pos) == ' ') ++pos;
+            int hi = hex(at(pos)); ++pos;
+            while (at(pos) == ' ') ++pos;
+            int lo = hex(at(pos)); ++pos;
+            if (hi < 0 || lo < 0) return false;
+            out[len++] = uint8_t(hi * 16 + lo);
+        }
+        if (pos >= n) return false;  // unterminated hex section
+        ++pos;
+    }
+    *out_len = len;
+    return len != 0;
+}
+
+uint32_t Dict::add_pattern(const uint8_t* pat, size_t len, uint32_t file, uint32_t line, uint64_t user) {
+    if (compiled || len == 0) return 0;
+    uint32_t s = 0;
+    for (size_t i = 0; i < len; ++i) s = fwd_->child_or_add(s, pat[i]);
+    if (fwd_->term[s]) { ++n_dups; return fwd_->term[s]; }  // PatternsTree.c:193-196: first occurrence wins
+    Pattern p;
+    p.file = file; p.line = line; p.len = uint32_t(len); p.off = bytes.size(); p.user = user;
+    bytes.insert(bytes.end(), pat, pat + len);
+    pats.push_back(p);
+    fwd_->term[s] = uint32_t(pats.size());
+    max_len = std::max<uint32_t>(max_len, uint32_t(len));
+    return uint32_t(pats.size());
+}
+
+// PatternsTree.c:260-291: every line read counts (1-based), trailing '\n' stripped, rejected and
+// empty lines skipped.
+int Dict::add_mem(const uint8_t* data, size_t n) {
+    uint32_t file = n_files++, line_no = 0;
+    std::vector<uint8_t> tmp;
+    size_t pos = 0;
+    while (pos < n) {
+        const uint8_t* nl = static_cast<const uint8_t*>(memchr(data + pos, '\n', n - pos));
+        size_t len = nl ? size_t(nl - (data + pos)) : n - pos;
+        ++line_no; ++n_lines;
+        tmp.resize(len + 1);
+        size_t plen = 0;
+        if (parse_line(data + pos, len, tmp.data(), &plen)) add_pattern(tmp.data(), plen, file, line_no, 0);
+        else if (len) ++n_rejected;
+        pos += len + (nl ? 1 : 0);
+    }
+    return 0;
+}
+
+int Dict::add_file(const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) { error = std::string("cannot open dictionary file ") + path; return -1; }
+    std::vector<uint8_t> data;
+    uint8_t buf[1 << 16];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof(buf), f)) > 0) data.insert(data.end(), buf, buf + got);
+    fclose(f);
+    return add_mem(data.data(), data.size());
+}
+
+bool Dict::is_pattern_suffix(uint32_t first, uint32_t second) const {  // PatternsTree.c:485-494
+    if (first == 0) return false;
+    for (uint32_t cur = second; cur; cur = pats[cur - 1].parent)
+        if (cur == first) return true;
+    return false;
+}
+
+int Dict::compile() {
+    if (compiled) { error = "dictionary already compiled"; return -1; }
+    n_ac_states = uint32_t(fwd_->size());
+    const uint32_t P = uint32_t(pats.size());
+
+    // ---- reversed-pattern trie ----
+    Trie rev;
+    rev.edge.reserve(bytes.size() * 2 + 16);
+    for (uint32_t i = 0; i < P; ++i) {
+        const uint8_t* b = bytes.data() + pats[i].off;
+        uint32_t s = 0;
+        for (uint32_t k = pats[i].len; k-- > 0;) s = rev.child_or_add(s, b[k]);
+        rev.term[s] = i + 1;
+    }
+    Bfs t(rev.edge, rev.term);
+    SfxTables& x = sfx;
+    x.n_nodes = t.n;
+    // best[v] = deepest terminal on the root->v path (v included)
+    std::vector<uint32_t> best(t.n, 0);
+    for (uint32_t v = 1; v < t.n; ++v) best[v] = t.term[v] ? t.term[v] : best[t.parent[v]];
+    // PatternsTree parent = deepest terminal among the PROPER ancestors of the pattern's node
+    for (uint32_t v = 1; v < t.n; ++v)
+        if (t.term[v]) pats[t.term[v] - 1].parent = best[t.parent[v]];
+    for (uint32_t i = 0; i < P; ++i) {  // parents are shorter, hence not necessarily earlier pids: iterate by chain
+        uint32_t c = 0;
+        for (uint32_t q = pats[i].parent; q; q = pats[q - 1].parent) ++c;
+        pats[i].chain = c;
+    }
+    uint32_t maxd = 0;
+    for (uint32_t v = 0; v < t.n; ++v) maxd = std::max(maxd, t.depth[v]);
+    x.depth_hist.assign(maxd + 1, 0);
+    for (uint32_t v = 0; v < t.n; ++v) x.depth_hist[t.depth[v]]++;
+
+    // byte classes: every byte that occurs in a pattern gets its own class; the rest share class 0
+    bool used[256] = {false};
+    for (uint8_t b : bytes) used[b] = true;
+    uint32_t n_used = 0;
+    for (int b = 0; b < 256; ++b) n_used += used[b];
+    uint32_t next_cls = (n_used == 256) ? 0 : 1;
+    for (int b = 0; b < 256; ++b) x.cls[b] = used[b] ? uint8_t(next_cls++) : 0;
+    x.n_classes = next_cls ? next_cls : 1;
+    x.log2_ncp = 0;
+    while ((1u << x.log2_ncp) < x.n_classes) ++x.log2_ncp;
+
+    // rows: internal nodes of depth >= 1 in BFS order
+    std::vector<uint32_t> row_of(t.n, 0xFFFFFFFFu);
+    uint32_t n_rows = 0, n1r = 0, n2c = 0;
+    for (uint32_t v = 1; v < t.n; ++v)
+        if (t.internal(v)) {
+            row_of[v] = n_rows++;
+            if (t.depth[v] == 1) ++n1r;
+            if (t.depth[v] == 2) ++n2c;
+        }
+    x.n_rows = n_rows; x.row2_base = n1r; x.n2_cont = n2c;
+    x.cont_base = 65536 - n2c;
+    x.fits_u16 = (n2c < 65536) && (uint64_t(P) + 1 <= x.cont_base);
+
+    auto entry_for_child = [&](uint32_t c) -> uint32_t {  // walk arrives at existing child c
+        return t.internal(c) ? (kContFlag | row_of[c]) : best[c];
+    };
+    const uint32_t ncp = 1u << x.log2_ncp;
+    x.rows.assign(size_t(n_rows) * ncp, 0);
+    x.row_best.assign(n_rows, 0);
+    for (uint32_t v = 1; v < t.n; ++v) {
+        if (!t.internal(v)) continue;
+        uint32_t* row = x.rows.data() + size_t(row_of[v]) * ncp;
+        for (uint32_t c = 0; c < ncp; ++c) row[c] = best[v];  // path dies here: answer is best(v)
+        for (uint32_t k = t.off[v]; k < t.off[v + 1]; ++k) row[x.cls[t.byte[k]]] = entry_for_child(t.child[k]);
+        x.row_best[row_of[v]] = best[v];
+    }
+    x.root1.assign(256, 0);
+    std::vector<uint32_t> d1(256, 0);
+    for (uint32_t k = t.off[0]; k < t.off[1]; ++k) {
+        d1[t.byte[k]] = t.child[k];
+        x.root1[t.byte[k]] = entry_for_child(t.child[k]);
+    }
+    x.root2.assign(65536, 0);
+    if (x.fits_u16) {
+        for (uint32_t a = 0; a < 256; ++a) {
+            uint32_t v = d1[a];
+            if (!v) continue;  // c_i starts no reversed pattern: no match
+            for (uint32_t b = 0; b < 256; ++b) x.root2[(a << 8) | b] = uint16_t(best[v]);
+            for (uint32_t k = t.off[v]; k < t.off[v + 1]; ++k) {
+                uint32_t c = t.child[k];
+                uint32_t code = t.internal(c) ? x.cont_base + (row_of[c] - x.row2_base) : best[c];
+                x.root2[(a << 8) | t.byte[k]] = uint16_t(code);
+            }
+        }
+    }
+    compiled = true;
+    return 0;
+}
+
+// Core/src/mpac.c:147-210 (goto + failure + nearest-output link), completed to a DFA:
+// delta(s,c) = goto(s,c) if present else delta(fail(s),c); longest(s) = id[suffix_link(s)].
+void Dict::build_dfa() {
+    if (dfa.built) return;
+    Bfs t(fwd_->edge, fwd_->term);
+    DfaTables& d = dfa;
+    d.n_states = t.n;
+    memcpy(d.cls, sfx.cls, 256);
+    d.n_classes = sfx.n_classes; d.log2_ncp = sfx.log2_ncp;
+    const uint32_t ncp = 1u << d.log2_ncp;
+    d.delta.assign(size_t(t.n) * ncp, 0);
+    d.longest.assign(t.n, 0);
+    std::vector<uint32_t> fail(t.n, 0);
+    uint32_t maxd = 0;
+    for (uint32_t v = 0; v < t.n; ++v) maxd = std::max(maxd, t.depth[v]);
+    d.depth_count.assign(maxd + 1, 0);
+    for (uint32_t v = 0; v < t.n; ++v) d.depth_count[t.depth[v]]++;
+    // BFS ids are already in breadth-first order: a state's failure target has a smaller depth,
+    // hence a smaller id, and is complete when the state is reached.
+    for (uint32_t s = 0; s < t.n; ++s) {
+        uint32_t* row = d.delta.data() + size_t(s) * ncp;
+        if (s == 0) {
+            for (uint32_t c = 0; c < ncp; ++c) row[c] = 0;
+        } else {
+            const uint32_t* frow = d.delta.data() + size_t(fail[s]) * ncp;
+            memcpy(row, frow, sizeof(uint32_t) * ncp);
+            d.longest[s] = t.term[s] ? uint16_t(t.term[s]) : d.longest[fail[s]];
+        }
+        for (uint32_t k = t.off[s]; k < t.off[s + 1]; ++k) {
+            uint32_t c = t.child[k], cl = d.cls[t.byte[k]];
+            fail[c] = (s == 0) ? 0 : row[cl];  // delta(fail(s), byte) is still in row[cl] (copied from frow)
+            row[cl] = c;
+        }
+    }
+    d.built = true;
+}
+
+void Dict::build_kr(uint64_t seed) {
+    KrTables& k = kr;
+    k = KrTables();
+    k.seed = seed;
+    k.r = 1 + splitmix64(seed) % (kKrP - 1);
+    struct Cand { uint32_t fp8, pid, len; };
+    std::vector<Cand> cs;
+    for (uint32_t i = 0; i < pats.size(); ++i)
+        if (pats[i].len > 8)
+            cs.push_back({uint32_t(kr_fp(bytes.data() + pats[i].off + pats[i].len - 8, 8, k.r)), i + 1, pats[i].len});
+    k.n_long = uint32_t(cs.size());
+    std::sort(cs.begin(), cs.end(), [](const Cand& a, const Cand& b) {
+        if (a.fp8 != b.fp8) return a.fp8 < b.fp8;
+        if (a.len != b.len) return a.len > b.len;  // longest candidate first
+        return a.pid < b.pid;
+    });
+    uint32_t n_keys = 0;
+    for (size_t i = 0; i < cs.size(); ++i) n_keys += (i == 0 || cs[i].fp8 != cs[i - 1].fp8);
+    k.bucket_bits = 4;
+    while ((1u << k.bucket_bits) < 2 * n_keys + 1) ++k.bucket_bits;
+    const uint32_t mask = (1u << k.bucket_bits) - 1;
+    k.slot_fp.assign(size_t(1) << k.bucket_bits, 0xFFFFFFFFu);
+    k.slot_begin.assign(size_t(1) << k.bucket_bits, 0);
+    k.slot_count.assign(size_t(1) << k.bucket_bits, 0);
+    k.bloom_bits = 19;  // 64 KiB of shared memory
+    k.bloom.assign((size_t(1) << k.bloom_bits) / 32, 0);
+    for (size_t i = 0; i < cs.size(); ++i) {
+        const Pattern& p = pats[cs[i].pid - 1];
+        const uint8_t* b = bytes.data() + p.off;
+        if (i == 0 || cs[i].fp8 != cs[i - 1].fp8) {
+            uint32_t h = uint32_t(splitmix64(cs[i].fp8)) & mask;
+            while (k.slot_fp[h] != 0xFFFFFFFFu) h = (h + 1) & mask;
+            k.slot_fp[h] = cs[i].fp8;
+            k.slot_begin[h] = uint32_t(i);
+            uint32_t bit = cs[i].fp8 & ((1u << k.bloom_bits) - 1);
+            k.bloom[bit >> 5] |= 1u << (bit & 31);
+        }
+        uint32_t h = uint32_t(splitmix64(cs[i].fp8)) & mask;
+        while (k.slot_fp[h] != cs[i].fp8) h = (h + 1) & mask;
+        k.slot_count[h]++;
+        k.cand_pid.push_back(cs[i].pid);
+        k.cand_len.push_back(p.len);
+        k.cand_stage_off.push_back(uint32_t(k.stage_fp.size()));
+        for (uint32_t l = 16; l <= p.len; l <<= 1) k.stage_fp.push_back(uint32_t(kr_fp(b + p.len - l, l, k.r)));
+        k.stage_fp.push_back(uint32_t(kr_fp(b, p.len, k.r)));
+    }
+    k.built = true;
+}
+
+}  // namespace pm

@@ -1,0 +1,122 @@
+// dict.hpp -- host-side dictionary compiler (product code, C++17, no CUDA).
+//
+// Turns the merged .dict patterns into the flat tables the sm_100a scan kernels read:
+//   * ingest with the reference's line grammar, de-dup and (file,line) ids
+//     (Core/src/parser.c:63-99, Core/src/PatternsTree.c:186-214, 260-291),
+//   * the reversed-pattern ("suffix") trie with every row flattened to "final pid | continue",
+//     including the 2-byte-suffix table that lives in shared memory,
+//   * the forward Aho-Corasick DFA (Core/src/mpac.c:147-210 completed to a full DFA),
+//   * the PatternsTree parent relation flattened to pid -> parent pid
+//     (Core/src/PatternsTree.c:378-403, 485-494),
+//   * the Karp-Rabin stage tables for the randomized variant
+//     (Core/src/Fingerprint.c:29-42, Core/src/bgps.c:215-249).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace pm {
+
+constexpr uint32_t kContFlag = 0x80000000u;  // row entry: continue to row (entry & ~kContFlag)
+constexpr uint64_t kKrP = 2147483647ull;     // field size p = 2^31-1 (Core/src/mpbg.c:83)
+
+struct Pattern {
+    uint32_t file = 0, line = 0, len = 0;
+    uint64_t off = 0;       // into Dict::bytes
+    uint64_t user = 0;      // opaque id of the caller (pattern_id_t in the shim)
+    uint32_t parent = 0;    // pid of the longest proper suffix that is a pattern, 0 = none
+    uint32_t chain = 0;     // number of ancestors (length of the parent chain)
+};
+
+// Tables of the exact backward scan ("sfx"): for stream position i the kernel walks the trie of
+// REVERSED patterns along c[i], c[i-1], ... until the path dies; every table entry already holds
+// the answer for the case that the walk ends there.
+struct SfxTables {
+    uint32_t n_nodes = 0;        // incl. root
+    uint32_t n_rows = 0;         // internal nodes of depth >= 1, BFS order
+    uint32_t row2_base = 0;      // first row that belongs to a depth-2 node
+    uint32_t n2_cont = 0;        // depth-2 nodes that own a row (continue codes of root2)
+    uint32_t cont_base = 65536;  // root2 entries >= cont_base mean "continue at row2_base + (e - cont_base)"
+    bool fits_u16 = false;       // P + 1 <= cont_base: dense uint16 results and root2 codes are possible
+    uint32_t n_classes = 0;      // byte classes used by the rows (class 0 = "byte occurs in no pattern" if any)
+    uint32_t log2_ncp = 0;       // row stride = 1 << log2_ncp >= n_classes
+    uint8_t cls[256] = {0};
+    std::vector<uint16_t> root2; // [c_i << 8 | c_{i-1}] -> final pid, or continue code
+    std::vector<uint32_t> root1; // [c_i] -> final pid | kContFlag+row (bounded walker at stream start)
+    std::vector<uint32_t> rows;  // [row << log2_ncp | cls] -> final pid | kContFlag+row
+    std::vector<uint32_t> row_best; // [row] -> deepest terminal pid on the path to the row's node
+    std::vector<uint32_t> depth_hist; // nodes per depth
+};
+
+// Flat Aho-Corasick DFA of the forward trie, states in BFS order (hot states first).
+struct DfaTables {
+    uint32_t n_states = 0;
+    uint32_t n_classes = 0, log2_ncp = 0;
+    uint8_t cls[256] = {0};
+    std::vector<uint32_t> delta;   // [state << log2_ncp | cls] -> next state
+    std::vector<uint16_t> longest; // [state] -> pid of the longest pattern that is a suffix of the state string
+    std::vector<uint32_t> depth_count; // states per depth
+    bool built = false;
+};
+
+// Karp-Rabin suffix-stage tables (randomized variant).
+struct KrTables {
+    uint64_t seed = 0, r = 0;
+    uint32_t n_long = 0;                 // patterns longer than 8 bytes
+    uint32_t bucket_bits = 0;            // hash table of 8-byte-suffix fingerprints: 1 << bucket_bits slots
+    std::vector<uint32_t> slot_fp;       // fp8 stored per slot (0xFFFFFFFF = empty), open addressing
+    std::vector<uint32_t> slot_begin;    // [slot] -> first candidate in cand_*, candidates of a slot are contiguous
+    std::vector<uint32_t> slot_count;
+    std::vector<uint32_t> cand_pid;      // candidates sorted by decreasing length within a slot
+    std::vector<uint32_t> cand_len;
+    std::vector<uint32_t> cand_stage_off;// into stage_fp: fps of the suffixes of length 16,32,..,2^k and the full length
+    std::vector<uint32_t> stage_fp;
+    std::vector<uint32_t> bloom;         // 1 << bloom_bits bits: fp8 prefilter held in shared memory
+    uint32_t bloom_bits = 0;
+    bool built = false;
+};
+
+class Dict {
+  public:
+    Dict();
+    // ---- ingest ----
+    static bool parse_line(const uint8_t* line, size_t n, uint8_t* out, size_t* out_len);
+    int add_file(const char* path);
+    int add_mem(const uint8_t* data, size_t n);
+    uint32_t add_pattern(const uint8_t* pat, size_t len, uint32_t file, uint32_t line, uint64_t user);
+    int compile();
+    void build_dfa();                 // lazily, the table is large (n_states * 256 * 4 bytes)
+    void build_kr(uint64_t seed);
+    bool is_pattern_suffix(uint32_t first, uint32_t second) const;
+
+    // ---- data ----
+    std::vector<Pattern> pats;        // pats[pid-1]
+    std::vector<uint8_t> bytes;
+    uint64_t n_lines = 0, n_rejected = 0, n_dups = 0;
+    uint32_t n_files = 0, max_len = 0;
+    uint32_t n_ac_states = 1;
+    bool compiled = false;
+    SfxTables sfx;
+    DfaTables dfa;
+    KrTables kr;
+    std::string error;
+
+  private:
+    // forward trie (also the de-dup structure): hash of (state << 8 | byte) -> child
+    struct Trie;
+    Trie* fwd_;
+  public:
+    ~Dict();
+    Dict(const Dict&) = delete;
+    Dict& operator=(const Dict&) = delete;
+};
+
+// Modular arithmetic in GF(2^31-1) shared by host table construction (and mirrored on the device).
+inline uint64_t kr_mul(uint64_t a, uint64_t b) { return (a * b) % kKrP; }
+uint64_t kr_pow(uint64_t a, uint64_t e);
+uint64_t kr_inv(uint64_t a);
+uint64_t kr_fp(const uint8_t* s, size_t n, uint64_t r);  // sum s[i] r^i mod p, unsigned bytes
+uint64_t splitmix64(uint64_t x);
+
+}  // namespace pm

@@ -1,0 +1,426 @@
+// engine.cu -- the C-ABI of libpm_b200.so (include/pm_b200.h): dictionary objects, the device-resident
+// engine, scan dispatch, the host-buffer pipeline.  No CPU fallback anywhere: every scan entry point
+// needs a CUDA device and fails loudly without one.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/pm_b200.h"
+#include "aux_kernels.cuh"
+#include "dfa_scan.cuh"
+#include "dict.hpp"
+#include "kr_scan.cuh"
+#include "pm_dev.cuh"
+#include "sfx_scan.cuh"
+
+namespace {
+thread_local std::string g_err;
+int fail(const std::string& m) { g_err = m; return -1; }
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return -1;
+}
+#define CU(call)                                         \
+    do {                                                 \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+}  // namespace
+
+struct pm_dict {
+    pm::Dict d;
+};
+
+namespace {
+template <class T>
+cudaError_t upload(const std::vector<T>& v, T** dptr, size_t* total) {
+    *dptr = nullptr;
+    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dptr), bytes);
+    if (e != cudaSuccess) return e;
+    *total += bytes;
+    if (!v.empty()) e = cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+constexpr size_t kHostChunk = size_t(16) << 20;  // bytes per pipeline slot of pm_engine_scan_host
+}  // namespace
+
+struct pm_engine {
+    const pm::Dict* dict = nullptr;
+    pm_dict* dict_owner = nullptr;
+    int device = 0, n_sms = 0;
+    size_t table_bytes = 0;
+    uint64_t launches = 0;
+    // sfx tables
+    uint16_t* d_root2 = nullptr;
+    uint32_t *d_root1 = nullptr, *d_rows = nullptr, *d_row_best = nullptr;
+    uint8_t* d_cls = nullptr;
+    // pattern tables
+    uint32_t *d_pat_off = nullptr, *d_pat_len = nullptr;
+    uint8_t* d_pat_bytes = nullptr;
+    uint16_t *d_parent = nullptr, *d_chain = nullptr;
+    uint64_t* d_pidhash = nullptr;
+    pm::PatTables pt{};
+    // dfa tables (lazy)
+    uint32_t* d_delta = nullptr;
+    uint16_t* d_longest = nullptr;
+    uint8_t* d_dfa_cls = nullptr;
+    bool dfa_ready = false;
+    // kr tables (lazy)
+    pm::KrDevTables kr{};
+    bool kr_ready = false;
+    uint64_t kr_seed = 0xF1A90003ull;
+    // scratch
+    unsigned long long* d_acc = nullptr;  // 8 x u64
+    // host pipeline (lazy)
+    bool pipe_ready = false;
+    uint8_t* d_in[2] = {nullptr, nullptr};
+    uint16_t* d_out[2] = {nullptr, nullptr};
+    uint8_t* h_in[2] = {nullptr, nullptr};
+    uint16_t* h_out[2] = {nullptr, nullptr};
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    // stream state carried between pm_engine_scan_host calls (== ac->current_state of the reference)
+    uint8_t h_hist[pm::kHalo];
+    size_t hist_valid = 0;
+};
+
+namespace {
+
+int ensure_dfa(pm_engine* e) {
+    if (e->dfa_ready) return 0;
+    pm::Dict* d = const_cast<pm::Dict*>(e->dict);
+    d->build_dfa();
+    CU(upload(d->dfa.delta, &e->d_delta, &e->table_bytes));
+    CU(upload(d->dfa.longest, &e->d_longest, &e->table_bytes));
+    std::vector<uint8_t> cls(d->dfa.cls, d->dfa.cls + 256);
+    CU(upload(cls, &e->d_dfa_cls, &e->table_bytes));
+    e->dfa_ready = true;
+    return 0;
+}
+
+int ensure_kr(pm_engine* e) {
+    if (e->kr_ready && e->dict->kr.seed == e->kr_seed) return 0;
+    pm::Dict* d = const_cast<pm::Dict*>(e->dict);
+    d->build_kr(e->kr_seed);
+    pm::kr_free_tables(&e->kr);
+    size_t bytes = 0;
+    cudaError_t ce = pm::kr_upload_tables(*d, &e->kr, &bytes);
+    if (ce != cudaSuccess) return cuda_fail(ce, "kr_upload_tables");
+    e->table_bytes += bytes;
+    e->kr_ready = true;
+    return 0;
+}
+
+int ensure_pipe(pm_engine* e) {
+    if (e->pipe_ready) return 0;
+    for (int b = 0; b < 2; ++b) {
+        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_in[b]), pm::kHalo + kHostChunk + 16));
+        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_out[b]), kHostChunk * sizeof(uint16_t)));
+        CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_in[b]), pm::kHalo + kHostChunk));
+        CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_out[b]), kHostChunk * sizeof(uint16_t)));
+        CU(cudaStreamCreateWithFlags(&e->st[b], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&e->done[b], cudaEventDisableTiming));
+    }
+    e->pipe_ready = true;
+    return 0;
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid, uint16_t* d_out,
+                     cudaStream_t st) {
+    if (n == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(d_stream) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
+        return fail("pm_engine_scan_device: d_stream and d_out must be 16-byte aligned");
+    const pm::Dict& d = *e->dict;
+    if (algo == PM_ALGO_SFX) {
+        pm::SfxParams p{};
+        p.stream = d_stream; p.n = n; p.hist_valid = hist_valid; p.out = d_out;
+        p.root2 = e->d_root2; p.root1 = e->d_root1; p.rows = e->d_rows; p.row_best = e->d_row_best; p.cls = e->d_cls;
+        p.cont_base = d.sfx.cont_base; p.row2_base = d.sfx.row2_base; p.log2_ncp = d.sfx.log2_ncp;
+        const bool ident = d.sfx.n_classes == 256;
+        cudaError_t ce = pm::sfx_scan_launch(p, ident, e->n_sms, d.max_len, st, &e->launches);
+        if (ce != cudaSuccess) return cuda_fail(ce, "sfx_scan_launch");
+        return 0;
+    }
+    if (algo == PM_ALGO_DFA) {
+        if (ensure_dfa(e)) return -1;
+        pm::DfaParams p{};
+        p.stream = d_stream; p.n = n; p.hist_valid = hist_valid; p.out = d_out;
+        p.delta = e->d_delta; p.longest = e->d_longest; p.cls = e->d_dfa_cls; p.log2_ncp = d.dfa.log2_ncp;
+        p.warm = d.max_len ? d.max_len - 1 : 0;
+        cudaError_t ce = pm::dfa_scan_launch(p, st, &e->launches);
+        if (ce != cudaSuccess) return cuda_fail(ce, "dfa_scan_launch");
+        return 0;
+    }
+    if (algo == PM_ALGO_KR) {
+        if (ensure_kr(e)) return -1;
+        // exact part (patterns <= 8 bytes, bgps.c:459-464) comes from the exact scan restricted by length,
+        // the fingerprint part from the KR kernel; see kr_scan.cu
+        pm::SfxParams p{};
+        p.stream = d_stream; p.n = n; p.hist_valid = hist_valid; p.out = d_out;
+        p.root2 = e->d_root2; p.root1 = e->d_root1; p.rows = e->d_rows; p.row_best = e->d_row_best; p.cls = e->d_cls;
+        p.cont_base = d.sfx.cont_base; p.row2_base = d.sfx.row2_base; p.log2_ncp = d.sfx.log2_ncp;
+        cudaError_t ce = pm::sfx_scan_launch(p, d.sfx.n_classes == 256, e->n_sms, d.max_len, st, &e->launches);
+        if (ce != cudaSuccess) return cuda_fail(ce, "sfx_scan_launch");
+        ce = pm::kr_scan_launch(e->kr, d_stream, n, hist_valid, d_out, e->pt, e->n_sms, st, &e->launches);
+        if (ce != cudaSuccess) return cuda_fail(ce, "kr_scan_launch");
+        return 0;
+    }
+    return fail("unknown algorithm id");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pm_last_error(void) { return g_err.c_str(); }
+int pm_version(void) { return 1; }
+
+pm_dict* pm_dict_create(void) { return new (std::nothrow) pm_dict(); }
+void pm_dict_free(pm_dict* d) { delete d; }
+int pm_parse_pattern_line(const uint8_t* line, size_t n, uint8_t* out, size_t* out_len) {
+    return pm::Dict::parse_line(line, n, out, out_len) ? 1 : 0;
+}
+int pm_dict_add_file(pm_dict* d, const char* path) {
+    if (d->d.compiled) return fail("dictionary already compiled");
+    if (d->d.add_file(path)) return fail(d->d.error);
+    return 0;
+}
+int pm_dict_add_mem(pm_dict* d, const uint8_t* data, size_t n) {
+    if (d->d.compiled) return fail("dictionary already compiled");
+    return d->d.add_mem(data, n);
+}
+uint32_t pm_dict_add_pattern(pm_dict* d, const uint8_t* pat, size_t len, uint32_t file, uint32_t line, uint64_t user_id) {
+    return d->d.add_pattern(pat, len, file, line, user_id);
+}
+int pm_dict_compile(pm_dict* d) {
+    if (d->d.max_len > pm::kMaxPatLen) return fail("pattern longer than the supported maximum (353 bytes)");
+    if (d->d.compile()) return fail(d->d.error);
+    if (!d->d.sfx.fits_u16) return fail("dictionary too large for dense uint16 results (needs P + #2-byte-continuations < 65536)");
+    return 0;
+}
+int pm_dict_get_info(const pm_dict* d, pm_dict_info* info) {
+    const pm::Dict& x = d->d;
+    memset(info, 0, sizeof(*info));
+    info->n_lines = x.n_lines; info->n_rejected = x.n_rejected; info->n_duplicates = x.n_dups;
+    info->n_patterns = uint32_t(x.pats.size()); info->max_pat_len = x.max_len; info->total_pat_bytes = x.bytes.size();
+    info->n_ac_states = x.n_ac_states; info->n_sfx_nodes = x.sfx.n_nodes; info->n_sfx_rows = x.sfx.n_rows;
+    info->n_classes = x.sfx.n_classes; info->n_hot2_cont = x.sfx.n2_cont;
+    info->table_bytes = x.sfx.root2.size() * 2 + x.sfx.rows.size() * 4 + x.sfx.row_best.size() * 4 + x.sfx.root1.size() * 4;
+    return 0;
+}
+int pm_dict_pattern(const pm_dict* d, uint32_t pid, uint32_t* file, uint32_t* line, uint64_t* user_id,
+                    uint32_t* parent_pid, uint32_t* len, const uint8_t** bytes) {
+    if (pid == 0 || pid > d->d.pats.size()) return fail("pid out of range");
+    const pm::Pattern& p = d->d.pats[pid - 1];
+    if (file) *file = p.file;
+    if (line) *line = p.line;
+    if (user_id) *user_id = p.user;
+    if (parent_pid) *parent_pid = p.parent;
+    if (len) *len = p.len;
+    if (bytes) *bytes = d->d.bytes.data() + p.off;
+    return 0;
+}
+int pm_dict_is_pattern_suffix(const pm_dict* d, uint32_t first_pid, uint32_t second_pid) {
+    return d->d.is_pattern_suffix(first_pid, second_pid) ? 1 : 0;
+}
+
+pm_engine* pm_engine_create(const pm_dict* dd, int device) {
+    if (!dd || !dd->d.compiled) { fail("pm_engine_create: dictionary is not compiled"); return nullptr; }
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0) {
+        g_err = std::string("pm_engine_create: no CUDA device (") + cudaGetErrorString(ce) + "); this engine has no CPU fallback";
+        return nullptr;
+    }
+    if ((ce = cudaSetDevice(device)) != cudaSuccess) { cuda_fail(ce, "cudaSetDevice"); return nullptr; }
+    pm_engine* e = new (std::nothrow) pm_engine();
+    if (!e) return nullptr;
+    e->dict = &dd->d;
+    e->device = device;
+    cudaDeviceGetAttribute(&e->n_sms, cudaDevAttrMultiProcessorCount, device);
+    const pm::Dict& d = dd->d;
+    auto up = [&](auto& vec, auto** ptr) -> bool {
+        cudaError_t r = upload(vec, ptr, &e->table_bytes);
+        if (r != cudaSuccess) { cuda_fail(r, "table upload"); return false; }
+        return true;
+    };
+    std::vector<uint8_t> cls(d.sfx.cls, d.sfx.cls + 256);
+    const size_t P = d.pats.size();
+    std::vector<uint32_t> off(P), len(P);
+    std::vector<uint16_t> parent(P + 1, 0), chain(P + 1, 0);
+    std::vector<uint64_t> pidhash(P + 1, 0);
+    for (size_t i = 0; i < P; ++i) {
+        off[i] = uint32_t(d.pats[i].off); len[i] = d.pats[i].len;
+        parent[i + 1] = uint16_t(d.pats[i].parent); chain[i + 1] = uint16_t(d.pats[i].chain);
+        pidhash[i + 1] = pm::splitmix64(((uint64_t(d.pats[i].file) + 1) << 32) | d.pats[i].line);
+    }
+    bool ok = up(d.sfx.root2, &e->d_root2) && up(d.sfx.root1, &e->d_root1) && up(d.sfx.rows, &e->d_rows) &&
+              up(d.sfx.row_best, &e->d_row_best) && up(cls, &e->d_cls) && up(off, &e->d_pat_off) &&
+              up(len, &e->d_pat_len) && up(d.bytes, &e->d_pat_bytes) && up(parent, &e->d_parent) &&
+              up(chain, &e->d_chain) && up(pidhash, &e->d_pidhash);
+    if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_acc), 8 * sizeof(unsigned long long)) != cudaSuccess) ok = false;
+    if (!ok) { pm_engine_free(e); return nullptr; }
+    e->pt.n_patterns = uint32_t(P);
+    e->pt.off = e->d_pat_off; e->pt.len = e->d_pat_len; e->pt.bytes = e->d_pat_bytes;
+    e->pt.parent = e->d_parent; e->pt.chain = e->d_chain; e->pt.pidhash = e->d_pidhash;
+    memset(e->h_hist, 0, sizeof(e->h_hist));
+    return e;
+}
+
+void pm_engine_free(pm_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    void* ptrs[] = {e->d_root2, e->d_root1, e->d_rows, e->d_row_best, e->d_cls, e->d_pat_off, e->d_pat_len, e->d_pat_bytes,
+                    e->d_parent, e->d_chain, e->d_pidhash, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_acc,
+                    e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1]};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    pm::kr_free_tables(&e->kr);
+    for (int b = 0; b < 2; ++b) {
+        if (e->h_in[b]) cudaFreeHost(e->h_in[b]);
+        if (e->h_out[b]) cudaFreeHost(e->h_out[b]);
+        if (e->st[b]) cudaStreamDestroy(e->st[b]);
+        if (e->done[b]) cudaEventDestroy(e->done[b]);
+    }
+    delete e;
+}
+
+size_t pm_engine_total_mem(const pm_engine* e) { return e ? e->table_bytes : 0; }
+uint64_t pm_engine_launch_count(const pm_engine* e) { return e ? e->launches : 0; }
+int pm_engine_set_kr_seed(pm_engine* e, uint64_t seed) {
+    e->kr_seed = seed;
+    return 0;
+}
+
+int pm_engine_scan_device(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid,
+                          uint16_t* d_out, void* cuda_stream) {
+    CU(cudaSetDevice(e->device));
+    return scan_device_impl(e, algo, d_stream, n, hist_valid, d_out, static_cast<cudaStream_t>(cuda_stream));
+}
+
+void pm_engine_reset(pm_engine* e) {
+    e->hist_valid = 0;
+    memset(e->h_hist, 0, sizeof(e->h_hist));
+}
+
+int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n, uint16_t* out) {
+    CU(cudaSetDevice(e->device));
+    if (ensure_pipe(e)) return -1;
+    if (algo == PM_ALGO_DFA && ensure_dfa(e)) return -1;
+    if (algo == PM_ALGO_KR && ensure_kr(e)) return -1;
+    const bool in_pinned = is_pinned(stream), out_pinned = is_pinned(out);
+    const size_t n_chunks = (n + kHostChunk - 1) / kHostChunk;
+    auto drain = [&](size_t k) -> int {  // chunk k has fully left the device
+        const int b = int(k & 1);
+        CU(cudaEventSynchronize(e->done[b]));
+        if (!out_pinned) {
+            const size_t o = k * kHostChunk, len = std::min(kHostChunk, n - o);
+            memcpy(out + o, e->h_out[b], len * sizeof(uint16_t));
+        }
+        return 0;
+    };
+    for (size_t k = 0; k < n_chunks; ++k) {
+        const int b = int(k & 1);
+        if (k >= 2 && drain(k - 2)) return -1;
+        const size_t o = k * kHostChunk, len = std::min(kHostChunk, n - o);
+        // history in front of the chunk: from this call's own bytes when there are enough, else carried
+        const size_t from_call = std::min<size_t>(o, pm::kHalo);
+        const size_t hist_total = std::min<size_t>(e->hist_valid + o, pm::kHalo);  // valid history bytes
+        uint8_t* din = e->d_in[b];
+        if (from_call < size_t(pm::kHalo)) {
+            // [carried tail][bytes of this call before o]: carried part sits at the front of the halo
+            const size_t carried = pm::kHalo - from_call;
+            CU(cudaMemcpyAsync(din, e->h_hist + from_call, carried, cudaMemcpyHostToDevice, e->st[b]));
+        }
+        if (in_pinned) {
+            CU(cudaMemcpyAsync(din + pm::kHalo - from_call, stream + o - from_call, from_call + len, cudaMemcpyHostToDevice, e->st[b]));
+        } else {
+            memcpy(e->h_in[b], stream + o - from_call, from_call + len);
+            CU(cudaMemcpyAsync(din + pm::kHalo - from_call, e->h_in[b], from_call + len, cudaMemcpyHostToDevice, e->st[b]));
+        }
+        if (scan_device_impl(e, algo, din + pm::kHalo, len, hist_total, e->d_out[b], e->st[b])) return -1;
+        CU(cudaMemcpyAsync(out_pinned ? out + o : e->h_out[b], e->d_out[b], len * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->st[b]));
+        CU(cudaEventRecord(e->done[b], e->st[b]));
+    }
+    for (size_t k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; ++k)
+        if (drain(k)) return -1;
+    // carry the last kHalo bytes: h_hist always holds the most recent bytes right-aligned
+    if (n >= size_t(pm::kHalo)) {
+        memcpy(e->h_hist, stream + n - pm::kHalo, pm::kHalo);
+    } else if (n) {
+        memmove(e->h_hist, e->h_hist + n, pm::kHalo - n);
+        memcpy(e->h_hist + pm::kHalo - n, stream, n);
+    }
+    e->hist_valid += n;
+    return 0;
+}
+
+int pm_engine_summarize(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t pos_base, uint64_t out4[4], void* cuda_stream) {
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    cudaError_t ce = pm::summarize_launch(d_out, n, pos_base, e->pt, e->d_acc, e->n_sms, st, &e->launches);
+    if (ce != cudaSuccess) return cuda_fail(ce, "summarize_launch");
+    unsigned long long h[4];
+    CU(cudaMemcpyAsync(h, e->d_acc, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int k = 0; k < 4; ++k) out4[k] = h[k];
+    return 0;
+}
+
+int pm_engine_compact(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t pos_base, int expand_ancestors,
+                      uint64_t* d_records, size_t cap, uint64_t* n_records, void* cuda_stream) {
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    unsigned long long* d_counts = nullptr;
+    CU(cudaMalloc(reinterpret_cast<void**>(&d_counts), (pm::compact_blocks(n) + 1) * sizeof(unsigned long long)));
+    cudaError_t ce = pm::compact_launch(d_out, n, pos_base, expand_ancestors != 0, e->pt, d_counts, e->d_acc + 4,
+                                        reinterpret_cast<unsigned long long*>(d_records), cap, st, &e->launches);
+    unsigned long long total = 0;
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(&total, e->d_acc + 4, sizeof(total), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(d_counts);
+    if (ce != cudaSuccess) return cuda_fail(ce, "compact");
+    *n_records = total;
+    return 0;
+}
+
+int pm_engine_generate(pm_engine* e, int kind, uint64_t off, size_t n, uint8_t* d_dst, void* cuda_stream) {
+    CU(cudaSetDevice(e->device));
+    if ((off & 4095) || (n & 4095)) return fail("pm_engine_generate: off and n must be multiples of 4096");
+    cudaError_t ce = pm::generate_launch(kind, off, n, d_dst, e->pt, static_cast<cudaStream_t>(cuda_stream), &e->launches);
+    if (ce != cudaSuccess) return cuda_fail(ce, "generate_launch");
+    return 0;
+}
+
+int pm_engine_time_scan(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid, uint16_t* d_out,
+                        int iters, float* ms_per_scan, void* cuda_stream) {
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    CU(cudaEventRecord(a, st));
+    for (int i = 0; i < iters; ++i)
+        if (scan_device_impl(e, algo, d_stream, n, hist_valid, d_out, st)) return -1;
+    CU(cudaEventRecord(b, st));
+    CU(cudaEventSynchronize(b));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *ms_per_scan = ms / float(iters > 0 ? iters : 1);
+    return 0;
+}
+
+}  // extern "C"

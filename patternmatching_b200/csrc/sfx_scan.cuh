@@ -1,0 +1,31 @@
+// sfx_scan.cuh -- launch interface of the exact backward suffix-trie scan (sfx_scan.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pm {
+
+constexpr int kSfxThreads = 1024;
+constexpr int kSfxPosPerThread = 16;
+constexpr int kSfxTile = kSfxThreads * kSfxPosPerThread;  // 16 KiB of stream per CTA iteration
+
+struct SfxParams {
+    const uint8_t* stream;    // device, 16-byte aligned; first reported byte
+    uint64_t n;               // bytes to report on
+    uint64_t hist_valid;      // readable bytes of the same stream directly before `stream`
+    uint16_t* out;            // device, 16-byte aligned, n entries
+    const uint16_t* root2;    // 65,536 entries
+    const uint32_t* root1;    // 256 entries
+    const uint32_t* rows;     // n_rows << log2_ncp entries
+    const uint32_t* row_best; // n_rows entries
+    const uint8_t* cls;       // 256 entries (device)
+    uint32_t cont_base, row2_base, log2_ncp;
+    uint32_t n_tiles;         // filled by the launcher
+};
+
+size_t sfx_smem_bytes();
+// Launches the scan (+ the start-of-stream fix-up when hist_valid < max_pat_len-1) on `st`.
+cudaError_t sfx_scan_launch(const SfxParams& p, bool ident_cls, int n_sms, uint32_t max_pat_len, cudaStream_t st,
+                            uint64_t* launches);
+
+}  // namespace pm
