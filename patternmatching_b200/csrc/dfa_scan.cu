@@ -22,18 +22,19 @@ __global__ void __launch_bounds__(kThreads) dfa_scan_kernel(const DfaParams p) {
     const uint64_t s0 = seg * uint64_t(kDfaSeg);
     if (s0 >= p.n) return;
     const uint64_t s1 = min(p.n, s0 + uint64_t(kDfaSeg));
-    // warm-up start, 16-byte aligned, never before the readable history
-    int64_t w = (int64_t(s0) - int64_t(p.warm)) & ~int64_t(15);
-    const int64_t lo = -int64_t(p.hist_valid & ~uint64_t(15));
-    if (w < lo) w = lo;
+    // warm-up start: max_pat_len-1 bytes back, never before the readable history
+    int64_t w = int64_t(s0) - int64_t(p.warm);
+    if (w < -int64_t(p.hist_valid)) w = -int64_t(p.hist_valid);
     const uint8_t* __restrict__ cls = p.cls;
     const uint32_t* __restrict__ delta = p.delta;
     const uint16_t* __restrict__ longest = p.longest;
     const uint32_t l2 = p.log2_ncp;
     uint32_t s = 0;
-    // warm-up: walk, do not report
-    for (int64_t q = w; q < int64_t(s0); q += 16) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.stream + q));
+    // warm-up: walk, do not report (byte steps up to a 16-byte boundary, then vector loads)
+    int64_t q0 = w;
+    for (; q0 < int64_t(s0) && (q0 & 15); ++q0) s = __ldg(delta + ((size_t(s) << l2) | __ldg(cls + *(p.stream + q0))));
+    for (; q0 < int64_t(s0); q0 += 16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.stream + q0));
         const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int k = 0; k < 16; ++k) {

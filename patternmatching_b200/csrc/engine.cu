@@ -77,6 +77,10 @@ struct pm_engine {
     uint64_t kr_seed = 0xF1A90003ull;
     // scratch
     unsigned long long* d_acc = nullptr;  // 8 x u64
+    // deferred-walk queues of the sfx scan, one per pipeline slot (slot 0 also serves pm_engine_scan_device)
+    uint64_t* d_queue[2] = {nullptr, nullptr};
+    uint32_t* d_qcount = nullptr;         // 2 counters
+    size_t queue_cap[2] = {0, 0};
     // host pipeline (lazy)
     bool pipe_ready = false;
     uint8_t* d_in[2] = {nullptr, nullptr};
@@ -137,8 +141,26 @@ bool is_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
+int fill_sfx_params(pm_engine* e, pm::SfxParams* p, size_t n, int slot) {
+    const pm::Dict& d = *e->dict;
+    p->root2 = e->d_root2; p->root1 = e->d_root1; p->rows = e->d_rows; p->row_best = e->d_row_best; p->cls = e->d_cls;
+    p->cont_base = d.sfx.cont_base; p->row2_base = d.sfx.row2_base; p->log2_ncp = d.sfx.log2_ncp;
+    // queue for walks deeper than 3 levels: sized for 1/64 of the positions (random bytes need ~1/1000);
+    // if it ever fills up the kernel finishes the excess walks inline
+    size_t want = std::min<size_t>(n / 64 + 65536, size_t(1) << 30);
+    if (d.sfx.n_rows >= (1u << 24)) want = 0;
+    if (want > e->queue_cap[slot]) {
+        if (e->d_queue[slot]) CU(cudaFree(e->d_queue[slot]));
+        e->d_queue[slot] = nullptr; e->queue_cap[slot] = 0;
+        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_queue[slot]), want * sizeof(uint64_t)));
+        e->queue_cap[slot] = want;
+    }
+    p->queue = e->d_queue[slot]; p->qcount = e->d_qcount + slot; p->qcap = uint32_t(want ? e->queue_cap[slot] : 0);
+    return 0;
+}
+
 int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid, uint16_t* d_out,
-                     cudaStream_t st) {
+                     cudaStream_t st, int slot = 0) {
     if (n == 0) return 0;
     if ((reinterpret_cast<uintptr_t>(d_stream) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
         return fail("pm_engine_scan_device: d_stream and d_out must be 16-byte aligned");
@@ -146,8 +168,7 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
     if (algo == PM_ALGO_SFX) {
         pm::SfxParams p{};
         p.stream = d_stream; p.n = n; p.hist_valid = hist_valid; p.out = d_out;
-        p.root2 = e->d_root2; p.root1 = e->d_root1; p.rows = e->d_rows; p.row_best = e->d_row_best; p.cls = e->d_cls;
-        p.cont_base = d.sfx.cont_base; p.row2_base = d.sfx.row2_base; p.log2_ncp = d.sfx.log2_ncp;
+        if (fill_sfx_params(e, &p, n, slot)) return -1;
         const bool ident = d.sfx.n_classes == 256;
         cudaError_t ce = pm::sfx_scan_launch(p, ident, e->n_sms, d.max_len, st, &e->launches);
         if (ce != cudaSuccess) return cuda_fail(ce, "sfx_scan_launch");
@@ -169,8 +190,7 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
         // the fingerprint part from the KR kernel; see kr_scan.cu
         pm::SfxParams p{};
         p.stream = d_stream; p.n = n; p.hist_valid = hist_valid; p.out = d_out;
-        p.root2 = e->d_root2; p.root1 = e->d_root1; p.rows = e->d_rows; p.row_best = e->d_row_best; p.cls = e->d_cls;
-        p.cont_base = d.sfx.cont_base; p.row2_base = d.sfx.row2_base; p.log2_ncp = d.sfx.log2_ncp;
+        if (fill_sfx_params(e, &p, n, slot)) return -1;
         cudaError_t ce = pm::sfx_scan_launch(p, d.sfx.n_classes == 256, e->n_sms, d.max_len, st, &e->launches);
         if (ce != cudaSuccess) return cuda_fail(ce, "sfx_scan_launch");
         ce = pm::kr_scan_launch(e->kr, d_stream, n, hist_valid, d_out, e->pt, e->n_sms, st, &e->launches);
@@ -271,6 +291,7 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
               up(len, &e->d_pat_len) && up(d.bytes, &e->d_pat_bytes) && up(parent, &e->d_parent) &&
               up(chain, &e->d_chain) && up(pidhash, &e->d_pidhash);
     if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_acc), 8 * sizeof(unsigned long long)) != cudaSuccess) ok = false;
+    if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_qcount), 2 * sizeof(uint32_t)) != cudaSuccess) ok = false;
     if (!ok) { pm_engine_free(e); return nullptr; }
     e->pt.n_patterns = uint32_t(P);
     e->pt.off = e->d_pat_off; e->pt.len = e->d_pat_len; e->pt.bytes = e->d_pat_bytes;
@@ -284,7 +305,7 @@ void pm_engine_free(pm_engine* e) {
     cudaSetDevice(e->device);
     void* ptrs[] = {e->d_root2, e->d_root1, e->d_rows, e->d_row_best, e->d_cls, e->d_pat_off, e->d_pat_len, e->d_pat_bytes,
                     e->d_parent, e->d_chain, e->d_pidhash, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_acc,
-                    e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1]};
+                    e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1], e->d_queue[0], e->d_queue[1], e->d_qcount};
     for (void* p : ptrs) if (p) cudaFree(p);
     pm::kr_free_tables(&e->kr);
     for (int b = 0; b < 2; ++b) {
@@ -349,7 +370,7 @@ int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n,
             memcpy(e->h_in[b], stream + o - from_call, from_call + len);
             CU(cudaMemcpyAsync(din + pm::kHalo - from_call, e->h_in[b], from_call + len, cudaMemcpyHostToDevice, e->st[b]));
         }
-        if (scan_device_impl(e, algo, din + pm::kHalo, len, hist_total, e->d_out[b], e->st[b])) return -1;
+        if (scan_device_impl(e, algo, din + pm::kHalo, len, hist_total, e->d_out[b], e->st[b], b)) return -1;
         CU(cudaMemcpyAsync(out_pinned ? out + o : e->h_out[b], e->d_out[b], len * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->st[b]));
         CU(cudaEventRecord(e->done[b], e->st[b]));
     }

@@ -8,12 +8,15 @@
 // c[i], c[i-1], c[i-2], ... in the trie of REVERSED patterns.  The host compiler (dict.cpp) has
 // flattened that trie so that every table entry is either the final answer or "continue at row r":
 //   level 1+2 : root2[c[i] << 8 | c[i-1]]   65,536 x u16 = 128 KiB, resident in SHARED memory
-//   level >=3 : rows[row << log2_ncp | cls(c[i-k])]   u32, global memory (hot part L2-resident)
-// All positions are independent, so there is no per-thread warm-up: a CTA stages one 16 KiB tile
-// plus a 352-byte left halo (>= max_pat_len-1) with ONE bulk async copy (TMA engine,
-// SASS UBLKCP), double buffered behind an mbarrier; every thread resolves 16 consecutive
-// positions (16 shared-memory gathers, ~10% of them followed by one L2 lookup), results are packed
-// in shared memory and leave with one bulk async store per tile.
+//   level 3   : rows[row << log2_ncp | cls(c[i-2])]   u32, global memory (6.9 MB, L2-resident)
+//   level >=4 : same rows; ~1e-3 of the positions on random bytes -- DEFERRED to a work queue and
+//               finished by sfx_deep_kernel so that a long dependent chain never stalls a warp
+// All positions are independent, so there is no per-thread warm-up.  Every WARP runs its own
+// software pipeline: lane 0 stages 1 KiB tiles plus a 352-byte left halo (>= max_pat_len-1,
+// SURVEY Q8) with bulk async copies (TMA engine, SASS UBLKCP) into a private double buffer behind
+// private mbarriers; there is no CTA-wide barrier after start-up, so warps hide each other's L2
+// latency.  A lane resolves 2 x 8 consecutive positions per 512-byte visit, arranged so that the
+// 16-byte result stores of a warp are fully coalesced.
 #include "pm_dev.cuh"
 #include "sfx_scan.cuh"
 
@@ -22,36 +25,38 @@ namespace pm {
 namespace {
 
 constexpr int kThreads = kSfxThreads;
-constexpr int kPos = kSfxPosPerThread;          // positions per thread per tile
-constexpr int kTile = kSfxTile;                 // bytes per tile
-constexpr int kTileBuf = kHalo + kTile;         // staged bytes per buffer
+constexpr int kWarps = kThreads / 32;
+constexpr int kTile = kSfxTile;                  // bytes per warp tile
+constexpr int kVisits = kTile / 512;             // 512 positions per warp visit
+constexpr int kStages = kSfxStages;
+constexpr int kStageBuf = kHalo + kTile;         // staged bytes per stage
 constexpr uint32_t kCont = 0x80000000u;
+constexpr uint32_t kQueueChunk = 256;                 // queue slots a warp reserves with one atomic
+constexpr uint64_t kQueueInvalid = ~0ull;             // padding of a partly used chunk
 
 // shared memory carve-up (bytes)
-constexpr int kOffRoot2 = 0;                           // 131072
-constexpr int kOffTile0 = 131072;
-constexpr int kOffTile1 = kOffTile0 + kTileBuf;
-constexpr int kOffOut = kOffTile1 + kTileBuf;          // kTile * 2
-constexpr int kOffCls = kOffOut + kTile * 2;           // 256
-constexpr int kOffBar = kOffCls + 256;                 // 2 x 8
-constexpr int kSmemBytes = kOffBar + 16;
-static_assert(kOffTile1 % 16 == 0 && kOffOut % 16 == 0 && kOffBar % 8 == 0, "alignment");
+constexpr int kOffRoot2 = 0;                     // 131072
+constexpr int kOffCls = 131072;                  // 256
+constexpr int kOffBar = kOffCls + 256;           // kWarps * kStages * 8
+constexpr int kOffStages = kOffBar + kWarps * kStages * 8;
+constexpr int kSmemBytes = kOffStages + kWarps * kStages * kStageBuf;
+static_assert(kOffStages % 16 == 0 && kStageBuf % 16 == 0, "bulk copies need 16-byte alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert((kStages & (kStages - 1)) == 0, "kStages must be a power of two");
 
-// byte / 16-bit window extraction from the 20-byte register window W = {prev, w.x, w.y, w.z, w.w}
+// byte / 16-bit window extraction from the 12-byte register window W = {c[g-4..g-1], c[g..g+3], c[g+4..g+7]}
 template <int O>
-__device__ __forceinline__ uint32_t win_u8(const uint32_t (&W)[5]) {
+__device__ __forceinline__ uint32_t win_u8(const uint32_t (&W)[3]) {
     return (W[O >> 2] >> (8 * (O & 3))) & 0xFFu;
 }
 template <int O>
-__device__ __forceinline__ uint32_t win_u16(const uint32_t (&W)[5]) {
+__device__ __forceinline__ uint32_t win_u16(const uint32_t (&W)[3]) {
     if constexpr ((O & 3) < 3) return (W[O >> 2] >> (8 * (O & 3))) & 0xFFFFu;
     else return __funnelshift_r(W[O >> 2], W[(O >> 2) + 1], 24) & 0xFFFFu;
 }
 
-// Levels >= 4 (about 1e-3 of the positions on uniform bytes): follow the rows until a final entry.
-// `pb` points at c[i] inside the staged tile; the halo guarantees pb[-k] is staged for every k the
-// trie can ask for (k < max_pat_len <= kHalo + 1).
+// Follow the rows until a final entry (levels >= 4).  `pb` points at c[i] inside a staged tile; the halo
+// guarantees pb[-k] is staged for every k the trie can ask for (k < max_pat_len <= kHalo + 1).
 template <bool kIdentCls>
 __device__ __noinline__ uint32_t sfx_walk_deep(uint32_t v, const uint8_t* pb, int k, const uint32_t* __restrict__ rows,
                                                uint32_t log2_ncp, const uint8_t* s_cls) {
@@ -64,16 +69,44 @@ __device__ __noinline__ uint32_t sfx_walk_deep(uint32_t v, const uint8_t* pb, in
     return v;
 }
 
-template <int J, bool kIdentCls>
-__device__ __forceinline__ void resolve_one(uint32_t (&e)[kPos], const uint32_t (&W)[5], const SfxParams& p,
-                                            const uint8_t* base, const uint8_t* s_cls) {
-    if (e[J] >= p.cont_base) {  // 2-byte suffix continues below the shared-memory table
-        uint32_t c2 = win_u8<2 + J>(W);  // c[i-2]
-        if constexpr (!kIdentCls) c2 = s_cls[c2];
-        uint32_t row = e[J] - p.cont_base + p.row2_base;
-        uint32_t v = __ldg(p.rows + ((size_t(row) << p.log2_ncp) | c2));
-        if (v & kCont) v = sfx_walk_deep<kIdentCls>(v, base + J, 3, p.rows, p.log2_ncp, s_cls);
-        e[J] = v;
+// Levels 1-3 for one group of 8 consecutive positions whose bytes sit in the register window W.
+// Phase A: 8 shared-memory gathers.  Phase B: the ~10% of entries that continue below the 2-byte table
+// fetch their level-3 row entry with PREDICATED loads -- no branch and no use of the loaded value here, so
+// all 16 loads of a visit are in flight together and a warp pays the L2 latency once per visit.
+template <bool kIdentCls>
+__device__ __forceinline__ void lookup_group(const uint16_t* s_root2, const uint32_t (&W)[3], uintptr_t rows_adj,
+                                             uint32_t cont_base, uint32_t log2_ncp, const uint8_t* s_cls, int valid,
+                                             uint32_t (&e)[8]) {
+    e[0] = s_root2[win_u16<3>(W)]; e[1] = s_root2[win_u16<4>(W)];
+    e[2] = s_root2[win_u16<5>(W)]; e[3] = s_root2[win_u16<6>(W)];
+    e[4] = s_root2[win_u16<7>(W)]; e[5] = s_root2[win_u16<8>(W)];
+    e[6] = s_root2[win_u16<9>(W)]; e[7] = s_root2[win_u16<10>(W)];
+    if (valid < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j >= valid) e[j] = 0;  // stale bytes beyond the stream: never looked up
+    }
+    uint32_t c2[8];
+    c2[0] = win_u8<2>(W); c2[1] = win_u8<3>(W); c2[2] = win_u8<4>(W); c2[3] = win_u8<5>(W);
+    c2[4] = win_u8<6>(W); c2[5] = win_u8<7>(W); c2[6] = win_u8<8>(W); c2[7] = win_u8<9>(W);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint32_t c = c2[j];
+        if constexpr (!kIdentCls) c = s_cls[c];
+        // rows_adj = &rows[(row2_base - cont_base) << log2_ncp]: entry e addresses row (e - cont_base + row2_base)
+        const uint32_t* addr = reinterpret_cast<const uint32_t*>(rows_adj + ((uintptr_t((e[j] << log2_ncp) | c)) << 2));
+        if (e[j] >= cont_base) e[j] = __ldg(addr);
+    }
+}
+
+__device__ __forceinline__ void store_group(uint16_t* out, uint64_t gpos, const uint32_t (&e)[8], int valid) {
+    if (valid >= 8) {
+        uint4 r;
+        r.x = e[0] | (e[1] << 16); r.y = e[2] | (e[3] << 16);
+        r.z = e[4] | (e[5] << 16); r.w = e[6] | (e[7] << 16);
+        __stcs(reinterpret_cast<uint4*>(out + gpos), r);  // write-once result: streaming store
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < valid) out[gpos + j] = uint16_t(e[j]);
     }
 }
 
@@ -81,124 +114,170 @@ template <bool kIdentCls>
 __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint16_t* s_root2 = reinterpret_cast<uint16_t*>(smem + kOffRoot2);
-    auto s_tile = [&](int b) -> uint8_t* { return smem + kOffTile0 + b * kTileBuf; };
-    uint16_t* s_out = reinterpret_cast<uint16_t*>(smem + kOffOut);
     uint8_t* s_cls = smem + kOffCls;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
 
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
+    const int lane = tid & 31, warp = tid >> 5;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar) + warp * kStages;
+    uint8_t* wbuf = smem + kOffStages + warp * (kStages * kStageBuf);
     const bool have_halo = p.hist_valid >= uint64_t(kHalo);
+    const uint32_t cont_base = p.cont_base, log2_ncp = p.log2_ncp;
+    const uintptr_t rows_adj = reinterpret_cast<uintptr_t>(p.rows) +
+                               ((uintptr_t(p.row2_base) << log2_ncp) << 2) - ((uintptr_t(cont_base) << log2_ncp) << 2);
 
-    if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
         fence_mbar_init();
     }
-    // zero the halo of buffer 0 (tile 0 without history reads it; the fix-up pass owns those positions)
-    for (int i = tid; i < kHalo / 4; i += kThreads) reinterpret_cast<uint32_t*>(s_tile(0))[i] = 0;
+    // halo of stage 0 zeroed: the very first tile of a stream without history reads it (the fix-up pass
+    // owns the positions that would need real history)
+    for (int i = lane; i < kHalo / 4; i += 32) reinterpret_cast<uint32_t*>(wbuf)[i] = 0;
     if (tid < 256) s_cls[tid] = p.cls[tid];
     fence_proxy_async();
-    __syncthreads();
+    __syncwarp();
 
-    auto issue_tile = [&](uint64_t t, int buf) {  // one elected thread
+    const uint64_t gw = uint64_t(blockIdx.x) * kWarps + warp;   // global warp id
+    const uint64_t G = uint64_t(gridDim.x) * kWarps;
+
+    auto issue_tile = [&](uint64_t t, int s) {  // lane 0 only
         const uint64_t s0 = t * uint64_t(kTile);
         const uint32_t len = uint32_t(min(uint64_t(kTile), p.n - s0));
         const uint32_t body = len & ~15u;
         const bool halo = (t > 0) || have_halo;
         const uint32_t bytes = body + (halo ? kHalo : 0);
-        if (bytes) {
-            mbar_arrive_expect_tx(&bars[buf], bytes);
-            bulk_g2s(s_tile(buf) + (halo ? 0 : kHalo), p.stream + s0 - (halo ? kHalo : 0), bytes, &bars[buf]);
-        } else {
-            mbar_arrive_expect_tx(&bars[buf], 0);
-        }
+        uint8_t* dst = wbuf + s * kStageBuf;
+        mbar_arrive_expect_tx(&bars[s], bytes);
+        if (bytes) bulk_g2s(dst + (halo ? 0 : kHalo), p.stream + s0 - (halo ? kHalo : 0), bytes, &bars[s]);
     };
 
-    uint64_t t = blockIdx.x;
-    if (t < p.n_tiles && tid == 0) issue_tile(t, 0);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            const uint64_t t = gw + uint64_t(s) * G;
+            if (t < p.n_tiles) issue_tile(t, s);
+        }
+    }
 
-    // root2 -> shared memory (once per CTA; 128 KiB of coalesced 16-byte loads, L2 hits after the first CTA)
+    // root2 -> shared memory (once per CTA; coalesced 16-byte loads, L2 hits after the first CTA)
     {
         const int4* src = reinterpret_cast<const int4*>(p.root2);
         int4* dst = reinterpret_cast<int4*>(s_root2);
         for (int i = tid; i < 131072 / 16; i += kThreads) dst[i] = __ldg(src + i);
     }
-    __syncthreads();
+    __syncthreads();  // the only CTA-wide barrier
 
-    for (uint32_t it = 0; t < p.n_tiles; t += gridDim.x, ++it) {
-        const int buf = it & 1;
+    uint32_t q_next = 0, q_end = 0;  // this warp's reserved range of the deferred-walk queue
+    uint32_t it = 0;
+    for (uint64_t t = gw; t < p.n_tiles; t += G, ++it) {
+        const int s = it & (kStages - 1);
         const uint64_t s0 = t * uint64_t(kTile);
         const uint32_t len = uint32_t(min(uint64_t(kTile), p.n - s0));
-        const uint64_t tn = t + gridDim.x;
-        if (tid == 0 && tn < p.n_tiles) issue_tile(tn, buf ^ 1);  // buffer was released by the barriers of it-1
+        uint8_t* stage = wbuf + s * kStageBuf;
         if (len & 15u) {  // ragged end of the stream: the last <16 bytes come in with plain loads
             const uint32_t body = len & ~15u;
-            if (uint32_t(tid) < (len & 15u)) s_tile(buf)[kHalo + body + tid] = p.stream[s0 + body + tid];
-            __syncthreads();
+            if (uint32_t(lane) < (len & 15u)) stage[kHalo + body + lane] = p.stream[s0 + body + lane];
+            __syncwarp();
         }
-        mbar_wait(&bars[buf], (it >> 1) & 1);
+        mbar_wait(&bars[s], (it / kStages) & 1);
 
-        const uint8_t* base = s_tile(buf) + kHalo + tid * kPos;
-        uint32_t e[kPos];
-        const bool active = uint32_t(tid * kPos) < len;
-        // the 20-byte register window {c[p0-4..p0-1], c[p0..p0+15]}; loaded by every thread so that the
-        // shuffle stays warp-convergent (inactive threads of a ragged last tile read stale bytes, unused)
-        uint32_t W[5];
-        {
-            const uint4 w = *reinterpret_cast<const uint4*>(base);
-            W[1] = w.x; W[2] = w.y; W[3] = w.z; W[4] = w.w;
-            W[0] = __shfl_up_sync(0xFFFFFFFFu, w.w, 1);
-            if (lane == 0) W[0] = *reinterpret_cast<const uint32_t*>(base - 4);
-        }
-        if (active) {
-            // phase A: levels 1+2, one shared-memory gather per position
+#pragma unroll 1
+        for (int v = 0; v < kVisits; ++v) {
+            const int base_off = v * 512;
+            if (uint32_t(base_off) >= len) break;
+            const uint8_t* vb = stage + kHalo + base_off;
+            // group A: positions base_off + 8*lane .. +8 ; group B: base_off + 256 + 8*lane .. +8
+            const uint2 a = *reinterpret_cast<const uint2*>(vb + 8 * lane);
+            const uint2 b = *reinterpret_cast<const uint2*>(vb + 256 + 8 * lane);
+            uint32_t WA[3], WB[3];
+            WA[1] = a.x; WA[2] = a.y; WB[1] = b.x; WB[2] = b.y;
+            WA[0] = __shfl_up_sync(0xFFFFFFFFu, a.y, 1);
+            WB[0] = __shfl_up_sync(0xFFFFFFFFu, b.y, 1);
+            const uint32_t a31 = __shfl_sync(0xFFFFFFFFu, a.y, 31);
+            if (lane == 0) {
+                WA[0] = *reinterpret_cast<const uint32_t*>(vb - 4);
+                WB[0] = a31;
+            }
+            const int ga = base_off + 8 * lane, gb = ga + 256;
+            const int va = int(len) - ga, vbn = int(len) - gb;   // positions of each group that exist (>= 8: all)
+            uint32_t ea[8], eb[8];
+            lookup_group<kIdentCls>(s_root2, WA, rows_adj, cont_base, log2_ncp, s_cls, va, ea);
+            lookup_group<kIdentCls>(s_root2, WB, rows_adj, cont_base, log2_ncp, s_cls, vbn, eb);
+            const uint32_t anya = (ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7]) & kCont;
+            const uint32_t anyb = (eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7]) & kCont;
+            if (__any_sync(0xFFFFFFFFu, (anya | anyb) != 0)) {
+                // Some walk of this visit is still alive after level 3 (~40% of the visits on random bytes, one
+                // or two positions each).  Hand those walks to the deep kernel: the warp owns a chunk of queue
+                // slots (one atomicAdd per kQueueChunk items -- a single global counter cannot take one atomic
+                // per item) and fills it in lane order.
+                uint32_t m = 0;
 #pragma unroll
-            for (int j = 0; j < kPos; ++j) e[j] = 0;
-            e[0] = s_root2[win_u16<3>(W)];   e[1] = s_root2[win_u16<4>(W)];
-            e[2] = s_root2[win_u16<5>(W)];   e[3] = s_root2[win_u16<6>(W)];
-            e[4] = s_root2[win_u16<7>(W)];   e[5] = s_root2[win_u16<8>(W)];
-            e[6] = s_root2[win_u16<9>(W)];   e[7] = s_root2[win_u16<10>(W)];
-            e[8] = s_root2[win_u16<11>(W)];  e[9] = s_root2[win_u16<12>(W)];
-            e[10] = s_root2[win_u16<13>(W)]; e[11] = s_root2[win_u16<14>(W)];
-            e[12] = s_root2[win_u16<15>(W)]; e[13] = s_root2[win_u16<16>(W)];
-            e[14] = s_root2[win_u16<17>(W)]; e[15] = s_root2[win_u16<18>(W)];
-            // phase B/C: level 3 from L2 (predicated, independent loads), deeper levels rarely
-            resolve_one<0, kIdentCls>(e, W, p, base, s_cls);   resolve_one<1, kIdentCls>(e, W, p, base, s_cls);
-            resolve_one<2, kIdentCls>(e, W, p, base, s_cls);   resolve_one<3, kIdentCls>(e, W, p, base, s_cls);
-            resolve_one<4, kIdentCls>(e, W, p, base, s_cls);   resolve_one<5, kIdentCls>(e, W, p, base, s_cls);
-            resolve_one<6, kIdentCls>(e, W, p, base, s_cls);   resolve_one<7, kIdentCls>(e, W, p, base, s_cls);
-            resolve_one<8, kIdentCls>(e, W, p, base, s_cls);   resolve_one<9, kIdentCls>(e, W, p, base, s_cls);
-            resolve_one<10, kIdentCls>(e, W, p, base, s_cls);  resolve_one<11, kIdentCls>(e, W, p, base, s_cls);
-            resolve_one<12, kIdentCls>(e, W, p, base, s_cls);  resolve_one<13, kIdentCls>(e, W, p, base, s_cls);
-            resolve_one<14, kIdentCls>(e, W, p, base, s_cls);  resolve_one<15, kIdentCls>(e, W, p, base, s_cls);
+                for (int j = 0; j < 8; ++j) m |= ((ea[j] >> 31) << j) | ((eb[j] >> 31) << (8 + j));
+                const uint32_t cnt = __popc(m);
+                uint32_t inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if (lane >= o) inc += y;
+                }
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                if (q_next + total > q_end) {
+                    for (uint32_t i = q_next + lane; i < q_end && i < p.qcap; i += 32) p.queue[i] = kQueueInvalid;
+                    const uint32_t need = total > kQueueChunk ? total : kQueueChunk;
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(p.qcount, need);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    q_next = base;
+                    q_end = base + need;
+                }
+                uint32_t my = q_next + inc - cnt;
+                q_next += total;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (ea[j] & kCont) {
+                        if (my < p.qcap) { p.queue[my] = ((s0 + ga + j) << 24) | (ea[j] & 0xFFFFFFu); ea[j] = 0; }
+                        else ea[j] = sfx_walk_deep<kIdentCls>(ea[j], vb + 8 * lane + j, 3, p.rows, log2_ncp, s_cls);
+                        ++my;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (eb[j] & kCont) {
+                        if (my < p.qcap) { p.queue[my] = ((s0 + gb + j) << 24) | (eb[j] & 0xFFFFFFu); eb[j] = 0; }
+                        else eb[j] = sfx_walk_deep<kIdentCls>(eb[j], vb + 256 + 8 * lane + j, 3, p.rows, log2_ncp, s_cls);
+                        ++my;
+                    }
+                }
+            }
+            if (va > 0) store_group(p.out, s0 + ga, ea, va);
+            if (vbn > 0) store_group(p.out, s0 + gb, eb, vbn);
         }
-
-        if (tid == 0) bulk_wait_read<0>();  // the previous tile's result has left shared memory
-        __syncthreads();                    // s_out is free; every thread is done reading s_tile[buf]
-        if (active) {
-            uint4 lo, hi;
-            lo.x = e[0] | (e[1] << 16);   lo.y = e[2] | (e[3] << 16);
-            lo.z = e[4] | (e[5] << 16);   lo.w = e[6] | (e[7] << 16);
-            hi.x = e[8] | (e[9] << 16);   hi.y = e[10] | (e[11] << 16);
-            hi.z = e[12] | (e[13] << 16); hi.w = e[14] | (e[15] << 16);
-            uint4* so = reinterpret_cast<uint4*>(s_out + tid * kPos);
-            so[0] = lo;
-            so[1] = hi;
-        }
-        fence_proxy_async();
-        __syncthreads();
-        const uint32_t out_bytes = len * 2;
-        if (tid == 0) {
-            if (out_bytes & ~15u) bulk_s2g(p.out + s0, s_out, out_bytes & ~15u);
-            bulk_commit();
-        }
-        if (out_bytes & 15u) {  // ragged end: < 8 results with plain stores
-            const uint32_t done = (out_bytes & ~15u) / 2;
-            if (uint32_t(tid) < len - done) p.out[s0 + done + tid] = s_out[done + tid];
-        }
+        __syncwarp();  // every lane is done reading the stage before it is refilled
+        const uint64_t tn = t + uint64_t(kStages) * G;
+        if (lane == 0 && tn < p.n_tiles) issue_tile(tn, s);
     }
-    if (tid == 0) bulk_wait<0>();
+    for (uint32_t i = q_next + lane; i < q_end && i < p.qcap; i += 32) p.queue[i] = kQueueInvalid;
+}
+
+// Deferred walks (levels >= 4): one thread per queue item, straight from global memory.  The
+// dependent chain of one item is long, but the items are independent and run side by side.
+__global__ void __launch_bounds__(256) sfx_deep_kernel(const SfxParams p) {
+    const uint32_t count = min(*p.qcount, p.qcap);
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
+        const uint64_t item = p.queue[q];
+        if (item == kQueueInvalid) continue;
+        const uint64_t pos = item >> 24;
+        uint32_t v = kCont | uint32_t(item & 0xFFFFFFu);
+        const uint64_t avail = pos + p.hist_valid + 1;  // bytes that exist up to and including c[pos]
+        uint64_t k = 3;
+        while (v & kCont) {
+            const uint32_t row = v & ~kCont;
+            if (k >= avail) { v = p.row_best[row]; break; }
+            v = __ldg(p.rows + ((size_t(row) << p.log2_ncp) | p.cls[*(p.stream + pos - k)]));
+            ++k;
+        }
+        p.out[pos] = uint16_t(v);
+    }
 }
 
 // Positions whose history is shorter than max_pat_len-1 (only at the very start of a stream):
@@ -230,13 +309,25 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
     auto kern = ident_cls ? sfx_scan_kernel<true> : sfx_scan_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
-    const uint32_t grid = uint32_t(p.n_tiles < uint64_t(n_sms) ? p.n_tiles : uint64_t(n_sms));
+    e = cudaMemsetAsync(p.qcount, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    const uint64_t ctas = (p.n_tiles + kWarps - 1) / kWarps;
+    const uint32_t grid = uint32_t(ctas < uint64_t(n_sms) ? ctas : uint64_t(n_sms));
     kern<<<grid, kThreads, kSmemBytes, st>>>(p);
     ++*launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (max_pat_len > 1 && p.hist_valid < max_pat_len - 1) {
-        const uint32_t count = uint32_t(p.n < uint64_t(max_pat_len - 1 - p.hist_valid) ? p.n : uint64_t(max_pat_len - 1 - p.hist_valid));
+    if (p.qcap) {
+        sfx_deep_kernel<<<n_sms * 8, 256, 0, st>>>(p);
+        ++*launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    // Start of a stream: tile 0 is staged without its halo unless a full kHalo bytes of history exist, so
+    // every position that could look back past the tile start is redone by the bounded walker.
+    if (max_pat_len > 1 && p.hist_valid < uint64_t(kHalo)) {
+        const uint64_t want = uint64_t(max_pat_len - 1);
+        const uint32_t count = uint32_t(p.n < want ? p.n : want);
         sfx_fixup_kernel<<<(count + 127) / 128, 128, 0, st>>>(p, count);
         ++*launches;
         e = cudaGetLastError();

@@ -6,8 +6,8 @@
 namespace pm {
 
 constexpr int kSfxThreads = 1024;
-constexpr int kSfxPosPerThread = 16;
-constexpr int kSfxTile = kSfxThreads * kSfxPosPerThread;  // 16 KiB of stream per CTA iteration
+constexpr int kSfxTile = 1024;   // bytes of stream per warp tile (multiple of 512)
+constexpr int kSfxStages = 2;    // private pipeline depth of a warp
 
 struct SfxParams {
     const uint8_t* stream;    // device, 16-byte aligned; first reported byte
@@ -20,7 +20,10 @@ struct SfxParams {
     const uint32_t* row_best; // n_rows entries
     const uint8_t* cls;       // 256 entries (device)
     uint32_t cont_base, row2_base, log2_ncp;
-    uint32_t n_tiles;         // filled by the launcher
+    uint64_t* queue;          // deferred deep walks: (position << 24) | row
+    uint32_t* qcount;         // number of items pushed (may exceed qcap: the excess was resolved inline)
+    uint32_t qcap;
+    uint64_t n_tiles;         // filled by the launcher
 };
 
 size_t sfx_smem_bytes();
