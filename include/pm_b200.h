@@ -137,6 +137,15 @@ int pm_engine_generate(pm_engine* e, int kind, uint64_t off, size_t n, uint8_t* 
  * bracketed by CUDA events recorded ON THAT STREAM and returns the mean milliseconds per scan. */
 int pm_engine_time_scan(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid,
                         uint16_t* d_out, int iters, float* ms_per_scan, void* cuda_stream);
+/* Per-kernel timing of the exact (sfx) scan for the roofline: while profiling is on, every scan records CUDA
+ * events on its own stream around the dominant kernel; pm_engine_read_profile synchronises the device and
+ * returns the number of profiled scans with the summed milliseconds of the dominant kernel and of the whole
+ * scans (dominant + deferred-walk + start-of-stream kernels), then clears the record. */
+int pm_engine_set_profiling(pm_engine* e, int on);
+int pm_engine_read_profile(pm_engine* e, uint32_t* n_scans, float* main_kernel_ms, float* total_ms);
+/* Page-locked host buffers for pm_engine_scan_host (a pageable buffer is staged through internal ones). */
+void* pm_host_alloc(size_t bytes);
+void pm_host_free(void* p);
 /* number of kernel launches issued by this engine since creation (bench.py's gpu_launches) */
 uint64_t pm_engine_launch_count(const pm_engine* e);
 

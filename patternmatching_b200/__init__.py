@@ -86,6 +86,10 @@ def lib():
         "pm_engine_generate": (C.c_int, [vp, C.c_int, u64, sz, vp, vp]),
         "pm_engine_time_scan": (C.c_int, [vp, C.c_int, vp, sz, sz, vp, C.c_int, C.POINTER(C.c_float), vp]),
         "pm_engine_launch_count": (u64, [vp]),
+        "pm_engine_set_profiling": (C.c_int, [vp, C.c_int]),
+        "pm_engine_read_profile": (C.c_int, [vp, C.POINTER(u32), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "pm_host_alloc": (vp, [sz]),
+        "pm_host_free": (None, [vp]),
         "gpu_create": (vp, []), "gpu_dfa_create": (vp, []), "gpu_kr_create": (vp, []),
         "gpu_add_pattern": (None, [vp, C.c_char_p, sz, vp]),
         "gpu_compile": (None, [vp]),
@@ -279,11 +283,46 @@ class Engine:
         k = STREAMS[kind] if isinstance(kind, str) else kind
         self._check(self.L.pm_engine_generate(self.h, k, off, n, _ptr(d_dst), cuda_stream), "pm_engine_generate")
 
+    def set_profiling(self, on=True):
+        self.L.pm_engine_set_profiling(self.h, int(on))
+
+    def read_profile(self):
+        """-> (n_scans, ms summed over the dominant kernel, ms summed over whole scans)"""
+        n = C.c_uint32(); a = C.c_float(); b = C.c_float()
+        self._check(self.L.pm_engine_read_profile(self.h, C.byref(n), C.byref(a), C.byref(b)), "pm_engine_read_profile")
+        return n.value, a.value, b.value
+
     def time_scan(self, d_stream, n, d_out, hist_valid=0, algo=ALGO_SFX, iters=1, cuda_stream=0):
         ms = C.c_float()
         self._check(self.L.pm_engine_time_scan(self.h, algo, _ptr(d_stream), n, hist_valid, _ptr(d_out), iters,
                                                C.byref(ms), cuda_stream), "pm_engine_time_scan")
         return ms.value
+
+
+class PinnedBuffer:
+    """Page-locked host memory as numpy arrays (input / result buffers of Engine.scan_host)."""
+
+    def __init__(self, nbytes):
+        self.L = lib()
+        self.nbytes = nbytes
+        self.ptr = self.L.pm_host_alloc(nbytes)
+        if not self.ptr:
+            raise _err(self.L, "pm_host_alloc")
+
+    def array(self, dtype=np.uint8):
+        n = self.nbytes // np.dtype(dtype).itemsize
+        return np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_ubyte)), shape=(self.nbytes,)).view(dtype)[:n]
+
+    def free(self):
+        if self.ptr:
+            self.L.pm_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class MpsGpu:

@@ -81,6 +81,10 @@ struct pm_engine {
     uint64_t* d_queue[2] = {nullptr, nullptr};
     uint32_t* d_qcount = nullptr;         // 2 counters
     size_t queue_cap[2] = {0, 0};
+    // optional per-kernel timing of the sfx scan (bench.py's roofline): 3 events per profiled scan
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    size_t prof_used = 0;
     // host pipeline (lazy)
     bool pipe_ready = false;
     uint8_t* d_in[2] = {nullptr, nullptr};
@@ -170,7 +174,19 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
         p.stream = d_stream; p.n = n; p.hist_valid = hist_valid; p.out = d_out;
         if (fill_sfx_params(e, &p, n, slot)) return -1;
         const bool ident = d.sfx.n_classes == 256;
-        cudaError_t ce = pm::sfx_scan_launch(p, ident, e->n_sms, d.max_len, st, &e->launches);
+        cudaEvent_t* ev = nullptr;
+        if (e->profiling) {
+            if (e->prof_used + 3 > e->prof_events.size()) {
+                for (int k = 0; k < 3; ++k) {
+                    cudaEvent_t x;
+                    CU(cudaEventCreate(&x));
+                    e->prof_events.push_back(x);
+                }
+            }
+            ev = e->prof_events.data() + e->prof_used;
+            e->prof_used += 3;
+        }
+        cudaError_t ce = pm::sfx_scan_launch(p, ident, e->n_sms, d.max_len, st, &e->launches, ev);
         if (ce != cudaSuccess) return cuda_fail(ce, "sfx_scan_launch");
         return 0;
     }
@@ -256,6 +272,14 @@ int pm_dict_is_pattern_suffix(const pm_dict* d, uint32_t first_pid, uint32_t sec
     return d->d.is_pattern_suffix(first_pid, second_pid) ? 1 : 0;
 }
 
+void* pm_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    cudaError_t ce = cudaMallocHost(&p, bytes ? bytes : 1);
+    if (ce != cudaSuccess) { cuda_fail(ce, "cudaMallocHost"); return nullptr; }
+    return p;
+}
+void pm_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 pm_engine* pm_engine_create(const pm_dict* dd, int device) {
     if (!dd || !dd->d.compiled) { fail("pm_engine_create: dictionary is not compiled"); return nullptr; }
     int count = 0;
@@ -308,6 +332,7 @@ void pm_engine_free(pm_engine* e) {
                     e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1], e->d_queue[0], e->d_queue[1], e->d_qcount};
     for (void* p : ptrs) if (p) cudaFree(p);
     pm::kr_free_tables(&e->kr);
+    for (cudaEvent_t x : e->prof_events) cudaEventDestroy(x);
     for (int b = 0; b < 2; ++b) {
         if (e->h_in[b]) cudaFreeHost(e->h_in[b]);
         if (e->h_out[b]) cudaFreeHost(e->h_out[b]);
@@ -319,6 +344,26 @@ void pm_engine_free(pm_engine* e) {
 
 size_t pm_engine_total_mem(const pm_engine* e) { return e ? e->table_bytes : 0; }
 uint64_t pm_engine_launch_count(const pm_engine* e) { return e ? e->launches : 0; }
+int pm_engine_set_profiling(pm_engine* e, int on) {
+    e->profiling = on != 0;
+    e->prof_used = 0;
+    return 0;
+}
+int pm_engine_read_profile(pm_engine* e, uint32_t* n_scans, float* main_kernel_ms, float* total_ms) {
+    CU(cudaSetDevice(e->device));
+    CU(cudaDeviceSynchronize());
+    float a = 0, b = 0;
+    for (size_t i = 0; i + 3 <= e->prof_used; i += 3) {
+        float x = 0, y = 0;
+        CU(cudaEventElapsedTime(&x, e->prof_events[i], e->prof_events[i + 1]));
+        CU(cudaEventElapsedTime(&y, e->prof_events[i], e->prof_events[i + 2]));
+        a += x; b += y;
+    }
+    *n_scans = uint32_t(e->prof_used / 3);
+    *main_kernel_ms = a; *total_ms = b;
+    e->prof_used = 0;
+    return 0;
+}
 int pm_engine_set_kr_seed(pm_engine* e, uint64_t seed) {
     e->kr_seed = seed;
     return 0;

@@ -302,7 +302,7 @@ __global__ void sfx_fixup_kernel(const SfxParams p, uint32_t count) {
 size_t sfx_smem_bytes() { return kSmemBytes; }
 
 cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, uint32_t max_pat_len, cudaStream_t st,
-                            uint64_t* launches) {
+                            uint64_t* launches, cudaEvent_t* ev) {
     SfxParams p = p_in;
     if (p.n == 0) return cudaSuccess;
     p.n_tiles = (p.n + kTile - 1) / kTile;
@@ -313,7 +313,9 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
     if (e != cudaSuccess) return e;
     const uint64_t ctas = (p.n_tiles + kWarps - 1) / kWarps;
     const uint32_t grid = uint32_t(ctas < uint64_t(n_sms) ? ctas : uint64_t(n_sms));
+    if (ev) cudaEventRecord(ev[0], st);
     kern<<<grid, kThreads, kSmemBytes, st>>>(p);
+    if (ev) cudaEventRecord(ev[1], st);
     ++*launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -332,6 +334,7 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
         ++*launches;
         e = cudaGetLastError();
     }
+    if (ev) cudaEventRecord(ev[2], st);
     return e;
 }
 

@@ -28,7 +28,8 @@ struct SfxParams {
 
 size_t sfx_smem_bytes();
 // Launches the scan (+ the start-of-stream fix-up when hist_valid < max_pat_len-1) on `st`.
+// ev[0..2], when non-null, are recorded on `st` before the main kernel, after it, and after the last kernel.
 cudaError_t sfx_scan_launch(const SfxParams& p, bool ident_cls, int n_sms, uint32_t max_pat_len, cudaStream_t st,
-                            uint64_t* launches);
+                            uint64_t* launches, cudaEvent_t* ev = nullptr);
 
 }  // namespace pm
