@@ -143,6 +143,8 @@ int pm_engine_time_scan(pm_engine* e, int algo, const uint8_t* d_stream, size_t 
  * scans (dominant + deferred-walk + start-of-stream kernels), then clears the record. */
 int pm_engine_set_profiling(pm_engine* e, int on);
 int pm_engine_read_profile(pm_engine* e, uint32_t* n_scans, float* main_kernel_ms, float* total_ms);
+/* queue slots reserved for deferred deep walks by the last pm_engine_scan_device (sfx) call; synchronises */
+uint64_t pm_engine_last_deferred(pm_engine* e);
 /* Page-locked host buffers for pm_engine_scan_host (a pageable buffer is staged through internal ones). */
 void* pm_host_alloc(size_t bytes);
 void pm_host_free(void* p);

@@ -88,6 +88,7 @@ def lib():
         "pm_engine_launch_count": (u64, [vp]),
         "pm_engine_set_profiling": (C.c_int, [vp, C.c_int]),
         "pm_engine_read_profile": (C.c_int, [vp, C.POINTER(u32), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "pm_engine_last_deferred": (u64, [vp]),
         "pm_host_alloc": (vp, [sz]),
         "pm_host_free": (None, [vp]),
         "gpu_create": (vp, []), "gpu_dfa_create": (vp, []), "gpu_kr_create": (vp, []),
@@ -282,6 +283,10 @@ class Engine:
     def generate(self, kind, off, n, d_dst, cuda_stream=0):
         k = STREAMS[kind] if isinstance(kind, str) else kind
         self._check(self.L.pm_engine_generate(self.h, k, off, n, _ptr(d_dst), cuda_stream), "pm_engine_generate")
+
+    @property
+    def last_deferred(self):
+        return self.L.pm_engine_last_deferred(self.h)
 
     def set_profiling(self, on=True):
         self.L.pm_engine_set_profiling(self.h, int(on))

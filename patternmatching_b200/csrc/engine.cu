@@ -344,6 +344,12 @@ void pm_engine_free(pm_engine* e) {
 
 size_t pm_engine_total_mem(const pm_engine* e) { return e ? e->table_bytes : 0; }
 uint64_t pm_engine_launch_count(const pm_engine* e) { return e ? e->launches : 0; }
+uint64_t pm_engine_last_deferred(pm_engine* e) {
+    uint32_t c = 0;
+    cudaSetDevice(e->device);
+    if (cudaMemcpy(&c, e->d_qcount, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return c;
+}
 int pm_engine_set_profiling(pm_engine* e, int on) {
     e->profiling = on != 0;
     e->prof_used = 0;

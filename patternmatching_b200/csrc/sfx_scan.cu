@@ -9,7 +9,8 @@
 // flattened that trie so that every table entry is either the final answer or "continue at row r":
 //   level 1+2 : root2[c[i] << 8 | c[i-1]]   65,536 x u16 = 128 KiB, resident in SHARED memory
 //   level 3   : rows[row << log2_ncp | cls(c[i-2])]   u32, global memory (6.9 MB, L2-resident)
-//   level >=4 : same rows; ~1e-3 of the positions on random bytes -- DEFERRED to a work queue and
+//   level 4   : same rows, second round of predicated loads for the ~1e-3 of positions still alive
+//   level >=5 : same rows; real / planted matches, ~1e-5 of random positions -- DEFERRED to a work queue and
 //               finished by sfx_deep_kernel so that a long dependent chain never stalls a warp
 // All positions are independent, so there is no per-thread warm-up.  Every WARP runs its own
 // software pipeline: lane 0 stages 1 KiB tiles plus a 352-byte left halo (>= max_pat_len-1,
@@ -55,7 +56,7 @@ __device__ __forceinline__ uint32_t win_u16(const uint32_t (&W)[3]) {
     else return __funnelshift_r(W[O >> 2], W[(O >> 2) + 1], 24) & 0xFFFFu;
 }
 
-// Follow the rows until a final entry (levels >= 4).  `pb` points at c[i] inside a staged tile; the halo
+// Follow the rows until a final entry (levels >= 5).  `pb` points at c[i] inside a staged tile; the halo
 // guarantees pb[-k] is staged for every k the trie can ask for (k < max_pat_len <= kHalo + 1).
 template <bool kIdentCls>
 __device__ __noinline__ uint32_t sfx_walk_deep(uint32_t v, const uint8_t* pb, int k, const uint32_t* __restrict__ rows,
@@ -95,6 +96,21 @@ __device__ __forceinline__ void lookup_group(const uint16_t* s_root2, const uint
         // rows_adj = &rows[(row2_base - cont_base) << log2_ncp]: entry e addresses row (e - cont_base + row2_base)
         const uint32_t* addr = reinterpret_cast<const uint32_t*>(rows_adj + ((uintptr_t((e[j] << log2_ncp) | c)) << 2));
         if (e[j] >= cont_base) e[j] = __ldg(addr);
+    }
+}
+
+// Level 4 for the entries of a group that are still "continue" after level 3: c[i-3] is byte 1+j of W.
+template <bool kIdentCls>
+__device__ __forceinline__ void level4_group(const uint32_t (&W)[3], const uint32_t* __restrict__ rows, uint32_t log2_ncp,
+                                             const uint8_t* s_cls, uint32_t (&e)[8]) {
+    uint32_t c3[8];
+    c3[0] = win_u8<1>(W); c3[1] = win_u8<2>(W); c3[2] = win_u8<3>(W); c3[3] = win_u8<4>(W);
+    c3[4] = win_u8<5>(W); c3[5] = win_u8<6>(W); c3[6] = win_u8<7>(W); c3[7] = win_u8<8>(W);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint32_t c = c3[j];
+        if constexpr (!kIdentCls) c = s_cls[c];
+        if (e[j] & kCont) e[j] = __ldg(rows + ((size_t(e[j] & ~kCont) << log2_ncp) | c));
     }
 }
 
@@ -207,9 +223,17 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
             const uint32_t anyb = (eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7]) & kCont;
             if (__any_sync(0xFFFFFFFFu, (anya | anyb) != 0)) {
                 // Some walk of this visit is still alive after level 3 (~40% of the visits on random bytes, one
-                // or two positions each).  Hand those walks to the deep kernel: the warp owns a chunk of queue
-                // slots (one atomicAdd per kQueueChunk items -- a single global counter cannot take one atomic
-                // per item) and fills it in lane order.
+                // or two positions each).  Level 4 is taken here with one more round of predicated loads (c[i-3]
+                // is still in the register window); that ends ~99% of them.
+                level4_group<kIdentCls>(WA, p.rows, log2_ncp, s_cls, ea);
+                level4_group<kIdentCls>(WB, p.rows, log2_ncp, s_cls, eb);
+            }
+            const uint32_t any5a = (ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7]) & kCont;
+            const uint32_t any5b = (eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7]) & kCont;
+            if (__any_sync(0xFFFFFFFFu, (any5a | any5b) != 0)) {
+                // Still alive after level 4 (planted / real matches, ~1e-5 of random positions): hand the walk to
+                // the deep kernel.  The warp owns a chunk of queue slots (one atomicAdd per kQueueChunk items -- a
+                // single global counter cannot take one atomic per item) and fills it in lane order.
                 uint32_t m = 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) m |= ((ea[j] >> 31) << j) | ((eb[j] >> 31) << (8 + j));
@@ -236,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
                 for (int j = 0; j < 8; ++j) {
                     if (ea[j] & kCont) {
                         if (my < p.qcap) { p.queue[my] = ((s0 + ga + j) << 24) | (ea[j] & 0xFFFFFFu); ea[j] = 0; }
-                        else ea[j] = sfx_walk_deep<kIdentCls>(ea[j], vb + 8 * lane + j, 3, p.rows, log2_ncp, s_cls);
+                        else ea[j] = sfx_walk_deep<kIdentCls>(ea[j], vb + 8 * lane + j, 4, p.rows, log2_ncp, s_cls);
                         ++my;
                     }
                 }
@@ -244,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
                 for (int j = 0; j < 8; ++j) {
                     if (eb[j] & kCont) {
                         if (my < p.qcap) { p.queue[my] = ((s0 + gb + j) << 24) | (eb[j] & 0xFFFFFFu); eb[j] = 0; }
-                        else eb[j] = sfx_walk_deep<kIdentCls>(eb[j], vb + 256 + 8 * lane + j, 3, p.rows, log2_ncp, s_cls);
+                        else eb[j] = sfx_walk_deep<kIdentCls>(eb[j], vb + 256 + 8 * lane + j, 4, p.rows, log2_ncp, s_cls);
                         ++my;
                     }
                 }
@@ -259,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
     for (uint32_t i = q_next + lane; i < q_end && i < p.qcap; i += 32) p.queue[i] = kQueueInvalid;
 }
 
-// Deferred walks (levels >= 4): one thread per queue item, straight from global memory.  The
+// Deferred walks (levels >= 5): one thread per queue item, straight from global memory.  The
 // dependent chain of one item is long, but the items are independent and run side by side.
 __global__ void __launch_bounds__(256) sfx_deep_kernel(const SfxParams p) {
     const uint32_t count = min(*p.qcount, p.qcap);
@@ -269,7 +293,7 @@ __global__ void __launch_bounds__(256) sfx_deep_kernel(const SfxParams p) {
         const uint64_t pos = item >> 24;
         uint32_t v = kCont | uint32_t(item & 0xFFFFFFu);
         const uint64_t avail = pos + p.hist_valid + 1;  // bytes that exist up to and including c[pos]
-        uint64_t k = 3;
+        uint64_t k = 4;
         while (v & kCont) {
             const uint32_t row = v & ~kCont;
             if (k >= avail) { v = p.row_best[row]; break; }

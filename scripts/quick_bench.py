@@ -23,5 +23,11 @@ for kind in kinds:
         algo = pm.ALGOS[a]
         eng.scan_device(buf, n, out, algo=algo); torch.cuda.synchronize()   # warm-up (+ lazy table build)
         ms = eng.time_scan(buf, n, out, algo=algo, iters=3)
+        if a == "sfx":
+            eng.set_profiling(True)
+            for _ in range(3):
+                eng.scan_device(buf, n, out, algo=algo)
+            np_, mainms, totms = eng.read_profile(); eng.set_profiling(False)
+            print(f"   sfx main kernel {mainms / np_:.3f} ms, whole scan {totms / np_:.3f} ms, deferred queue slots {eng.last_deferred}")
         s = eng.summarize(out, n)
         print(f"{kind:8s} {a:4s} {ms:9.3f} ms  {n / ms / 1e6:9.1f} GB/s stream  {3 * n / ms / 1e6:9.1f} GB/s alg(3B/B)  pos={s['positions']} matches={s['matches']} h={s['hsum_all']:016x}", flush=True)

@@ -1,0 +1,95 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol that
+include/pm_b200.h declares, the host dictionary compiler reproduces the reference's ingest
+(de-dup, ids, parents, state count), and there is no CPU fallback for scanning."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import patternmatching_b200 as pm
+from conftest import GOLDEN, ROOT, TINY_DICT, dict_paths
+from oracle_lib import Oracle, parse_line
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "pm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"typedef struct \{.*?\} \w+;", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:pm|gpu|mps)_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_functions()
+    assert len(names) >= 35
+    L = C.CDLL(pm.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert pm.lib().pm_version() >= 1
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the refusal path is exercised on the CPU box")
+    d = pm.Dictionary().add_bytes(b"he\nshe\n").compile()
+    with pytest.raises(pm.PmError, match="no CUDA device"):
+        pm.Engine(d)
+
+
+@pytest.mark.parametrize("name", ["snort", "et", "merged"])
+def test_host_compiler_matches_reference_counts(name):
+    gold = json.load(open(os.path.join(GOLDEN, f"ref_{name}.json")))
+    d = pm.Dictionary()
+    for p in dict_paths(name):
+        d.add_file(p)
+    d.compile()
+    i = d.info
+    assert i.n_patterns == gold["n_patterns"] and i.n_ac_states == gold["n_states"] and i.max_pat_len == gold["max_pat_len"]
+    assert (i.n_lines, i.n_rejected, i.n_duplicates) == (gold["n_lines"], gold["n_rejected"], gold["n_duplicates"])
+
+
+def test_host_compiler_patterns_and_parents_equal_oracle(dict_merged, oracle_merged):
+    P = dict_merged.n_patterns
+    assert P == oracle_merged.n_patterns
+    of, ol = oracle_merged.id_arrays()
+    par = oracle_merged.parents()
+    rng = np.random.default_rng(1)
+    for pid in list(range(1, 400)) + rng.integers(1, P + 1, 3000).tolist() + [P]:
+        f, l, _, parent, b = dict_merged.pattern(pid)
+        o = oracle_merged.pattern(pid - 1)
+        assert (f, l, b) == (o[0], o[1], o[3])
+        assert parent == par[pid - 1] + 1
+    files, lines = dict_merged.id_arrays()
+    assert np.array_equal(files[1:], of) and np.array_equal(lines[1:], ol)
+    # is_pattern_suffix on pids == PatternsTree.c:485-494 on the oracle
+    for a, b in rng.integers(1, P + 1, (2000, 2)).tolist():
+        assert dict_merged.is_pattern_suffix(a, b) == bool(oracle_merged.L.pmo_is_pattern_suffix(oracle_merged.h, a - 1, b - 1))
+    deep = int(np.argmax([0] + [dict_merged.pattern(p)[3] > 0 for p in range(1, 2000)]))
+    assert dict_merged.is_pattern_suffix(dict_merged.pattern(deep)[3], deep)
+
+
+def test_parse_line_same_as_oracle():
+    cases = [b"abc", b"|41 42|CD", b"|41 |", b"|4|", b"|41", b"", b"||", b"a||b", b"| 2E 65 6D 66 |", b"|0a0D|", b"x|7C|y",
+             b"|30 14 06 03 55 04 03 14 0D 2A|.dropbox.com", b"T|00|e|00|", b"|  41|", b"|4 1|", b"|zz|"]
+    for c in cases:
+        assert pm.parse_pattern_line(c) == parse_line(c), c
+
+
+def test_add_pattern_dedup_returns_first_pid():
+    d = pm.Dictionary()
+    assert d.add_pattern(b"abc", 0, 1, 111) == 1
+    assert d.add_pattern(b"xyz", 0, 2, 222) == 2
+    assert d.add_pattern(b"abc", 0, 3, 333) == 1          # PatternsTree.c:193-196
+    assert d.add_pattern(b"a\x00b", 0, 4, 444) == 3       # binary patterns with NUL bytes are kept whole
+    d.compile()
+    assert d.n_patterns == 3 and d.pattern(1)[2] == 111 and d.pattern(3)[4] == b"a\x00b"
+
+
+def test_tiny_dictionary_shape():
+    d = pm.Dictionary().add_bytes(TINY_DICT).compile()
+    o = Oracle(); o.add_dict_bytes(TINY_DICT); o.compile()
+    assert d.n_patterns == 11 and d.info.n_rejected == 2 and d.info.n_ac_states == o.n_states
+    assert d.info.n_classes < 256                           # alphabet compression: unused bytes share class 0
