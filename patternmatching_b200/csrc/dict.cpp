@@ -230,31 +230,56 @@ int Dict::compile() {
     x.log2_ncp = 0;
     while ((1u << x.log2_ncp) < x.n_classes) ++x.log2_ncp;
 
-    // rows: internal nodes of depth >= 1 in BFS order
+    // Single-pattern tails: a node whose subtree is one path down to a leaf needs no rows -- the rest of the
+    // walk is a comparison against the text of that leaf's pattern (every node on the path spells a suffix of
+    // it, and the terminals on the path are exactly its PatternsTree ancestors).
+    std::vector<uint8_t> single(t.n, 0);
+    std::vector<uint32_t> leaf_pid(t.n, 0);
+    for (uint32_t v = t.n; v-- > 0;) {
+        const uint32_t nc = t.off[v + 1] - t.off[v];
+        if (nc == 0) { single[v] = 1; leaf_pid[v] = t.term[v]; }
+        else if (nc == 1 && single[t.child[t.off[v]]]) { single[v] = 1; leaf_pid[v] = leaf_pid[t.child[t.off[v]]]; }
+    }
+    auto in_tail = [&](uint32_t v) { return single[v] && t.depth[v] >= kTailMinDepth; };
+    // rows: internal nodes of depth >= 1 that are not folded into a tail, in BFS order
     std::vector<uint32_t> row_of(t.n, 0xFFFFFFFFu);
-    uint32_t n_rows = 0, n1r = 0, n2c = 0;
+    uint32_t n_rows = 0, n1r = 0, n2c = 0, n_tail = 0;
     for (uint32_t v = 1; v < t.n; ++v)
         if (t.internal(v)) {
+            if (in_tail(v)) { ++n_tail; continue; }
             row_of[v] = n_rows++;
             if (t.depth[v] == 1) ++n1r;
             if (t.depth[v] == 2) ++n2c;
         }
-    x.n_rows = n_rows; x.row2_base = n1r; x.n2_cont = n2c;
+    x.n_rows = n_rows; x.row2_base = n1r; x.n2_cont = n2c; x.n_tail_nodes = n_tail;
     x.cont_base = 65536 - n2c;
-    x.fits_u16 = (n2c < 65536) && (uint64_t(P) + 1 <= x.cont_base);
+    x.fits_u16 = (n2c < 65536) && (uint64_t(P) + 1 <= x.cont_base) && n_rows < (1u << 24);
 
     auto entry_for_child = [&](uint32_t c) -> uint32_t {  // walk arrives at existing child c
-        return t.internal(c) ? (kContFlag | row_of[c]) : best[c];
+        if (!t.internal(c)) return best[c];
+        if (in_tail(c)) return kTailFlag | leaf_pid[c];
+        return kContFlag | row_of[c];
     };
     const uint32_t ncp = 1u << x.log2_ncp;
     x.rows.assign(size_t(n_rows) * ncp, 0);
     x.row_best.assign(n_rows, 0);
     for (uint32_t v = 1; v < t.n; ++v) {
-        if (!t.internal(v)) continue;
+        if (!t.internal(v) || in_tail(v)) continue;
         uint32_t* row = x.rows.data() + size_t(row_of[v]) * ncp;
         for (uint32_t c = 0; c < ncp; ++c) row[c] = best[v];  // path dies here: answer is best(v)
         for (uint32_t k = t.off[v]; k < t.off[v + 1]; ++k) row[x.cls[t.byte[k]]] = entry_for_child(t.child[k]);
         x.row_best[row_of[v]] = best[v];
+    }
+    // tail records: for a leaf pattern q the tail starts at the shallowest node of depth >= kTailMinDepth on
+    // its path whose subtree is a single path
+    x.tail_rec.assign(size_t(P + 1) * 4, 0);
+    for (uint32_t v = 1; v < t.n; ++v) {
+        if (!in_tail(v) || in_tail(t.parent[v])) continue;     // v = first node of a tail
+        const uint32_t q = leaf_pid[v], d = t.depth[v];
+        uint32_t next_len = pats[q - 1].len;                     // shortest chain member longer than d
+        for (uint32_t a = q; a && pats[a - 1].len > d; a = pats[a - 1].parent) next_len = pats[a - 1].len;
+        uint32_t* r = x.tail_rec.data() + size_t(q) * 4;
+        r[0] = uint32_t(pats[q - 1].off); r[1] = pats[q - 1].len; r[2] = next_len; r[3] = best[v];
     }
     x.root1.assign(256, 0);
     std::vector<uint32_t> d1(256, 0);

@@ -18,7 +18,9 @@
 
 namespace pm {
 
-constexpr uint32_t kContFlag = 0x80000000u;  // row entry: continue to row (entry & ~kContFlag)
+constexpr uint32_t kContFlag = 0x80000000u;  // row entry: continue to row (entry & 0x00FFFFFF)
+constexpr uint32_t kTailFlag = 0x40000000u;  // row entry: the rest of the path is the single pattern (entry & 0xFFFF)
+constexpr uint32_t kTailMinDepth = 4;        // tails start at nodes of at least this depth (levels 1-4 stay table-driven)
 constexpr uint64_t kKrP = 2147483647ull;     // field size p = 2^31-1 (Core/src/mpbg.c:83)
 
 struct Pattern {
@@ -34,7 +36,8 @@ struct Pattern {
 // the answer for the case that the walk ends there.
 struct SfxTables {
     uint32_t n_nodes = 0;        // incl. root
-    uint32_t n_rows = 0;         // internal nodes of depth >= 1, BFS order
+    uint32_t n_rows = 0;         // nodes that own a row: internal, and not inside a single-pattern tail; BFS order
+    uint32_t n_tail_nodes = 0;   // internal nodes folded into tails (compared against the pattern text instead)
     uint32_t row2_base = 0;      // first row that belongs to a depth-2 node
     uint32_t n2_cont = 0;        // depth-2 nodes that own a row (continue codes of root2)
     uint32_t cont_base = 65536;  // root2 entries >= cont_base mean "continue at row2_base + (e - cont_base)"
@@ -46,6 +49,10 @@ struct SfxTables {
     std::vector<uint32_t> root1; // [c_i] -> final pid | kContFlag+row (bounded walker at stream start)
     std::vector<uint32_t> rows;  // [row << log2_ncp | cls] -> final pid | kContFlag+row
     std::vector<uint32_t> row_best; // [row] -> deepest terminal pid on the path to the row's node
+    // by pid (entry 0 unused): {offset of the pattern text in Dict::bytes, length, length of the shortest of
+    // {the pattern and its PatternsTree ancestors} that is longer than the tail-start depth, pid of the longest
+    // one that is not}: what a walk needs when it reaches "tail of pattern pid"
+    std::vector<uint32_t> tail_rec;   // 4 x uint32 per pid
     std::vector<uint32_t> depth_hist; // nodes per depth
 };
 

@@ -47,6 +47,7 @@ cudaError_t upload(const std::vector<T>& v, T** dptr, size_t* total) {
     if (!v.empty()) e = cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
     return e;
 }
+constexpr size_t kPatPad = 16;  // zero bytes in front of the device copy of the pattern text (8-byte windows)
 constexpr size_t kHostChunk = size_t(16) << 20;  // bytes per pipeline slot of pm_engine_scan_host
 }  // namespace
 
@@ -64,6 +65,7 @@ struct pm_engine {
     uint32_t *d_pat_off = nullptr, *d_pat_len = nullptr;
     uint8_t* d_pat_bytes = nullptr;
     uint16_t *d_parent = nullptr, *d_chain = nullptr;
+    uint32_t* d_tail_rec = nullptr;
     uint64_t* d_pidhash = nullptr;
     pm::PatTables pt{};
     // dfa tables (lazy)
@@ -149,10 +151,11 @@ int fill_sfx_params(pm_engine* e, pm::SfxParams* p, size_t n, int slot) {
     const pm::Dict& d = *e->dict;
     p->root2 = e->d_root2; p->root1 = e->d_root1; p->rows = e->d_rows; p->row_best = e->d_row_best; p->cls = e->d_cls;
     p->cont_base = d.sfx.cont_base; p->row2_base = d.sfx.row2_base; p->log2_ncp = d.sfx.log2_ncp;
+    p->tail_rec = reinterpret_cast<const uint4*>(e->d_tail_rec); p->pat_bytes = e->d_pat_bytes + kPatPad;
+    p->pat_len = e->d_pat_len; p->parent = e->d_parent;
     // queue for walks deeper than 3 levels: sized for 1/64 of the positions (random bytes need ~1/1000);
     // if it ever fills up the kernel finishes the excess walks inline
     size_t want = std::min<size_t>(n / 64 + 65536, size_t(1) << 30);
-    if (d.sfx.n_rows >= (1u << 24)) want = 0;
     if (want > e->queue_cap[slot]) {
         if (e->d_queue[slot]) CU(cudaFree(e->d_queue[slot]));
         e->d_queue[slot] = nullptr; e->queue_cap[slot] = 0;
@@ -310,15 +313,18 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
         parent[i + 1] = uint16_t(d.pats[i].parent); chain[i + 1] = uint16_t(d.pats[i].chain);
         pidhash[i + 1] = pm::splitmix64(((uint64_t(d.pats[i].file) + 1) << 32) | d.pats[i].line);
     }
+    std::vector<uint8_t> padded_bytes(kPatPad + d.bytes.size() + 16, 0);
+    std::copy(d.bytes.begin(), d.bytes.end(), padded_bytes.begin() + kPatPad);
     bool ok = up(d.sfx.root2, &e->d_root2) && up(d.sfx.root1, &e->d_root1) && up(d.sfx.rows, &e->d_rows) &&
               up(d.sfx.row_best, &e->d_row_best) && up(cls, &e->d_cls) && up(off, &e->d_pat_off) &&
-              up(len, &e->d_pat_len) && up(d.bytes, &e->d_pat_bytes) && up(parent, &e->d_parent) &&
+              up(len, &e->d_pat_len) && up(padded_bytes, &e->d_pat_bytes) && up(parent, &e->d_parent) &&
+              up(d.sfx.tail_rec, &e->d_tail_rec) &&
               up(chain, &e->d_chain) && up(pidhash, &e->d_pidhash);
     if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_acc), 8 * sizeof(unsigned long long)) != cudaSuccess) ok = false;
     if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_qcount), 2 * sizeof(uint32_t)) != cudaSuccess) ok = false;
     if (!ok) { pm_engine_free(e); return nullptr; }
     e->pt.n_patterns = uint32_t(P);
-    e->pt.off = e->d_pat_off; e->pt.len = e->d_pat_len; e->pt.bytes = e->d_pat_bytes;
+    e->pt.off = e->d_pat_off; e->pt.len = e->d_pat_len; e->pt.bytes = e->d_pat_bytes + kPatPad;
     e->pt.parent = e->d_parent; e->pt.chain = e->d_chain; e->pt.pidhash = e->d_pidhash;
     memset(e->h_hist, 0, sizeof(e->h_hist));
     return e;
@@ -328,7 +334,7 @@ void pm_engine_free(pm_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     void* ptrs[] = {e->d_root2, e->d_root1, e->d_rows, e->d_row_best, e->d_cls, e->d_pat_off, e->d_pat_len, e->d_pat_bytes,
-                    e->d_parent, e->d_chain, e->d_pidhash, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_acc,
+                    e->d_parent, e->d_chain, e->d_pidhash, e->d_tail_rec, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_acc,
                     e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1], e->d_queue[0], e->d_queue[1], e->d_qcount};
     for (void* p : ptrs) if (p) cudaFree(p);
     pm::kr_free_tables(&e->kr);

@@ -10,8 +10,9 @@
 //   level 1+2 : root2[c[i] << 8 | c[i-1]]   65,536 x u16 = 128 KiB, resident in SHARED memory
 //   level 3   : rows[row << log2_ncp | cls(c[i-2])]   u32, global memory (6.9 MB, L2-resident)
 //   level 4   : same rows, second round of predicated loads for the ~1e-3 of positions still alive
-//   level >=5 : same rows; real / planted matches, ~1e-5 of random positions -- DEFERRED to a work queue and
-//               finished by sfx_deep_kernel so that a long dependent chain never stalls a warp
+//   level >=5 : same rows / pattern-text tails; real or planted matches, ~1e-5 of random positions --
+//               DEFERRED to a work queue and finished by sfx_deep_kernel, so that a long dependent
+//               chain never stalls a scanning warp
 // All positions are independent, so there is no per-thread warm-up.  Every WARP runs its own
 // software pipeline: lane 0 stages 1 KiB tiles plus a 352-byte left halo (>= max_pat_len-1,
 // SURVEY Q8) with bulk async copies (TMA engine, SASS UBLKCP) into a private double buffer behind
@@ -31,9 +32,11 @@ constexpr int kTile = kSfxTile;                  // bytes per warp tile
 constexpr int kVisits = kTile / 512;             // 512 positions per warp visit
 constexpr int kStages = kSfxStages;
 constexpr int kStageBuf = kHalo + kTile;         // staged bytes per stage
-constexpr uint32_t kCont = 0x80000000u;
-constexpr uint32_t kQueueChunk = 256;                 // queue slots a warp reserves with one atomic
-constexpr uint64_t kQueueInvalid = ~0ull;             // padding of a partly used chunk
+constexpr uint32_t kCont = 0x80000000u;   // entry: continue at row (entry & 0xFFFFFF)
+constexpr uint32_t kTail = 0x40000000u;   // entry: the rest of the path is the text of pattern (entry & 0xFFFF)
+constexpr uint32_t kAlive = kCont | kTail;
+constexpr uint32_t kQueueChunk = 64;             // queue slots a warp reserves with one atomic
+constexpr uint64_t kQueueInvalid = ~0ull;        // padding of a partly used chunk
 
 // shared memory carve-up (bytes)
 constexpr int kOffRoot2 = 0;                     // 131072
@@ -56,16 +59,52 @@ __device__ __forceinline__ uint32_t win_u16(const uint32_t (&W)[3]) {
     else return __funnelshift_r(W[O >> 2], W[(O >> 2) + 1], 24) & 0xFFFFu;
 }
 
-// Follow the rows until a final entry (levels >= 5).  `pb` points at c[i] inside a staged tile; the halo
-// guarantees pb[-k] is staged for every k the trie can ask for (k < max_pat_len <= kHalo + 1).
-template <bool kIdentCls>
-__device__ __noinline__ uint32_t sfx_walk_deep(uint32_t v, const uint8_t* pb, int k, const uint32_t* __restrict__ rows,
-                                               uint32_t log2_ncp, const uint8_t* s_cls) {
+// The 8 bytes that END at address a (a[-7..0]) as a little-endian word, a[0] in the top byte, from two aligned
+// loads.  Bytes below `floor` are not read (they may lie outside the allocation) and come back as zero.
+__device__ __forceinline__ uint64_t load8_ending_at(const uint8_t* a, const uint8_t* floor) {
+    const uintptr_t ua = reinterpret_cast<uintptr_t>(a);
+    const uint64_t* hi_p = reinterpret_cast<const uint64_t*>(ua & ~uintptr_t(7));
+    const uint32_t sh = uint32_t(ua & 7) * 8;  // a[0] is byte (ua & 7) of the high word
+    const uint64_t hi = __ldg(hi_p);
+    uint64_t lo = 0;
+    if (sh != 56 && reinterpret_cast<const uint8_t*>(hi_p) > floor) lo = __ldg(hi_p - 1);
+    return sh == 56 ? hi : ((hi << (56 - sh)) | (lo >> (sh + 8)));
+}
+
+// Finish a walk that is alive after k consumed bytes, straight from global memory: follow rows while the
+// entry says "continue"; once it says "tail of pattern q" the remaining path is the text of q, so compare the
+// stream against it (8 bytes per step) and answer with the longest of {q and its PatternsTree ancestors} that
+// fits the matched length (the terminals on a tail are exactly those patterns).  `ci` points at c[i] in the
+// stream; avail = number of stream bytes that exist up to and including c[i].
+__device__ __noinline__ uint32_t sfx_finish(const SfxParams& p, uint32_t v, uint64_t k, const uint8_t* __restrict__ ci,
+                                            uint64_t avail) {
     while (v & kCont) {
-        uint32_t c = pb[-k];
-        if constexpr (!kIdentCls) c = s_cls[c];
-        v = __ldg(rows + ((size_t(v & ~kCont) << log2_ncp) | c));
+        const uint32_t row = v & 0xFFFFFFu;
+        if (k >= avail) return __ldg(p.row_best + row);
+        v = __ldg(p.rows + ((size_t(row) << p.log2_ncp) | __ldg(p.cls + *(ci - k))));
         ++k;
+    }
+    if (v & kTail) {
+        const uint32_t q = v & 0xFFFFu;
+        const uint4 rec = __ldg(p.tail_rec + q);             // x = text offset, y = length, z = next terminal, w = best
+        const uint32_t len = rec.y;
+        const uint8_t* text = p.pat_bytes + rec.x;           // q's text; the k consumed bytes are its last k bytes
+        const uint64_t lim = uint64_t(len) < avail ? uint64_t(len) : avail;
+        const uint8_t* floor_s = ci - (avail - 1);
+        uint64_t m = k;
+        while (m < lim) {
+            const uint64_t a = load8_ending_at(ci - m, floor_s);
+            const uint64_t b = load8_ending_at(text + (len - 1 - m), p.pat_bytes);
+            const uint64_t x = a ^ b;
+            const uint64_t same = x ? uint64_t(__clzll((long long)x) >> 3) : 8;   // equal bytes from the top (= backwards)
+            const uint64_t left = lim - m;
+            m += same < left ? same : left;
+            if (same < 8) break;
+        }
+        if (m < rec.z) return rec.w;                          // no further terminal reached: best at the tail start
+        uint32_t cand = q;
+        while (cand && uint64_t(__ldg(p.pat_len + cand - 1)) > m) cand = __ldg(p.parent + cand);
+        return cand;
     }
     return v;
 }
@@ -110,7 +149,7 @@ __device__ __forceinline__ void level4_group(const uint32_t (&W)[3], const uint3
     for (int j = 0; j < 8; ++j) {
         uint32_t c = c3[j];
         if constexpr (!kIdentCls) c = s_cls[c];
-        if (e[j] & kCont) e[j] = __ldg(rows + ((size_t(e[j] & ~kCont) << log2_ncp) | c));
+        if (e[j] & kCont) e[j] = __ldg(rows + ((size_t(e[j] & 0xFFFFFFu) << log2_ncp) | c));
     }
 }
 
@@ -228,15 +267,15 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
                 level4_group<kIdentCls>(WA, p.rows, log2_ncp, s_cls, ea);
                 level4_group<kIdentCls>(WB, p.rows, log2_ncp, s_cls, eb);
             }
-            const uint32_t any5a = (ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7]) & kCont;
-            const uint32_t any5b = (eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7]) & kCont;
+            const uint32_t any5a = (ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7]) & kAlive;
+            const uint32_t any5b = (eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7]) & kAlive;
             if (__any_sync(0xFFFFFFFFu, (any5a | any5b) != 0)) {
                 // Still alive after level 4 (planted / real matches, ~1e-5 of random positions): hand the walk to
                 // the deep kernel.  The warp owns a chunk of queue slots (one atomicAdd per kQueueChunk items -- a
                 // single global counter cannot take one atomic per item) and fills it in lane order.
                 uint32_t m = 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) m |= ((ea[j] >> 31) << j) | ((eb[j] >> 31) << (8 + j));
+                for (int j = 0; j < 8; ++j) m |= (uint32_t((ea[j] & kAlive) != 0) << j) | (uint32_t((eb[j] & kAlive) != 0) << (8 + j));
                 const uint32_t cnt = __popc(m);
                 uint32_t inc = cnt;
 #pragma unroll
@@ -258,17 +297,19 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
                 q_next += total;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (ea[j] & kCont) {
-                        if (my < p.qcap) { p.queue[my] = ((s0 + ga + j) << 24) | (ea[j] & 0xFFFFFFu); ea[j] = 0; }
-                        else ea[j] = sfx_walk_deep<kIdentCls>(ea[j], vb + 8 * lane + j, 4, p.rows, log2_ncp, s_cls);
+                    if (ea[j] & kAlive) {
+                        const uint64_t pos = s0 + ga + j;
+                        if (my < p.qcap) { p.queue[my] = (pos << 25) | (uint64_t((ea[j] & kTail) != 0) << 24) | (ea[j] & 0xFFFFFFu); ea[j] = 0; }
+                        else ea[j] = sfx_finish(p, ea[j], 4, p.stream + pos, pos + p.hist_valid + 1);
                         ++my;
                     }
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (eb[j] & kCont) {
-                        if (my < p.qcap) { p.queue[my] = ((s0 + gb + j) << 24) | (eb[j] & 0xFFFFFFu); eb[j] = 0; }
-                        else eb[j] = sfx_walk_deep<kIdentCls>(eb[j], vb + 256 + 8 * lane + j, 4, p.rows, log2_ncp, s_cls);
+                    if (eb[j] & kAlive) {
+                        const uint64_t pos = s0 + gb + j;
+                        if (my < p.qcap) { p.queue[my] = (pos << 25) | (uint64_t((eb[j] & kTail) != 0) << 24) | (eb[j] & 0xFFFFFFu); eb[j] = 0; }
+                        else eb[j] = sfx_finish(p, eb[j], 4, p.stream + pos, pos + p.hist_valid + 1);
                         ++my;
                     }
                 }
@@ -283,24 +324,16 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
     for (uint32_t i = q_next + lane; i < q_end && i < p.qcap; i += 32) p.queue[i] = kQueueInvalid;
 }
 
-// Deferred walks (levels >= 5): one thread per queue item, straight from global memory.  The
-// dependent chain of one item is long, but the items are independent and run side by side.
+// Deferred walks (levels >= 5): one thread per queue item, straight from global memory.  The dependent
+// chain of one item is long, but the items are independent and run side by side.
 __global__ void __launch_bounds__(256) sfx_deep_kernel(const SfxParams p) {
     const uint32_t count = min(*p.qcount, p.qcap);
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
         const uint64_t item = p.queue[q];
         if (item == kQueueInvalid) continue;
-        const uint64_t pos = item >> 24;
-        uint32_t v = kCont | uint32_t(item & 0xFFFFFFu);
-        const uint64_t avail = pos + p.hist_valid + 1;  // bytes that exist up to and including c[pos]
-        uint64_t k = 4;
-        while (v & kCont) {
-            const uint32_t row = v & ~kCont;
-            if (k >= avail) { v = p.row_best[row]; break; }
-            v = __ldg(p.rows + ((size_t(row) << p.log2_ncp) | p.cls[*(p.stream + pos - k)]));
-            ++k;
-        }
-        p.out[pos] = uint16_t(v);
+        const uint64_t pos = item >> 25;
+        const uint32_t v = ((item >> 24) & 1 ? kTail : kCont) | uint32_t(item & 0xFFFFFFu);
+        p.out[pos] = uint16_t(sfx_finish(p, v, 4, p.stream + pos, pos + p.hist_valid + 1));
     }
 }
 
@@ -310,15 +343,7 @@ __global__ void sfx_fixup_kernel(const SfxParams p, uint32_t count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count || i >= p.n) return;
     const uint64_t avail = uint64_t(i) + p.hist_valid + 1;
-    uint32_t v = p.root1[p.stream[i]];
-    uint64_t k = 1;
-    while (v & kCont) {
-        const uint32_t row = v & ~kCont;
-        if (k >= avail) { v = p.row_best[row]; break; }
-        v = p.rows[(size_t(row) << p.log2_ncp) | p.cls[*(p.stream + i - k)]];
-        ++k;
-    }
-    p.out[i] = uint16_t(v);
+    p.out[i] = uint16_t(sfx_finish(p, p.root1[p.stream[i]], 1, p.stream + i, avail));
 }
 
 }  // namespace
@@ -333,10 +358,10 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
     auto kern = ident_cls ? sfx_scan_kernel<true> : sfx_scan_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(p.qcount, 0, sizeof(uint32_t), st);
-    if (e != cudaSuccess) return e;
     const uint64_t ctas = (p.n_tiles + kWarps - 1) / kWarps;
     const uint32_t grid = uint32_t(ctas < uint64_t(n_sms) ? ctas : uint64_t(n_sms));
+    e = cudaMemsetAsync(p.qcount, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[0], st);
     kern<<<grid, kThreads, kSmemBytes, st>>>(p);
     if (ev) cudaEventRecord(ev[1], st);

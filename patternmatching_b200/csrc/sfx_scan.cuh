@@ -19,8 +19,12 @@ struct SfxParams {
     const uint32_t* rows;     // n_rows << log2_ncp entries
     const uint32_t* row_best; // n_rows entries
     const uint8_t* cls;       // 256 entries (device)
+    const uint4* tail_rec;    // by pid: {text offset, length, next terminal length, best at tail start} (see dict.hpp)
+    const uint8_t* pat_bytes; // pattern text (padded in front so that 8-byte windows never underrun)
+    const uint32_t* pat_len;  // by canonical index (pid - 1)
+    const uint16_t* parent;   // by pid: PatternsTree parent
     uint32_t cont_base, row2_base, log2_ncp;
-    uint64_t* queue;          // deferred deep walks: (position << 24) | row
+    uint64_t* queue;          // deferred deep walks: (position << 25) | (is_tail << 24) | row-or-pid
     uint32_t* qcount;         // number of items pushed (may exceed qcap: the excess was resolved inline)
     uint32_t qcap;
     uint64_t n_tiles;         // filled by the launcher
