@@ -6,7 +6,7 @@
 namespace pm {
 
 constexpr int kSfxThreads = 1024;
-constexpr int kSfxTile = 1024;   // bytes of stream per warp tile (multiple of 512)
+constexpr int kSfxTile = 512;    // bytes of stream per warp tile (multiple of 512)
 constexpr int kSfxStages = 2;    // private pipeline depth of a warp
 
 struct SfxParams {

@@ -262,3 +262,28 @@ def test_large_stream_properties(engine_merged):
         for key in parts:
             parts[key] = (parts[key] + s[key]) % (1 << 64)
     assert parts == s_sfx and bool(torch.equal(out, out2))
+
+
+def test_driver_binary_csv(tmp_path):
+    """pm_driver keeps the reference's flags and the first six CSV columns (measure.c:352-396); the exact
+    GPU matchers must score 0/0/0 against the reliable instance like AC/LMAC do in results.csv:2-3."""
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "patternmatching_b200", "pm_driver")
+    out = tmp_path / "results.csv"
+    open(out, "w").write("stale content that must be truncated " * 50)
+    args = [exe, "-v", "-o", str(out), "-s", os.path.join(DATA, "dictionaries_generated.stream")]
+    for p in dict_paths("merged"):
+        args += ["-d", p]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    rows = [l.split(",") for l in open(out).read().splitlines()]
+    assert rows[0][:6] == ["Algorithm", "Time (in secs)", "Total Memory Used", "False Positive Rate", "False Negative Rate",
+                           "Partial Success Rate"]
+    assert len(rows) == 4
+    for row in rows[1:3]:
+        assert [float(x) for x in row[3:6]] == [0.0, 0.0, 0.0] and int(row[2]) > 0 and int(row[6]) == 10240
+    kr = [float(x) for x in rows[3][3:6]]
+    assert kr[0] <= 1e-3 and kr[1] == 0.0          # randomized row: no false negatives, (almost) no false positives
+    # missing output file -> usage + failure, like the reference's parse_arguments
+    assert subprocess.run([exe, "-d", "x"], capture_output=True).returncode != 0
