@@ -324,16 +324,75 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
     for (uint32_t i = q_next + lane; i < q_end && i < p.qcap; i += 32) p.queue[i] = kQueueInvalid;
 }
 
-// Deferred walks (levels >= 5): one thread per queue item, straight from global memory.  The dependent
-// chain of one item is long, but the items are independent and run side by side.
+// Deferred walks (levels >= 5).  The items are independent but their dependent chains differ wildly in length
+// (one lookup ... hundreds for a long repetitive pattern), so "one item per thread, loop until done" leaves
+// 90% of the lanes idle behind the longest chain of their warp.  Instead every lane runs a small state machine
+// and pulls its next item the moment its current one ends; one pass of the loop = at most one dependent
+// memory step (a row lookup, an 8-byte tail compare, or a step up the PatternsTree chain).
 __global__ void __launch_bounds__(256) sfx_deep_kernel(const SfxParams p) {
     const uint32_t count = min(*p.qcount, p.qcap);
-    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
-        const uint64_t item = p.queue[q];
-        if (item == kQueueInvalid) continue;
-        const uint64_t pos = item >> 25;
-        const uint32_t v = ((item >> 24) & 1 ? kTail : kCont) | uint32_t(item & 0xFFFFFFu);
-        p.out[pos] = uint16_t(sfx_finish(p, v, 4, p.stream + pos, pos + p.hist_valid + 1));
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    enum { kFetch = 0, kRow = 1, kTailCmp = 2, kChain = 3 };
+    int state = kFetch;
+    uint32_t v = 0, len = 0, next_term = 0, best_start = 0, cand = 0;
+    uint64_t pos = 0, k = 0, avail = 0, lim = 0;
+    const uint8_t* ci = nullptr;
+    const uint8_t* text = nullptr;
+    for (;;) {
+        if (state == kFetch) {
+            uint64_t item = kQueueInvalid;
+            while (q < count && item == kQueueInvalid) { item = p.queue[q]; q += stride; }
+            if (item == kQueueInvalid) break;  // this lane has run out of items
+            pos = item >> 25;
+            v = ((item >> 24) & 1 ? kTail : kCont) | uint32_t(item & 0xFFFFFFu);
+            k = 4;
+            ci = p.stream + pos;
+            avail = pos + p.hist_valid + 1;
+            state = (v & kCont) ? kRow : kTailCmp;
+            if (state == kTailCmp) {
+                const uint4 rec = __ldg(p.tail_rec + (v & 0xFFFFu));
+                text = p.pat_bytes + rec.x; len = rec.y; next_term = rec.z; best_start = rec.w;
+                lim = uint64_t(len) < avail ? uint64_t(len) : avail;
+            }
+        } else if (state == kRow) {
+            const uint32_t row = v & 0xFFFFFFu;
+            if (k >= avail) {
+                p.out[pos] = uint16_t(__ldg(p.row_best + row));
+                state = kFetch;
+            } else {
+                v = __ldg(p.rows + ((size_t(row) << p.log2_ncp) | __ldg(p.cls + *(ci - k))));
+                ++k;
+                if (v & kTail) {
+                    const uint4 rec = __ldg(p.tail_rec + (v & 0xFFFFu));
+                    text = p.pat_bytes + rec.x; len = rec.y; next_term = rec.z; best_start = rec.w;
+                    lim = uint64_t(len) < avail ? uint64_t(len) : avail;
+                    state = kTailCmp;
+                } else if (!(v & kCont)) {
+                    p.out[pos] = uint16_t(v);
+                    state = kFetch;
+                }
+            }
+        } else if (state == kTailCmp) {
+            // k = bytes matched so far (the last k bytes of the pattern)
+            bool done = k >= lim;
+            if (!done) {
+                const uint64_t a = load8_ending_at(ci - k, ci - (avail - 1));
+                const uint64_t b = load8_ending_at(text + (len - 1 - k), p.pat_bytes);
+                const uint64_t x = a ^ b;
+                const uint64_t same = x ? uint64_t(__clzll((long long)x) >> 3) : 8;
+                const uint64_t left = lim - k;
+                k += same < left ? same : left;
+                done = same < 8 || k >= lim;
+            }
+            if (done) {
+                if (k < next_term) { p.out[pos] = uint16_t(best_start); state = kFetch; }
+                else { cand = v & 0xFFFFu; state = kChain; }
+            }
+        } else {  // kChain: longest of {pattern, its ancestors} that fits the k matched bytes
+            if (cand && uint64_t(__ldg(p.pat_len + cand - 1)) > k) cand = __ldg(p.parent + cand);
+            else { p.out[pos] = uint16_t(cand); state = kFetch; }
+        }
     }
 }
 
