@@ -47,6 +47,7 @@ cudaError_t upload(const std::vector<T>& v, T** dptr, size_t* total) {
     if (!v.empty()) e = cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
     return e;
 }
+constexpr size_t kMaxCtas = 1024;  // upper bound of scan CTAs per launch (one per SM)
 constexpr size_t kPatPad = 16;  // zero bytes in front of the device copy of the pattern text (8-byte windows)
 constexpr size_t kHostChunk = size_t(16) << 20;  // bytes per pipeline slot of pm_engine_scan_host
 }  // namespace
@@ -153,16 +154,20 @@ int fill_sfx_params(pm_engine* e, pm::SfxParams* p, size_t n, int slot) {
     p->cont_base = d.sfx.cont_base; p->row2_base = d.sfx.row2_base; p->log2_ncp = d.sfx.log2_ncp;
     p->tail_rec = reinterpret_cast<const uint4*>(e->d_tail_rec); p->pat_bytes = e->d_pat_bytes + kPatPad;
     p->pat_len = e->d_pat_len; p->parent = e->d_parent;
-    // queue for walks deeper than 3 levels: sized for 1/64 of the positions (random bytes need ~1/1000);
-    // if it ever fills up the kernel finishes the excess walks inline
-    size_t want = std::min<size_t>(n / 64 + 65536, size_t(1) << 30);
+    // Deferred-walk queue: one strip per scan CTA.  Random bytes defer ~1e-5 of the positions, C3 ~1.3e-3;
+    // strips are sized for 1/64 of the positions (at least 4096 slots) and a CTA that fills its strip
+    // finishes further walks inline.
+    const size_t ctas = std::max<size_t>(pm::sfx_scan_ctas(n, e->n_sms), 1);
+    const size_t per_cta = std::max<size_t>(4096, n / 64 / ctas);
+    const size_t want = ctas * per_cta;
     if (want > e->queue_cap[slot]) {
         if (e->d_queue[slot]) CU(cudaFree(e->d_queue[slot]));
         e->d_queue[slot] = nullptr; e->queue_cap[slot] = 0;
         CU(cudaMalloc(reinterpret_cast<void**>(&e->d_queue[slot]), want * sizeof(uint64_t)));
         e->queue_cap[slot] = want;
     }
-    p->queue = e->d_queue[slot]; p->qcount = e->d_qcount + slot; p->qcap = uint32_t(want ? e->queue_cap[slot] : 0);
+    p->queue = e->d_queue[slot]; p->qcount = e->d_qcount + size_t(slot) * kMaxCtas;
+    p->q_per_cta = uint32_t(std::min<size_t>(e->queue_cap[slot] / ctas, 1u << 30));
     return 0;
 }
 
@@ -321,7 +326,7 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
               up(d.sfx.tail_rec, &e->d_tail_rec) &&
               up(chain, &e->d_chain) && up(pidhash, &e->d_pidhash);
     if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_acc), 8 * sizeof(unsigned long long)) != cudaSuccess) ok = false;
-    if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_qcount), 2 * sizeof(uint32_t)) != cudaSuccess) ok = false;
+    if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_qcount), 2 * kMaxCtas * sizeof(uint32_t)) != cudaSuccess) ok = false;
     if (!ok) { pm_engine_free(e); return nullptr; }
     e->pt.n_patterns = uint32_t(P);
     e->pt.off = e->d_pat_off; e->pt.len = e->d_pat_len; e->pt.bytes = e->d_pat_bytes + kPatPad;
@@ -351,10 +356,12 @@ void pm_engine_free(pm_engine* e) {
 size_t pm_engine_total_mem(const pm_engine* e) { return e ? e->table_bytes : 0; }
 uint64_t pm_engine_launch_count(const pm_engine* e) { return e ? e->launches : 0; }
 uint64_t pm_engine_last_deferred(pm_engine* e) {
-    uint32_t c = 0;
+    std::vector<uint32_t> c(kMaxCtas);
     cudaSetDevice(e->device);
-    if (cudaMemcpy(&c, e->d_qcount, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
-    return c;
+    if (cudaMemcpy(c.data(), e->d_qcount, kMaxCtas * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    uint64_t sum = 0;
+    for (size_t i = 0; i < size_t(e->n_sms) && i < kMaxCtas; ++i) sum += c[i];
+    return sum;
 }
 int pm_engine_set_profiling(pm_engine* e, int on) {
     e->profiling = on != 0;

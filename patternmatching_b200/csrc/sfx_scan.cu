@@ -35,14 +35,13 @@ constexpr int kStageBuf = kHalo + kTile;         // staged bytes per stage
 constexpr uint32_t kCont = 0x80000000u;   // entry: continue at row (entry & 0xFFFFFF)
 constexpr uint32_t kTail = 0x40000000u;   // entry: the rest of the path is the text of pattern (entry & 0xFFFF)
 constexpr uint32_t kAlive = kCont | kTail;
-constexpr uint32_t kQueueChunk = 64;             // queue slots a warp reserves with one atomic
-constexpr uint64_t kQueueInvalid = ~0ull;        // padding of a partly used chunk
 
 // shared memory carve-up (bytes)
 constexpr int kOffRoot2 = 0;                     // 131072
 constexpr int kOffCls = 131072;                  // 256
 constexpr int kOffBar = kOffCls + 256;           // kWarps * kStages * 8
-constexpr int kOffStages = kOffBar + kWarps * kStages * 8;
+constexpr int kOffQCnt = kOffBar + kWarps * kStages * 8;           // 16 (one counter, padded)
+constexpr int kOffStages = kOffQCnt + 16;
 constexpr int kSmemBytes = kOffStages + kWarps * kStages * kStageBuf;
 static_assert(kOffStages % 16 == 0 && kStageBuf % 16 == 0, "bulk copies need 16-byte alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -51,11 +50,11 @@ static_assert((kStages & (kStages - 1)) == 0, "kStages must be a power of two");
 // byte / 16-bit window extraction from the 12-byte register window W = {c[g-4..g-1], c[g..g+3], c[g+4..g+7]}
 template <int O>
 __device__ __forceinline__ uint32_t win_u8(const uint32_t (&W)[3]) {
-    return (W[O >> 2] >> (8 * (O & 3))) & 0xFFu;
+    return __byte_perm(W[O >> 2], 0u, 0x4440u | uint32_t(O & 3));  // one PRMT, zero-extended
 }
 template <int O>
 __device__ __forceinline__ uint32_t win_u16(const uint32_t (&W)[3]) {
-    if constexpr ((O & 3) < 3) return (W[O >> 2] >> (8 * (O & 3))) & 0xFFFFu;
+    if constexpr ((O & 3) < 3) return __byte_perm(W[O >> 2], 0u, 0x4400u | uint32_t(((O & 3) + 1) << 4) | uint32_t(O & 3));
     else return __funnelshift_r(W[O >> 2], W[(O >> 2) + 1], 24) & 0xFFFFu;
 }
 
@@ -189,6 +188,8 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
     // owns the positions that would need real history)
     for (int i = lane; i < kHalo / 4; i += 32) reinterpret_cast<uint32_t*>(wbuf)[i] = 0;
     if (tid < 256) s_cls[tid] = p.cls[tid];
+    uint32_t* s_qcnt = reinterpret_cast<uint32_t*>(smem + kOffQCnt);
+    if (tid == 0) *s_qcnt = 0;
     fence_proxy_async();
     __syncwarp();
 
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
     }
     __syncthreads();  // the only CTA-wide barrier
 
-    uint32_t q_next = 0, q_end = 0;  // this warp's reserved range of the deferred-walk queue
+    uint64_t* q_strip = p.queue + size_t(blockIdx.x) * p.q_per_cta;  // this CTA's strip of the deferred-walk queue
     uint32_t it = 0;
     for (uint64_t t = gw; t < p.n_tiles; t += G, ++it) {
         const int s = it & (kStages - 1);
@@ -269,48 +270,34 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
             }
             const uint32_t any5a = (ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7]) & kAlive;
             const uint32_t any5b = (eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7]) & kAlive;
-            if (__any_sync(0xFFFFFFFFu, (any5a | any5b) != 0)) {
+            if ((any5a | any5b) != 0) {
                 // Still alive after level 4 (planted / real matches, ~1e-5 of random positions): hand the walk to
-                // the deep kernel.  The warp owns a chunk of queue slots (one atomicAdd per kQueueChunk items -- a
-                // single global counter cannot take one atomic per item) and fills it in lane order.
-                uint32_t m = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) m |= (uint32_t((ea[j] & kAlive) != 0) << j) | (uint32_t((eb[j] & kAlive) != 0) << (8 + j));
-                const uint32_t cnt = __popc(m);
-                uint32_t inc = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                    if (lane >= o) inc += y;
-                }
-                const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-                if (q_next + total > q_end) {
-                    for (uint32_t i = q_next + lane; i < q_end && i < p.qcap; i += 32) p.queue[i] = kQueueInvalid;
-                    const uint32_t need = total > kQueueChunk ? total : kQueueChunk;
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(p.qcount, need);
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    q_next = base;
-                    q_end = base + need;
-                }
-                uint32_t my = q_next + inc - cnt;
-                q_next += total;
+                // the deep kernel.  Every CTA owns a strip of the queue and hands out its slots with a shared-memory
+                // counter: no global atomics (one hot global counter cost 1.9 ms per GiB) and no warp-wide scans.
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     if (ea[j] & kAlive) {
                         const uint64_t pos = s0 + ga + j;
-                        if (my < p.qcap) { p.queue[my] = (pos << 25) | (uint64_t((ea[j] & kTail) != 0) << 24) | (ea[j] & 0xFFFFFFu); ea[j] = 0; }
-                        else ea[j] = sfx_finish(p, ea[j], 4, p.stream + pos, pos + p.hist_valid + 1);
-                        ++my;
+                        const uint32_t slot = atomicAdd(s_qcnt, 1u);
+                        if (slot < p.q_per_cta) {
+                            q_strip[slot] = (pos << 25) | (uint64_t((ea[j] & kTail) != 0) << 24) | (ea[j] & 0xFFFFFFu);
+                            ea[j] = 0;  // placeholder; sfx_deep_kernel writes the result
+                        } else {
+                            ea[j] = sfx_finish(p, ea[j], 4, p.stream + pos, pos + p.hist_valid + 1);
+                        }
                     }
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     if (eb[j] & kAlive) {
                         const uint64_t pos = s0 + gb + j;
-                        if (my < p.qcap) { p.queue[my] = (pos << 25) | (uint64_t((eb[j] & kTail) != 0) << 24) | (eb[j] & 0xFFFFFFu); eb[j] = 0; }
-                        else eb[j] = sfx_finish(p, eb[j], 4, p.stream + pos, pos + p.hist_valid + 1);
-                        ++my;
+                        const uint32_t slot = atomicAdd(s_qcnt, 1u);
+                        if (slot < p.q_per_cta) {
+                            q_strip[slot] = (pos << 25) | (uint64_t((eb[j] & kTail) != 0) << 24) | (eb[j] & 0xFFFFFFu);
+                            eb[j] = 0;
+                        } else {
+                            eb[j] = sfx_finish(p, eb[j], 4, p.stream + pos, pos + p.hist_valid + 1);
+                        }
                     }
                 }
             }
@@ -321,7 +308,8 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
         const uint64_t tn = t + uint64_t(kStages) * G;
         if (lane == 0 && tn < p.n_tiles) issue_tile(tn, s);
     }
-    for (uint32_t i = q_next + lane; i < q_end && i < p.qcap; i += 32) p.queue[i] = kQueueInvalid;
+    __syncthreads();  // every warp of the CTA has finished its tiles
+    if (tid == 0) p.qcount[blockIdx.x] = min(*s_qcnt, p.q_per_cta);
 }
 
 // Deferred walks (levels >= 5).  The items are independent but their dependent chains differ wildly in length
@@ -329,10 +317,11 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
 // 90% of the lanes idle behind the longest chain of their warp.  Instead every lane runs a small state machine
 // and pulls its next item the moment its current one ends; one pass of the loop = at most one dependent
 // memory step (a row lookup, an 8-byte tail compare, or a step up the PatternsTree chain).
-__global__ void __launch_bounds__(256) sfx_deep_kernel(const SfxParams p) {
-    const uint32_t count = min(*p.qcount, p.qcap);
-    const uint32_t stride = gridDim.x * blockDim.x;
-    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
+    // CTA b drains the strip of scan CTA b, its threads round-robin over the items
+    const uint64_t* q_strip = p.queue + size_t(blockIdx.x) * p.q_per_cta;
+    const uint32_t count = p.qcount[blockIdx.x];
+    uint32_t q = threadIdx.x;
     enum { kFetch = 0, kRow = 1, kTailCmp = 2, kChain = 3 };
     int state = kFetch;
     uint32_t v = 0, len = 0, next_term = 0, best_start = 0, cand = 0;
@@ -341,9 +330,9 @@ __global__ void __launch_bounds__(256) sfx_deep_kernel(const SfxParams p) {
     const uint8_t* text = nullptr;
     for (;;) {
         if (state == kFetch) {
-            uint64_t item = kQueueInvalid;
-            while (q < count && item == kQueueInvalid) { item = p.queue[q]; q += stride; }
-            if (item == kQueueInvalid) break;  // this lane has run out of items
+            if (q >= count) break;  // this lane has run out of items
+            const uint64_t item = q_strip[q];
+            q += blockDim.x;
             pos = item >> 25;
             v = ((item >> 24) & 1 ? kTail : kCont) | uint32_t(item & 0xFFFFFFu);
             k = 4;
@@ -409,6 +398,12 @@ __global__ void sfx_fixup_kernel(const SfxParams p, uint32_t count) {
 
 size_t sfx_smem_bytes() { return kSmemBytes; }
 
+size_t sfx_scan_ctas(uint64_t n, int n_sms) {
+    const uint64_t tiles = (n + kTile - 1) / kTile;
+    const uint64_t ctas = (tiles + kWarps - 1) / kWarps;
+    return size_t(ctas < uint64_t(n_sms) ? ctas : uint64_t(n_sms));
+}
+
 cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, uint32_t max_pat_len, cudaStream_t st,
                             uint64_t* launches, cudaEvent_t* ev) {
     SfxParams p = p_in;
@@ -419,16 +414,14 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
     if (e != cudaSuccess) return e;
     const uint64_t ctas = (p.n_tiles + kWarps - 1) / kWarps;
     const uint32_t grid = uint32_t(ctas < uint64_t(n_sms) ? ctas : uint64_t(n_sms));
-    e = cudaMemsetAsync(p.qcount, 0, sizeof(uint32_t), st);
-    if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[0], st);
     kern<<<grid, kThreads, kSmemBytes, st>>>(p);
     if (ev) cudaEventRecord(ev[1], st);
     ++*launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (p.qcap) {
-        sfx_deep_kernel<<<n_sms * 8, 256, 0, st>>>(p);
+    {
+        sfx_deep_kernel<<<grid, 1024, 0, st>>>(p);  // CTA b drains the strip of scan CTA b
         ++*launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

@@ -24,15 +24,18 @@ struct SfxParams {
     const uint32_t* pat_len;  // by canonical index (pid - 1)
     const uint16_t* parent;   // by pid: PatternsTree parent
     uint32_t cont_base, row2_base, log2_ncp;
-    uint64_t* queue;          // deferred deep walks: (position << 25) | (is_tail << 24) | row-or-pid
-    uint32_t* qcount;         // number of items pushed (may exceed qcap: the excess was resolved inline)
-    uint32_t qcap;
+    uint64_t* queue;          // deferred deep walks: (position << 25) | (is_tail << 24) | row-or-pid;
+                              // CTA b owns queue[b * q_per_cta .. (b+1) * q_per_cta)
+    uint32_t* qcount;         // [grid] items each CTA deferred
+    uint32_t q_per_cta;       // strip length; a CTA that fills its strip finishes further walks inline
     uint64_t n_tiles;         // filled by the launcher
 };
 
 size_t sfx_smem_bytes();
 // Launches the scan (+ the start-of-stream fix-up when hist_valid < max_pat_len-1) on `st`.
 // ev[0..2], when non-null, are recorded on `st` before the main kernel, after it, and after the last kernel.
+// number of CTAs the launcher will use for n bytes: sizes the queue
+size_t sfx_scan_ctas(uint64_t n, int n_sms);
 cudaError_t sfx_scan_launch(const SfxParams& p, bool ident_cls, int n_sms, uint32_t max_pat_len, cudaStream_t st,
                             uint64_t* launches, cudaEvent_t* ev = nullptr);
 
