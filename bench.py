@@ -121,7 +121,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gib", type=float, default=16.0, help="stream GiB per GPU")
-    ap.add_argument("--stream", default="planted", choices=["uniform", "planted", "almost", "ab"])
+    ap.add_argument("--stream", default="planted", choices=["uniform", "planted", "almost", "ab", "ascii"])
     ap.add_argument("--algo", default="sfx", choices=["sfx", "dfa", "kr"])
     ap.add_argument("--e2e-mib", type=int, default=1024, help="host-buffer bytes per e2e step")
     ap.add_argument("--ref-mib", type=int, default=256, help="upper bound of the CPU sample (MiB)")

@@ -82,7 +82,8 @@ enum {
     PM_STREAM_UNIFORM = 0, /* uniform bytes (splitmix64 counter generator) */
     PM_STREAM_PLANTED = 1, /* uniform background + one planted pattern per 4096-byte block */
     PM_STREAM_ALMOST  = 2, /* concatenated random-length pattern prefixes (write_first_lines.py semantics) */
-    PM_STREAM_AB      = 3  /* {a,b} with P(a)=0.75 (adversarial small alphabet) */
+    PM_STREAM_AB      = 3, /* {a,b} with P(a)=0.75 (adversarial small alphabet) */
+    PM_STREAM_ASCII   = 4  /* uniform printable ASCII 0x20..0x7E (text-like traffic) */
 };
 
 /* Upload the compiled tables to CUDA device `device`.  NULL (and pm_last_error) when there is no

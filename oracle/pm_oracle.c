@@ -461,6 +461,16 @@ void pmo_gen_almost(const PmOracle* o, uint64_t off, size_t n, uint8_t* out) {
     }
 }
 
+/* S-ascii: printable ASCII (0x20..0x7E), uniform -- text-like traffic; byte i = 0x20 + (8-bit lane of
+ * splitmix64(0xA5C11006 + i/8) * 95 >> 8). */
+void pmo_gen_ascii(uint64_t off, size_t n, uint8_t* out) {
+    for (size_t j = 0; j < n; ++j) {
+        uint64_t i = off + j;
+        uint32_t v = (uint8_t)(pmo_splitmix64(0xA5C11006ULL + (i >> 3)) >> (8 * (i & 7)));
+        out[j] = (uint8_t)(0x20 + ((v * 95) >> 8));
+    }
+}
+
 /* S-ab: bytes over {a,b} with P(a) = 192/256, seed 0xADE50004. */
 void pmo_gen_ab(uint64_t off, size_t n, uint8_t* out) {
     for (size_t j = 0; j < n; ++j) {

@@ -82,6 +82,7 @@ void pmo_gen_uniform(uint64_t off, size_t n, uint8_t* out);
 void pmo_gen_planted(const PmOracle* o, uint64_t off, size_t n, uint8_t* out);
 void pmo_gen_almost(const PmOracle* o, uint64_t off, size_t n, uint8_t* out);
 void pmo_gen_ab(uint64_t off, size_t n, uint8_t* out);
+void pmo_gen_ascii(uint64_t off, size_t n, uint8_t* out);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libpm_b200.so")
 ALGO_SFX, ALGO_DFA, ALGO_KR = 0, 1, 2
 ALGOS = {"sfx": ALGO_SFX, "dfa": ALGO_DFA, "kr": ALGO_KR}
 STREAM_UNIFORM, STREAM_PLANTED, STREAM_ALMOST, STREAM_AB = 0, 1, 2, 3
-STREAMS = {"uniform": 0, "planted": 1, "almost": 2, "ab": 3}
+STREAMS = {"uniform": 0, "planted": 1, "almost": 2, "ab": 3, "ascii": 4}
 HALO = 352  # bytes of history that make a shard scan identical to the continuous scan (>= max_pat_len-1)
 
 

@@ -28,6 +28,16 @@ __global__ void gen_ab_kernel(uint64_t off, uint64_t n, uint8_t* __restrict__ ds
     reinterpret_cast<uint64_t*>(dst)[i] = o;
 }
 
+__global__ void gen_ascii_kernel(uint64_t off, uint64_t n, uint8_t* __restrict__ dst) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i * 8 >= n) return;
+    const uint64_t w = splitmix64_d(0xA5C11006ull + (off >> 3) + i);
+    uint64_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o |= uint64_t(0x20 + ((((w >> (8 * k)) & 0xFF) * 95) >> 8)) << (8 * k);
+    reinterpret_cast<uint64_t*>(dst)[i] = o;
+}
+
 // one planted pattern per 4096-byte block, on top of the uniform background
 __global__ void gen_plant_kernel(uint64_t off, uint64_t n, uint8_t* __restrict__ dst, PatTables t) {
     const uint64_t bi = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -224,6 +234,10 @@ cudaError_t generate_launch(int kind, uint64_t off, uint64_t n, uint8_t* dst, co
             break;
         case 3:
             gen_ab_kernel<<<(words + 255) / 256, 256, 0, st>>>(off, n, dst);
+            ++*launches;
+            break;
+        case 4:
+            gen_ascii_kernel<<<(words + 255) / 256, 256, 0, st>>>(off, n, dst);
             ++*launches;
             break;
         default:

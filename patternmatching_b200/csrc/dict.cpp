@@ -281,6 +281,13 @@ int Dict::compile() {
         uint32_t* r = x.tail_rec.data() + size_t(q) * 4;
         r[0] = uint32_t(pats[q - 1].off); r[1] = pats[q - 1].len; r[2] = next_len; r[3] = best[v];
     }
+    x.l3f.assign(n2c, 0);
+    for (uint32_t v = 1; v < t.n; ++v) {
+        if (t.depth[v] != 2 || !t.internal(v)) continue;
+        uint32_t bloom = 0;
+        for (uint32_t k = t.off[v]; k < t.off[v + 1]; ++k) bloom |= 1u << (t.byte[k] & 15);
+        x.l3f[row_of[v] - n1r] = (best[v] << 16) | bloom;
+    }
     x.root1.assign(256, 0);
     std::vector<uint32_t> d1(256, 0);
     for (uint32_t k = t.off[0]; k < t.off[1]; ++k) {

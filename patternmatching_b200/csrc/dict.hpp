@@ -46,6 +46,10 @@ struct SfxTables {
     uint32_t log2_ncp = 0;       // row stride = 1 << log2_ncp >= n_classes
     uint8_t cls[256] = {0};
     std::vector<uint16_t> root2; // [c_i << 8 | c_{i-1}] -> final pid, or continue code
+    // level-3 filter, one word per depth-2 row (index = continue code - cont_base): high half = deepest terminal
+    // at the depth-2 node (the answer when c[i-2] leads nowhere), low half = 16-bit Bloom of the bytes that DO
+    // lead somewhere (bit = byte & 15).  Lives in shared memory: only Bloom hits go to the rows in L2.
+    std::vector<uint32_t> l3f;
     std::vector<uint32_t> root1; // [c_i] -> final pid | kContFlag+row (bounded walker at stream start)
     std::vector<uint32_t> rows;  // [row << log2_ncp | cls] -> final pid | kContFlag+row
     std::vector<uint32_t> row_best; // [row] -> deepest terminal pid on the path to the row's node

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -67,6 +68,7 @@ struct pm_engine {
     uint8_t* d_pat_bytes = nullptr;
     uint16_t *d_parent = nullptr, *d_chain = nullptr;
     uint32_t* d_tail_rec = nullptr;
+    uint32_t* d_l3f = nullptr;
     uint64_t* d_pidhash = nullptr;
     pm::PatTables pt{};
     // dfa tables (lazy)
@@ -152,6 +154,7 @@ int fill_sfx_params(pm_engine* e, pm::SfxParams* p, size_t n, int slot) {
     const pm::Dict& d = *e->dict;
     p->root2 = e->d_root2; p->root1 = e->d_root1; p->rows = e->d_rows; p->row_best = e->d_row_best; p->cls = e->d_cls;
     p->cont_base = d.sfx.cont_base; p->row2_base = d.sfx.row2_base; p->log2_ncp = d.sfx.log2_ncp;
+    p->l3f = getenv("PM_SFX_NO_L3") ? nullptr : e->d_l3f; p->n_l3 = uint32_t(d.sfx.l3f.size());
     p->tail_rec = reinterpret_cast<const uint4*>(e->d_tail_rec); p->pat_bytes = e->d_pat_bytes + kPatPad;
     p->pat_len = e->d_pat_len; p->parent = e->d_parent;
     // Deferred-walk queue: one strip per scan CTA.  Random bytes defer ~1e-5 of the positions, C3 ~1.3e-3;
@@ -323,7 +326,7 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
     bool ok = up(d.sfx.root2, &e->d_root2) && up(d.sfx.root1, &e->d_root1) && up(d.sfx.rows, &e->d_rows) &&
               up(d.sfx.row_best, &e->d_row_best) && up(cls, &e->d_cls) && up(off, &e->d_pat_off) &&
               up(len, &e->d_pat_len) && up(padded_bytes, &e->d_pat_bytes) && up(parent, &e->d_parent) &&
-              up(d.sfx.tail_rec, &e->d_tail_rec) &&
+              up(d.sfx.tail_rec, &e->d_tail_rec) && up(d.sfx.l3f, &e->d_l3f) &&
               up(chain, &e->d_chain) && up(pidhash, &e->d_pidhash);
     if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_acc), 8 * sizeof(unsigned long long)) != cudaSuccess) ok = false;
     if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_qcount), 2 * kMaxCtas * sizeof(uint32_t)) != cudaSuccess) ok = false;
@@ -339,7 +342,7 @@ void pm_engine_free(pm_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     void* ptrs[] = {e->d_root2, e->d_root1, e->d_rows, e->d_row_best, e->d_cls, e->d_pat_off, e->d_pat_len, e->d_pat_bytes,
-                    e->d_parent, e->d_chain, e->d_pidhash, e->d_tail_rec, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_acc,
+                    e->d_parent, e->d_chain, e->d_pidhash, e->d_tail_rec, e->d_l3f, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_acc,
                     e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1], e->d_queue[0], e->d_queue[1], e->d_qcount};
     for (void* p : ptrs) if (p) cudaFree(p);
     pm::kr_free_tables(&e->kr);

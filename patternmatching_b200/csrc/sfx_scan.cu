@@ -41,7 +41,8 @@ constexpr int kOffRoot2 = 0;                     // 131072
 constexpr int kOffCls = 131072;                  // 256
 constexpr int kOffBar = kOffCls + 256;           // kWarps * kStages * 8
 constexpr int kOffQCnt = kOffBar + kWarps * kStages * 8;           // 16 (one counter, padded)
-constexpr int kOffStages = kOffQCnt + 16;
+constexpr int kOffL3 = kOffQCnt + 16;                             // kSfxMaxL3 * 4
+constexpr int kOffStages = kOffL3 + int(kSfxMaxL3) * 4;
 constexpr int kSmemBytes = kOffStages + kWarps * kStages * kStageBuf;
 static_assert(kOffStages % 16 == 0 && kStageBuf % 16 == 0, "bulk copies need 16-byte alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -56,6 +57,12 @@ template <int O>
 __device__ __forceinline__ uint32_t win_u16(const uint32_t (&W)[3]) {
     if constexpr ((O & 3) < 3) return __byte_perm(W[O >> 2], 0u, 0x4400u | uint32_t(((O & 3) + 1) << 4) | uint32_t(O & 3));
     else return __funnelshift_r(W[O >> 2], W[(O >> 2) + 1], 24) & 0xFFFFu;
+}
+
+// (e << 8) | byte O of the window, for a 16-bit entry e: one PRMT {byte O of W, e.b0, e.b1, e.b2 (= 0)}
+template <int O>
+__device__ __forceinline__ uint32_t win_row_index(const uint32_t (&W)[3], uint32_t e) {
+    return __byte_perm(W[O >> 2], e, 0x6540u | uint32_t(O & 3));
 }
 
 // The 8 bytes that END at address a (a[-7..0]) as a little-endian word, a[0] in the top byte, from two aligned
@@ -109,13 +116,15 @@ __device__ __noinline__ uint32_t sfx_finish(const SfxParams& p, uint32_t v, uint
 }
 
 // Levels 1-3 for one group of 8 consecutive positions whose bytes sit in the register window W.
-// Phase A: 8 shared-memory gathers.  Phase B: the ~10% of entries that continue below the 2-byte table
-// fetch their level-3 row entry with PREDICATED loads -- no branch and no use of the loaded value here, so
-// all 16 loads of a visit are in flight together and a warp pays the L2 latency once per visit.
-template <bool kIdentCls>
-__device__ __forceinline__ void lookup_group(const uint16_t* s_root2, const uint32_t (&W)[3], uintptr_t rows_adj,
-                                             uint32_t cont_base, uint32_t log2_ncp, const uint8_t* s_cls, int valid,
-                                             uint32_t (&e)[8]) {
+// Phase A: 8 shared-memory gathers from root2.  Phase B: an entry that continues below the 2-byte table
+// (~10% on random bytes, ~60% on text) first consults the level-3 filter word of its row in SHARED memory:
+// unless the Bloom bit of c[i-2] is set the answer is the row's own best pid; only Bloom hits (true children
+// 0.9%, false positives ~14% of the continuing entries) fetch their row entry from L2, with PREDICATED loads --
+// no branch and no use of the loaded value here, so all loads of a visit are in flight together.
+template <bool kIdentCls, bool kL3>
+__device__ __forceinline__ bool lookup_group(const uint16_t* s_root2, const uint32_t* s_l3, const uint32_t (&W)[3],
+                                             uintptr_t rows_adj, uint32_t cont_base, uint32_t log2_ncp,
+                                             const uint8_t* s_cls, int valid, uint32_t (&e)[8]) {
     e[0] = s_root2[win_u16<3>(W)]; e[1] = s_root2[win_u16<4>(W)];
     e[2] = s_root2[win_u16<5>(W)]; e[3] = s_root2[win_u16<6>(W)];
     e[4] = s_root2[win_u16<7>(W)]; e[5] = s_root2[win_u16<8>(W)];
@@ -124,17 +133,49 @@ __device__ __forceinline__ void lookup_group(const uint16_t* s_root2, const uint
 #pragma unroll
         for (int j = 0; j < 8; ++j) if (j >= valid) e[j] = 0;  // stale bytes beyond the stream: never looked up
     }
+    const bool first_cont = e[0] >= cont_base;  // sample for the adaptive choice of the level-3 path
     uint32_t c2[8];
     c2[0] = win_u8<2>(W); c2[1] = win_u8<3>(W); c2[2] = win_u8<4>(W); c2[3] = win_u8<5>(W);
     c2[4] = win_u8<6>(W); c2[5] = win_u8<7>(W); c2[6] = win_u8<8>(W); c2[7] = win_u8<9>(W);
+    if constexpr (kL3) {
+        uint32_t f[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        uint32_t c = c2[j];
-        if constexpr (!kIdentCls) c = s_cls[c];
-        // rows_adj = &rows[(row2_base - cont_base) << log2_ncp]: entry e addresses row (e - cont_base + row2_base)
-        const uint32_t* addr = reinterpret_cast<const uint32_t*>(rows_adj + ((uintptr_t((e[j] << log2_ncp) | c)) << 2));
-        if (e[j] >= cont_base) e[j] = __ldg(addr);
+        for (int j = 0; j < 8; ++j) {
+            f[j] = 0;
+            if (e[j] >= cont_base) f[j] = s_l3[e[j] - cont_base];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint32_t c = c2[j];
+            const bool cont = e[j] >= cont_base;
+            const bool hit = ((f[j] >> (c & 15u)) & 1u) != 0;   // f == 0 when the entry does not continue
+            if constexpr (!kIdentCls) c = s_cls[c];
+            const uint32_t* addr = reinterpret_cast<const uint32_t*>(rows_adj + ((uintptr_t((e[j] << log2_ncp) | c)) << 2));
+            if (cont) e[j] = f[j] >> 16;
+            if (hit) e[j] = __ldg(addr);
+        }
+    } else if constexpr (kIdentCls) {
+        // 256 byte classes: the row index (e << 8 | c[i-2]) is ONE byte permute of the entry and the window word
+        uint32_t idx[8];
+        idx[0] = win_row_index<2>(W, e[0]); idx[1] = win_row_index<3>(W, e[1]);
+        idx[2] = win_row_index<4>(W, e[2]); idx[3] = win_row_index<5>(W, e[3]);
+        idx[4] = win_row_index<6>(W, e[4]); idx[5] = win_row_index<7>(W, e[5]);
+        idx[6] = win_row_index<8>(W, e[6]); idx[7] = win_row_index<9>(W, e[7]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            // rows_adj = &rows[(row2_base - cont_base) << 8]: entry e addresses row (e - cont_base + row2_base)
+            const uint32_t* addr = reinterpret_cast<const uint32_t*>(rows_adj + (uintptr_t(idx[j]) << 2));
+            if (e[j] >= cont_base) e[j] = __ldg(addr);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t c = s_cls[c2[j]];
+            const uint32_t* addr = reinterpret_cast<const uint32_t*>(rows_adj + ((uintptr_t((e[j] << log2_ncp) | c)) << 2));
+            if (e[j] >= cont_base) e[j] = __ldg(addr);
+        }
     }
+    return first_cont;
 }
 
 // Level 4 for the entries of a group that are still "continue" after level 3: c[i-3] is byte 1+j of W.
@@ -148,7 +189,8 @@ __device__ __forceinline__ void level4_group(const uint32_t (&W)[3], const uint3
     for (int j = 0; j < 8; ++j) {
         uint32_t c = c3[j];
         if constexpr (!kIdentCls) c = s_cls[c];
-        if (e[j] & kCont) e[j] = __ldg(rows + ((size_t(e[j] & 0xFFFFFFu) << log2_ncp) | c));
+        const uint32_t l2 = kIdentCls ? 8u : log2_ncp;
+        if (e[j] & kCont) e[j] = __ldg(rows + ((size_t(e[j] & 0xFFFFFFu) << l2) | c));
     }
 }
 
@@ -189,7 +231,14 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
     for (int i = lane; i < kHalo / 4; i += 32) reinterpret_cast<uint32_t*>(wbuf)[i] = 0;
     if (tid < 256) s_cls[tid] = p.cls[tid];
     uint32_t* s_qcnt = reinterpret_cast<uint32_t*>(smem + kOffQCnt);
+    uint32_t* s_l3 = reinterpret_cast<uint32_t*>(smem + kOffL3);
     if (tid == 0) *s_qcnt = 0;
+    const bool have_l3 = p.l3f != nullptr;
+    if (have_l3) for (uint32_t i = tid; i < p.n_l3; i += kThreads) s_l3[i] = __ldg(p.l3f + i);
+    // Per-warp choice of the level-3 path, re-made every visit from a 32-position sample of the previous one:
+    // on binary / random bytes ~10% of the positions continue below root2 and the plain predicated L2 lookups
+    // are cheapest; on text ~60% continue, and the shared-memory filter (2.1x faster there) takes over.
+    bool use_l3 = false;
     fence_proxy_async();
     __syncwarp();
 
@@ -257,8 +306,15 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
             const int ga = base_off + 8 * lane, gb = ga + 256;
             const int va = int(len) - ga, vbn = int(len) - gb;   // positions of each group that exist (>= 8: all)
             uint32_t ea[8], eb[8];
-            lookup_group<kIdentCls>(s_root2, WA, rows_adj, cont_base, log2_ncp, s_cls, va, ea);
-            lookup_group<kIdentCls>(s_root2, WB, rows_adj, cont_base, log2_ncp, s_cls, vbn, eb);
+            bool sample_cont;
+            if (use_l3) {
+                sample_cont = lookup_group<kIdentCls, true>(s_root2, s_l3, WA, rows_adj, cont_base, log2_ncp, s_cls, va, ea);
+                lookup_group<kIdentCls, true>(s_root2, s_l3, WB, rows_adj, cont_base, log2_ncp, s_cls, vbn, eb);
+            } else {
+                sample_cont = lookup_group<kIdentCls, false>(s_root2, s_l3, WA, rows_adj, cont_base, log2_ncp, s_cls, va, ea);
+                lookup_group<kIdentCls, false>(s_root2, s_l3, WB, rows_adj, cont_base, log2_ncp, s_cls, vbn, eb);
+            }
+            use_l3 = have_l3 && __popc(__ballot_sync(0xFFFFFFFFu, sample_cont)) >= 8;
             const uint32_t anya = (ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7]) & kCont;
             const uint32_t anyb = (eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7]) & kCont;
             if (__any_sync(0xFFFFFFFFu, (anya | anyb) != 0)) {
@@ -409,6 +465,7 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
     SfxParams p = p_in;
     if (p.n == 0) return cudaSuccess;
     p.n_tiles = (p.n + kTile - 1) / kTile;
+    if (p.n_l3 > kSfxMaxL3) p.l3f = nullptr;  // the filter does not fit beside root2: plain L2 lookups only
     auto kern = ident_cls ? sfx_scan_kernel<true> : sfx_scan_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;

@@ -19,6 +19,8 @@ struct SfxParams {
     const uint32_t* rows;     // n_rows << log2_ncp entries
     const uint32_t* row_best; // n_rows entries
     const uint8_t* cls;       // 256 entries (device)
+    const uint32_t* l3f;      // level-3 filter words, n_l3 entries (see dict.hpp); nullptr = not used
+    uint32_t n_l3;
     const uint4* tail_rec;    // by pid: {text offset, length, next terminal length, best at tail start} (see dict.hpp)
     const uint8_t* pat_bytes; // pattern text (padded in front so that 8-byte windows never underrun)
     const uint32_t* pat_len;  // by canonical index (pid - 1)
@@ -36,6 +38,7 @@ size_t sfx_smem_bytes();
 // ev[0..2], when non-null, are recorded on `st` before the main kernel, after it, and after the last kernel.
 // number of CTAs the launcher will use for n bytes: sizes the queue
 size_t sfx_scan_ctas(uint64_t n, int n_sms);
+constexpr uint32_t kSfxMaxL3 = 10240;  // filter words that fit beside root2 in shared memory
 cudaError_t sfx_scan_launch(const SfxParams& p, bool ident_cls, int n_sms, uint32_t max_pat_len, cudaStream_t st,
                             uint64_t* launches, cudaEvent_t* ev = nullptr);
 

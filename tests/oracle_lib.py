@@ -65,6 +65,7 @@ def lib():
         L.pmo_gen_planted.argtypes = [vp, C.c_uint64, sz, u8p]
         L.pmo_gen_almost.argtypes = [vp, C.c_uint64, sz, u8p]
         L.pmo_gen_ab.argtypes = [C.c_uint64, sz, u8p]
+        L.pmo_gen_ascii.argtypes = [C.c_uint64, sz, u8p]
         _lib = L
     return _lib
 
@@ -187,6 +188,8 @@ class Oracle:
             self.L.pmo_gen_almost(self.h, off, n, out.ctypes.data)
         elif kind == "ab":
             self.L.pmo_gen_ab(off, n, out.ctypes.data)
+        elif kind == "ascii":
+            self.L.pmo_gen_ascii(off, n, out.ctypes.data)
         else:
             raise ValueError(kind)
         return out

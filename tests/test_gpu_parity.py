@@ -75,7 +75,7 @@ def test_tiny_appendix_a_example():
         assert int((got > 0).sum()) == 7
 
 
-@pytest.mark.parametrize("kind", ["uniform", "planted", "almost"])
+@pytest.mark.parametrize("kind", ["uniform", "planted", "almost", "ascii"])
 def test_synthetic_streams_exact(kind, oracle_merged, engine_merged):
     n = 1 << 21
     stream = oracle_merged.gen(kind, 0, n)
@@ -183,7 +183,7 @@ def test_small_alphabet_adversarial_dictionary():
     assert (s["positions"], s["matches"], s["hsum_longest"], s["hsum_all"]) == (so.positions, so.matches, so.hsum_longest, so.hsum_all)
 
 
-@pytest.mark.parametrize("kind", ["uniform", "planted", "almost", "ab"])
+@pytest.mark.parametrize("kind", ["uniform", "planted", "almost", "ab", "ascii"])
 def test_device_generators_match_oracle(kind, oracle_merged, engine_merged):
     torch, dev = torch_dev()
     off, n = 4096 * 7, 4096 * 33
