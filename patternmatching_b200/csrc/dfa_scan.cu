@@ -6,22 +6,30 @@
 // DFA, so one table lookup per byte replaces the failure-link loop; worst-case work per byte is
 // constant whatever the input (the backward scan's is O(match depth)).
 //
-// The stream is cut into per-thread segments of kDfaSeg bytes; a thread first walks the
-// max_pat_len-1 bytes before its segment from the root without reporting (after that many bytes the
-// state reports exactly what a continuous scan reports -- SURVEY Q8) and then reports its own bytes.
+// The stream is cut into per-thread segments; a thread first walks the max_pat_len-1 bytes before its
+// segment from the root without reporting (after that many bytes the state reports exactly what a
+// continuous scan reports -- SURVEY Q8) and then reports its own bytes.  Two variants:
+//   hot  (default): states are numbered breadth-first, so the hot ones are the first ones: the transition
+//         rows of the first `hot_rows` states (u16 entries) and the longest-pattern ids of the first
+//         `hot_long` states live in SHARED memory (snort+et: the root and all 256 depth-1 states = 88% of the
+//         steps on random bytes; a small-alphabet dictionary: the whole automaton); the rest is read from the
+//         flat u32 table in global memory.  One dependent shared-memory gather per byte on the hot path.
+//   flat (PM_DFA_FLAT=1): every lookup from global memory through L1/L2 at full occupancy -- better when
+//         most steps are deep (pattern-prefix soup), where occupancy and L1 matter more than hot rows.
 #include "dfa_scan.cuh"
 #include "pm_dev.cuh"
 
 namespace pm {
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 128;      // flat variant
+constexpr int kHotThreads = 1024;  // hot variant: one CTA per SM, ~200 KB of hot tables
 
-__global__ void __launch_bounds__(kThreads) dfa_scan_kernel(const DfaParams p) {
+__global__ void __launch_bounds__(kThreads) dfa_flat_kernel(const DfaParams p) {
     const uint64_t seg = uint64_t(blockIdx.x) * kThreads + threadIdx.x;
-    const uint64_t s0 = seg * uint64_t(kDfaSeg);
+    const uint64_t s0 = seg * uint64_t(p.seg);
     if (s0 >= p.n) return;
-    const uint64_t s1 = min(p.n, s0 + uint64_t(kDfaSeg));
+    const uint64_t s1 = min(p.n, s0 + uint64_t(p.seg));
     // warm-up start: max_pat_len-1 bytes back, never before the readable history
     int64_t w = int64_t(s0) - int64_t(p.warm);
     if (w < -int64_t(p.hist_valid)) w = -int64_t(p.hist_valid);
@@ -65,13 +73,113 @@ __global__ void __launch_bounds__(kThreads) dfa_scan_kernel(const DfaParams p) {
     }
 }
 
+
+template <bool kIdentCls>
+__device__ __forceinline__ uint32_t dfa_step(uint32_t s, uint32_t c, const DfaParams& p, const uint16_t* s_hot,
+                                             const uint8_t* s_cls) {
+    if constexpr (!kIdentCls) c = s_cls[c];
+    const uint32_t idx = (s << p.log2_ncp) | c;
+    return s < p.hot_rows ? uint32_t(s_hot[idx]) : __ldg(p.delta + idx);
+}
+
+__device__ __forceinline__ uint32_t dfa_longest(uint32_t s, const DfaParams& p, const uint16_t* s_long) {
+    return s < p.hot_long ? uint32_t(s_long[s]) : uint32_t(__ldg(p.longest + s));
+}
+
+template <bool kIdentCls>
+__global__ void __launch_bounds__(kHotThreads, 1) dfa_hot_kernel(const DfaParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint16_t* s_hot = reinterpret_cast<uint16_t*>(smem);
+    uint16_t* s_long = s_hot + (size_t(p.hot_rows) << p.log2_ncp);
+    uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_long + p.hot_long);
+    // hot tables -> shared memory (u32 global entries narrowed to u16: the host guarantees they fit)
+    for (uint32_t i = threadIdx.x; i < (p.hot_rows << p.log2_ncp); i += kHotThreads) s_hot[i] = uint16_t(__ldg(p.delta + i));
+    for (uint32_t i = threadIdx.x; i < p.hot_long; i += kHotThreads) s_long[i] = __ldg(p.longest + i);
+    if (threadIdx.x < 256) s_cls[threadIdx.x] = p.cls[threadIdx.x];
+    __syncthreads();
+
+    const uint64_t n_seg = (p.n + p.seg - 1) / p.seg;
+    for (uint64_t seg = uint64_t(blockIdx.x) * kHotThreads + threadIdx.x; seg < n_seg; seg += uint64_t(gridDim.x) * kHotThreads) {
+        const uint64_t s0 = seg * uint64_t(p.seg);
+        const uint64_t s1 = min(p.n, s0 + uint64_t(p.seg));
+        // warm-up start: max_pat_len-1 bytes back, never before the readable history
+        int64_t w = int64_t(s0) - int64_t(p.warm);
+        if (w < -int64_t(p.hist_valid)) w = -int64_t(p.hist_valid);
+        uint32_t s = 0;
+        int64_t q0 = w;
+        for (; q0 < int64_t(s0) && (q0 & 15); ++q0) s = dfa_step<kIdentCls>(s, *(p.stream + q0), p, s_hot, s_cls);
+        for (; q0 < int64_t(s0); q0 += 16) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.stream + q0));
+            const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) s = dfa_step<kIdentCls>(s, (ws[k >> 2] >> (8 * (k & 3))) & 0xFF, p, s_hot, s_cls);
+        }
+        uint64_t q = s0;
+        for (; q + 16 <= s1; q += 16) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.stream + q));
+            const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+            uint32_t r[8];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                s = dfa_step<kIdentCls>(s, (ws[k >> 2] >> (8 * (k & 3))) & 0xFF, p, s_hot, s_cls);
+                const uint32_t o = dfa_longest(s, p, s_long);
+                if (k & 1) r[k >> 1] |= o << 16; else r[k >> 1] = o;
+            }
+            uint4* dst = reinterpret_cast<uint4*>(p.out + q);
+            __stcs(dst, make_uint4(r[0], r[1], r[2], r[3]));
+            __stcs(dst + 1, make_uint4(r[4], r[5], r[6], r[7]));
+        }
+        for (; q < s1; ++q) {  // ragged end
+            s = dfa_step<kIdentCls>(s, p.stream[q], p, s_hot, s_cls);
+            p.out[q] = uint16_t(dfa_longest(s, p, s_long));
+        }
+    }
+}
+
 }  // namespace
 
-cudaError_t dfa_scan_launch(const DfaParams& p, cudaStream_t st, uint64_t* launches) {
+void dfa_plan_hot(uint32_t n_states, uint32_t log2_ncp, const uint32_t* depth_count, uint32_t n_depths,
+                  uint32_t* hot_rows, uint32_t* hot_long) {
+    // Hot rows: whole BFS levels while their transition targets (states of the next level) still fit u16 and
+    // the rows fit the shared-memory budget; hot longest-ids: as many leading states as fit in the rest.
+    const size_t budget = 200 * 1024, row_bytes = size_t(2) << log2_ncp;
+    uint32_t rows = 0, upto = 0;
+    for (uint32_t d = 0; d < n_depths; ++d) {
+        const uint32_t level_end = upto + depth_count[d];                       // states of depth <= d
+        const uint64_t next_end = uint64_t(level_end) + (d + 1 < n_depths ? depth_count[d + 1] : 0);
+        if (next_end > 65536 || size_t(level_end) * row_bytes > budget - 8192) break;
+        rows = level_end;
+        upto = level_end;
+    }
+    *hot_rows = rows;
+    const size_t left = budget - size_t(rows) * row_bytes;
+    const uint64_t max_long = left / 2;
+    *hot_long = uint32_t(n_states < max_long ? n_states : max_long);
+}
+
+cudaError_t dfa_scan_launch(const DfaParams& p_in, bool ident_cls, bool flat, int n_sms, cudaStream_t st, uint64_t* launches) {
+    DfaParams p = p_in;
     if (p.n == 0) return cudaSuccess;
-    const uint64_t segs = (p.n + kDfaSeg - 1) / kDfaSeg;
-    const uint32_t grid = uint32_t((segs + kThreads - 1) / kThreads);
-    dfa_scan_kernel<<<grid, kThreads, 0, st>>>(p);
+    if (flat || p.hot_rows == 0) {
+        p.seg = 4096;
+        const uint64_t segs = (p.n + p.seg - 1) / p.seg;
+        const uint32_t grid = uint32_t((segs + kThreads - 1) / kThreads);
+        dfa_flat_kernel<<<grid, kThreads, 0, st>>>(p);
+        ++*launches;
+        return cudaGetLastError();
+    }
+    // segment length: long enough to amortise the warm-up, short enough to give every SM work
+    uint32_t seg = 4096;
+    while (seg < 16384 && p.n / (uint64_t(seg) * 2) >= uint64_t(n_sms) * kHotThreads * 2) seg *= 2;
+    p.seg = seg;
+    const size_t smem = (size_t(p.hot_rows) << p.log2_ncp) * 2 + size_t(p.hot_long) * 2 + 256;
+    auto kern = ident_cls ? dfa_hot_kernel<true> : dfa_hot_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    const uint64_t n_seg = (p.n + seg - 1) / seg;
+    const uint64_t ctas = (n_seg + kHotThreads - 1) / kHotThreads;
+    const uint32_t grid = uint32_t(ctas < uint64_t(n_sms) ? ctas : uint64_t(n_sms));
+    kern<<<grid, kHotThreads, smem, st>>>(p);
     ++*launches;
     return cudaGetLastError();
 }

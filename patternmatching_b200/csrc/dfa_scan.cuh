@@ -5,8 +5,6 @@
 
 namespace pm {
 
-constexpr int kDfaSeg = 4096;  // bytes reported per thread
-
 struct DfaParams {
     const uint8_t* stream;   // device, 16-byte aligned
     uint64_t n;
@@ -17,8 +15,15 @@ struct DfaParams {
     const uint8_t* cls;      // 256 entries
     uint32_t log2_ncp;
     uint32_t warm;           // max_pat_len - 1
+    uint32_t hot_rows;       // leading states whose rows are kept in shared memory as u16 (hot variant)
+    uint32_t hot_long;       // leading states whose longest-ids are kept in shared memory
+    uint32_t seg;            // bytes reported per thread (filled by the launcher)
 };
 
-cudaError_t dfa_scan_launch(const DfaParams& p, cudaStream_t st, uint64_t* launches);
+// how many leading states go to shared memory (whole BFS levels whose targets fit u16)
+void dfa_plan_hot(uint32_t n_states, uint32_t log2_ncp, const uint32_t* depth_count, uint32_t n_depths,
+                  uint32_t* hot_rows, uint32_t* hot_long);
+
+cudaError_t dfa_scan_launch(const DfaParams& p, bool ident_cls, bool flat, int n_sms, cudaStream_t st, uint64_t* launches);
 
 }  // namespace pm

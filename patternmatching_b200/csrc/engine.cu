@@ -207,7 +207,9 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
         p.stream = d_stream; p.n = n; p.hist_valid = hist_valid; p.out = d_out;
         p.delta = e->d_delta; p.longest = e->d_longest; p.cls = e->d_dfa_cls; p.log2_ncp = d.dfa.log2_ncp;
         p.warm = d.max_len ? d.max_len - 1 : 0;
-        cudaError_t ce = pm::dfa_scan_launch(p, st, &e->launches);
+        pm::dfa_plan_hot(d.dfa.n_states, d.dfa.log2_ncp, d.dfa.depth_count.data(), uint32_t(d.dfa.depth_count.size()),
+                         &p.hot_rows, &p.hot_long);
+        cudaError_t ce = pm::dfa_scan_launch(p, d.dfa.n_classes == 256, getenv("PM_DFA_FLAT") != nullptr, e->n_sms, st, &e->launches);
         if (ce != cudaSuccess) return cuda_fail(ce, "dfa_scan_launch");
         return 0;
     }
