@@ -76,7 +76,8 @@ int pm_dict_is_pattern_suffix(const pm_dict* d, uint32_t first_pid, uint32_t sec
 enum {
     PM_ALGO_SFX = 0, /* exact: per-position backward walk of the reversed-pattern trie (default) */
     PM_ALGO_DFA = 1, /* exact: per-thread forward walk of the flat Aho-Corasick DFA */
-    PM_ALGO_KR  = 2  /* randomized: Karp-Rabin suffix-stage fingerprints (mpbg/bgps/kmprt style) */
+    PM_ALGO_KR  = 2, /* randomized: Karp-Rabin suffix-stage fingerprints (mpbg/bgps/kmprt style) */
+    PM_ALGO_AUTO = 3 /* exact: SFX unless a sample of the stream shows deep walks (then DFA); see pm_engine_auto_choice */
 };
 enum {
     PM_STREAM_UNIFORM = 0, /* uniform bytes (splitmix64 counter generator) */
@@ -144,6 +145,8 @@ int pm_engine_time_scan(pm_engine* e, int algo, const uint8_t* d_stream, size_t 
  * scans (dominant + deferred-walk + start-of-stream kernels), then clears the record. */
 int pm_engine_set_profiling(pm_engine* e, int on);
 int pm_engine_read_profile(pm_engine* e, uint32_t* n_scans, float* main_kernel_ms, float* total_ms);
+/* what PM_ALGO_AUTO decided for the current stream: -1 undecided, PM_ALGO_SFX, PM_ALGO_DFA (hot rows), 4 = DFA flat */
+int pm_engine_auto_choice(const pm_engine* e);
 /* queue slots reserved for deferred deep walks by the last pm_engine_scan_device (sfx) call; synchronises */
 uint64_t pm_engine_last_deferred(pm_engine* e);
 /* Page-locked host buffers for pm_engine_scan_host (a pageable buffer is staged through internal ones). */

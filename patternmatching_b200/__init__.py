@@ -17,8 +17,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpm_b200.so")
 
-ALGO_SFX, ALGO_DFA, ALGO_KR = 0, 1, 2
-ALGOS = {"sfx": ALGO_SFX, "dfa": ALGO_DFA, "kr": ALGO_KR}
+ALGO_SFX, ALGO_DFA, ALGO_KR, ALGO_AUTO = 0, 1, 2, 3
+ALGOS = {"sfx": ALGO_SFX, "dfa": ALGO_DFA, "kr": ALGO_KR, "auto": ALGO_AUTO}
 STREAM_UNIFORM, STREAM_PLANTED, STREAM_ALMOST, STREAM_AB = 0, 1, 2, 3
 STREAMS = {"uniform": 0, "planted": 1, "almost": 2, "ab": 3, "ascii": 4}
 HALO = 352  # bytes of history that make a shard scan identical to the continuous scan (>= max_pat_len-1)
@@ -89,6 +89,7 @@ def lib():
         "pm_engine_set_profiling": (C.c_int, [vp, C.c_int]),
         "pm_engine_read_profile": (C.c_int, [vp, C.POINTER(u32), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "pm_engine_last_deferred": (u64, [vp]),
+        "pm_engine_auto_choice": (C.c_int, [vp]),
         "pm_host_alloc": (vp, [sz]),
         "pm_host_free": (None, [vp]),
         "gpu_create": (vp, []), "gpu_dfa_create": (vp, []), "gpu_kr_create": (vp, []),
@@ -283,6 +284,10 @@ class Engine:
     def generate(self, kind, off, n, d_dst, cuda_stream=0):
         k = STREAMS[kind] if isinstance(kind, str) else kind
         self._check(self.L.pm_engine_generate(self.h, k, off, n, _ptr(d_dst), cuda_stream), "pm_engine_generate")
+
+    @property
+    def auto_choice(self):
+        return self.L.pm_engine_auto_choice(self.h)
 
     @property
     def last_deferred(self):

@@ -82,17 +82,25 @@ __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
 __global__ void __launch_bounds__(256) summarize_kernel(const uint16_t* __restrict__ out, uint64_t n, uint64_t pos_base,
                                                        PatTables t, unsigned long long* __restrict__ acc) {
     uint64_t positions = 0, matches = 0, h0 = 0, h1 = 0;
-    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
-        uint32_t pid = out[i];
-        if (!pid) continue;
-        const uint64_t pos = pos_base + i;
+    auto one = [&](uint32_t pid, uint64_t pos) {
+        if (!pid) return;
         ++positions;
-        h0 += splitmix64_d(pos ^ t.pidhash[pid]);
-        for (; pid; pid = t.parent[pid]) {
-            h1 += splitmix64_d(pos ^ t.pidhash[pid]);
-            ++matches;
-        }
+        h0 += splitmix64_d(pos ^ __ldg(t.pidhash + pid));
+        const uint32_t b = __ldg(t.anc_off + pid), e = __ldg(t.anc_off + pid + 1);
+        matches += e - b;
+        for (uint32_t k = b; k < e; ++k) h1 += splitmix64_d(pos ^ __ldg(t.pidhash + __ldg(t.anc_list + k)));
+    };
+    // 8 positions (one 16-byte load) per thread and step; `out` is 16-byte aligned
+    const uint64_t n8 = n / 8;
+    const uint4* out8 = reinterpret_cast<const uint4*>(out);
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint4 v = __ldcs(out8 + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        if ((v.x | v.y | v.z | v.w) == 0) continue;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) one((w[k >> 1] >> (16 * (k & 1))) & 0xFFFF, pos_base + i * 8 + k);
     }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) one(out[n8 * 8 + threadIdx.x], pos_base + n8 * 8 + threadIdx.x);
     __shared__ uint64_t sh[4][8];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint64_t v[4] = {warp_sum(positions), warp_sum(matches), warp_sum(h0), warp_sum(h1)};
@@ -112,7 +120,7 @@ constexpr int kCompactChunk = 2048;  // positions per CTA
 constexpr int kCompactThreads = 256;
 
 __device__ __forceinline__ uint32_t recs_at(uint32_t pid, bool expand, const PatTables& t) {
-    return pid ? (expand ? 1u + t.chain[pid] : 1u) : 0u;
+    return pid ? (expand ? t.anc_off[pid + 1] - t.anc_off[pid] : 1u) : 0u;
 }
 
 __global__ void __launch_bounds__(kCompactThreads) compact_count_kernel(const uint16_t* __restrict__ out, uint64_t n,
@@ -204,11 +212,13 @@ __global__ void __launch_bounds__(kCompactThreads) compact_write_kernel(const ui
         uint32_t q = pid[k];
         if (!q) continue;
         const uint64_t pos = pos_base + base + k;
-        do {
+        if (!expand) {
             if (dst < cap) recs[dst] = (pos << 24) | q;
             ++dst;
-            q = expand ? t.parent[q] : 0;
-        } while (q);
+        } else {
+            for (uint32_t a = t.anc_off[q]; a < t.anc_off[q + 1]; ++a, ++dst)
+                if (dst < cap) recs[dst] = (pos << 24) | t.anc_list[a];
+        }
     }
 }
 
@@ -250,7 +260,7 @@ cudaError_t summarize_launch(const uint16_t* out, uint64_t n, uint64_t pos_base,
                              unsigned long long* d_acc4, int n_sms, cudaStream_t st, uint64_t* launches) {
     cudaError_t e = cudaMemsetAsync(d_acc4, 0, 4 * sizeof(unsigned long long), st);
     if (e != cudaSuccess || n == 0) return e;
-    uint64_t want = (n + 255) / 256;
+    uint64_t want = (n / 8 + 255) / 256 + 1;
     const uint32_t grid = uint32_t(want < uint64_t(n_sms) * 8 ? want : uint64_t(n_sms) * 8);
     summarize_kernel<<<grid, 256, 0, st>>>(out, n, pos_base, t, d_acc4);
     ++*launches;

@@ -15,6 +15,8 @@ struct PatTables {
     const uint16_t* parent;   // PatternsTree parent pid (Core/src/PatternsTree.h:90-94), 0 = root
     const uint16_t* chain;    // number of ancestors
     const uint64_t* pidhash;  // splitmix64(((file+1) << 32) | line), see oracle/pm_oracle.h match_digest
+    const uint32_t* anc_off;  // output links flattened to ranges: the patterns ending where pid ends are
+    const uint16_t* anc_list; // anc_list[anc_off[pid] .. anc_off[pid+1]) (pid first, then its ancestors)
 };
 
 cudaError_t generate_launch(int kind, uint64_t off, uint64_t n, uint8_t* dst, const PatTables& t, cudaStream_t st,

@@ -214,6 +214,13 @@ int Dict::compile() {
         for (uint32_t q = pats[i].parent; q; q = pats[q - 1].parent) ++c;
         pats[i].chain = c;
     }
+    anc_off.assign(size_t(P) + 2, 0);
+    anc_list.clear();
+    for (uint32_t pid = 1; pid <= P; ++pid) {
+        anc_off[pid] = uint32_t(anc_list.size());
+        for (uint32_t q = pid; q; q = pats[q - 1].parent) anc_list.push_back(uint16_t(q));
+    }
+    anc_off[P + 1] = uint32_t(anc_list.size());
     uint32_t maxd = 0;
     for (uint32_t v = 0; v < t.n; ++v) maxd = std::max(maxd, t.depth[v]);
     x.depth_hist.assign(maxd + 1, 0);

@@ -104,6 +104,10 @@ class Dict {
     // ---- data ----
     std::vector<Pattern> pats;        // pats[pid-1]
     std::vector<uint8_t> bytes;
+    // output links flattened to pattern-id ranges: all patterns that end where pid ends (pid itself, then its
+    // PatternsTree ancestors, longest first) are anc_list[anc_off[pid] .. anc_off[pid + 1])
+    std::vector<uint32_t> anc_off;    // P + 2 entries (entry 0: the empty range of "no pattern")
+    std::vector<uint16_t> anc_list;
     uint64_t n_lines = 0, n_rejected = 0, n_dups = 0;
     uint32_t n_files = 0, max_len = 0;
     uint32_t n_ac_states = 1;

@@ -69,6 +69,8 @@ struct pm_engine {
     uint16_t *d_parent = nullptr, *d_chain = nullptr;
     uint32_t* d_tail_rec = nullptr;
     uint32_t* d_l3f = nullptr;
+    uint32_t* d_anc_off = nullptr;
+    uint16_t* d_anc_list = nullptr;
     uint64_t* d_pidhash = nullptr;
     pm::PatTables pt{};
     // dfa tables (lazy)
@@ -86,6 +88,10 @@ struct pm_engine {
     uint64_t* d_queue[2] = {nullptr, nullptr};
     uint32_t* d_qcount = nullptr;         // 2 counters
     size_t queue_cap[2] = {0, 0};
+    // PM_ALGO_AUTO: scratch result buffer for the sampling scans, decision cached per stream (until reset)
+    uint16_t* d_sample_out = nullptr;
+    int auto_choice = -1;
+    bool auto_flat = false;
     // optional per-kernel timing of the sfx scan (bench.py's roofline): 3 events per profiled scan
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
@@ -175,8 +181,49 @@ int fill_sfx_params(pm_engine* e, pm::SfxParams* p, size_t n, int slot) {
 }
 
 int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid, uint16_t* d_out,
-                     cudaStream_t st, int slot = 0) {
+                     cudaStream_t st, int slot = 0);
+
+// PM_ALGO_AUTO: run the backward scan over four 256 KiB windows of the stream and look at how many walks were
+// still alive after level 4.  Uniform / planted / text traffic defers 1e-5 .. 2e-3 of the positions; inputs made
+// of pattern prefixes or small-alphabet adversarial dictionaries defer 10..100% and belong to the forward DFA,
+// whose work per byte is constant.  Synchronises `st` (one small D2H copy).
+constexpr size_t kSampleWin = size_t(256) << 10;
+int choose_algo(pm_engine* e, const uint8_t* d_stream, size_t n, size_t hist_valid, cudaStream_t st, int slot) {
+    if (n < 4 * kSampleWin) { e->auto_flat = false; return PM_ALGO_SFX; }
+    if (!e->d_sample_out) CU(cudaMalloc(reinterpret_cast<void**>(&e->d_sample_out), kSampleWin * sizeof(uint16_t)));
+    uint64_t deferred = 0;
+    std::vector<uint32_t> counts(kMaxCtas);
+    for (int w = 0; w < 4; ++w) {
+        const size_t off = (n / 4 * size_t(w)) & ~size_t(4095);
+        if (scan_device_impl(e, PM_ALGO_SFX, d_stream + off, kSampleWin, std::min<size_t>(off + hist_valid, pm::kHalo),
+                             e->d_sample_out, st, slot)) return -1;
+        const size_t ctas = pm::sfx_scan_ctas(kSampleWin, e->n_sms);
+        CU(cudaMemcpyAsync(counts.data(), e->d_qcount + size_t(slot) * kMaxCtas, ctas * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < ctas; ++i) deferred += counts[i];
+    }
+    const bool deep = deferred * 32 > 4 * kSampleWin;     // more than 1/32 of the positions walk past level 4
+    if (!deep) { e->auto_flat = false; return PM_ALGO_SFX; }
+    if (ensure_dfa(e)) return -1;
+    uint32_t hot_rows = 0, hot_long = 0;
+    const pm::Dict& d = *e->dict;
+    pm::dfa_plan_hot(d.dfa.n_states, d.dfa.log2_ncp, d.dfa.depth_count.data(), uint32_t(d.dfa.depth_count.size()), &hot_rows, &hot_long);
+    e->auto_flat = hot_rows < d.dfa.n_states;              // deep walks and an automaton that does not fit: occupancy + L1 win
+    return PM_ALGO_DFA;
+}
+
+int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid, uint16_t* d_out,
+                     cudaStream_t st, int slot) {
     if (n == 0) return 0;
+    bool force_flat = false;
+    if (algo == PM_ALGO_AUTO) {
+        if (e->auto_choice < 0) {
+            e->auto_choice = choose_algo(e, d_stream, n, hist_valid, st, slot);
+            if (e->auto_choice < 0) return -1;
+        }
+        algo = e->auto_choice;
+        force_flat = e->auto_flat;
+    }
     if ((reinterpret_cast<uintptr_t>(d_stream) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
         return fail("pm_engine_scan_device: d_stream and d_out must be 16-byte aligned");
     const pm::Dict& d = *e->dict;
@@ -209,7 +256,7 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
         p.warm = d.max_len ? d.max_len - 1 : 0;
         pm::dfa_plan_hot(d.dfa.n_states, d.dfa.log2_ncp, d.dfa.depth_count.data(), uint32_t(d.dfa.depth_count.size()),
                          &p.hot_rows, &p.hot_long);
-        cudaError_t ce = pm::dfa_scan_launch(p, d.dfa.n_classes == 256, getenv("PM_DFA_FLAT") != nullptr, e->n_sms, st, &e->launches);
+        cudaError_t ce = pm::dfa_scan_launch(p, d.dfa.n_classes == 256, force_flat || getenv("PM_DFA_FLAT") != nullptr, e->n_sms, st, &e->launches);
         if (ce != cudaSuccess) return cuda_fail(ce, "dfa_scan_launch");
         return 0;
     }
@@ -329,6 +376,7 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
               up(d.sfx.row_best, &e->d_row_best) && up(cls, &e->d_cls) && up(off, &e->d_pat_off) &&
               up(len, &e->d_pat_len) && up(padded_bytes, &e->d_pat_bytes) && up(parent, &e->d_parent) &&
               up(d.sfx.tail_rec, &e->d_tail_rec) && up(d.sfx.l3f, &e->d_l3f) &&
+              up(d.anc_off, &e->d_anc_off) && up(d.anc_list, &e->d_anc_list) &&
               up(chain, &e->d_chain) && up(pidhash, &e->d_pidhash);
     if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_acc), 8 * sizeof(unsigned long long)) != cudaSuccess) ok = false;
     if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_qcount), 2 * kMaxCtas * sizeof(uint32_t)) != cudaSuccess) ok = false;
@@ -336,6 +384,7 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
     e->pt.n_patterns = uint32_t(P);
     e->pt.off = e->d_pat_off; e->pt.len = e->d_pat_len; e->pt.bytes = e->d_pat_bytes + kPatPad;
     e->pt.parent = e->d_parent; e->pt.chain = e->d_chain; e->pt.pidhash = e->d_pidhash;
+    e->pt.anc_off = e->d_anc_off; e->pt.anc_list = e->d_anc_list;
     memset(e->h_hist, 0, sizeof(e->h_hist));
     return e;
 }
@@ -344,7 +393,7 @@ void pm_engine_free(pm_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     void* ptrs[] = {e->d_root2, e->d_root1, e->d_rows, e->d_row_best, e->d_cls, e->d_pat_off, e->d_pat_len, e->d_pat_bytes,
-                    e->d_parent, e->d_chain, e->d_pidhash, e->d_tail_rec, e->d_l3f, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_acc,
+                    e->d_parent, e->d_chain, e->d_pidhash, e->d_tail_rec, e->d_l3f, e->d_anc_off, e->d_anc_list, e->d_sample_out, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_acc,
                     e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1], e->d_queue[0], e->d_queue[1], e->d_qcount};
     for (void* p : ptrs) if (p) cudaFree(p);
     pm::kr_free_tables(&e->kr);
@@ -360,6 +409,7 @@ void pm_engine_free(pm_engine* e) {
 
 size_t pm_engine_total_mem(const pm_engine* e) { return e ? e->table_bytes : 0; }
 uint64_t pm_engine_launch_count(const pm_engine* e) { return e ? e->launches : 0; }
+int pm_engine_auto_choice(const pm_engine* e) { return e->auto_choice < 0 ? -1 : (e->auto_choice == PM_ALGO_DFA && e->auto_flat ? 4 : e->auto_choice); }
 uint64_t pm_engine_last_deferred(pm_engine* e) {
     std::vector<uint32_t> c(kMaxCtas);
     cudaSetDevice(e->device);
@@ -396,10 +446,12 @@ int pm_engine_set_kr_seed(pm_engine* e, uint64_t seed) {
 int pm_engine_scan_device(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid,
                           uint16_t* d_out, void* cuda_stream) {
     CU(cudaSetDevice(e->device));
+    if (algo == PM_ALGO_AUTO) e->auto_choice = -1;  // device scans are independent calls: decide per call
     return scan_device_impl(e, algo, d_stream, n, hist_valid, d_out, static_cast<cudaStream_t>(cuda_stream));
 }
 
 void pm_engine_reset(pm_engine* e) {
+    e->auto_choice = -1;  // a new stream: PM_ALGO_AUTO samples again
     e->hist_valid = 0;
     memset(e->h_hist, 0, sizeof(e->h_hist));
 }
@@ -409,6 +461,7 @@ int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n,
     if (ensure_pipe(e)) return -1;
     if (algo == PM_ALGO_DFA && ensure_dfa(e)) return -1;
     if (algo == PM_ALGO_KR && ensure_kr(e)) return -1;
+    if (algo == PM_ALGO_AUTO && e->auto_choice < 0 && n < 4 * kSampleWin) algo = PM_ALGO_SFX;  // too short to sample
     const bool in_pinned = is_pinned(stream), out_pinned = is_pinned(out);
     const size_t n_chunks = (n + kHostChunk - 1) / kHostChunk;
     auto drain = [&](size_t k) -> int {  // chunk k has fully left the device

@@ -39,7 +39,7 @@ static void* create_with(int algo) {
     return g;
 }
 
-void* gpu_create(void) { return create_with(PM_ALGO_SFX); }
+void* gpu_create(void) { return create_with(PM_ALGO_AUTO); }  /* exact; picks the kernel from a sample of the stream */
 void* gpu_dfa_create(void) { return create_with(PM_ALGO_DFA); }
 void* gpu_kr_create(void) { return create_with(PM_ALGO_KR); }
 
@@ -116,6 +116,6 @@ static void fill(pm_mps_elem* e, const char* name, void* (*create)(void)) {
     e->free = gpu_free;
 }
 /* what a mps_gpu_register() added to mps_table_setup (Core/src/mps.c:120-124) would call */
-void mps_gpu_register_into(pm_mps_elem* slot) { fill(slot, "B200 suffix-trie scan", gpu_create); }
+void mps_gpu_register_into(pm_mps_elem* slot) { fill(slot, "B200 exact dictionary scan", gpu_create); }
 void mps_gpu_dfa_register_into(pm_mps_elem* slot) { fill(slot, "B200 Aho-Corasick DFA", gpu_dfa_create); }
 void mps_gpu_kr_register_into(pm_mps_elem* slot) { fill(slot, "B200 Karp-Rabin stages", gpu_kr_create); }

@@ -287,3 +287,34 @@ def test_driver_binary_csv(tmp_path):
     assert kr[0] <= 1e-3 and kr[1] == 0.0          # randomized row: no false negatives, (almost) no false positives
     # missing output file -> usage + failure, like the reference's parse_arguments
     assert subprocess.run([exe, "-d", "x"], capture_output=True).returncode != 0
+
+
+def test_auto_picks_the_kernel_from_a_sample(oracle_merged, engine_merged):
+    """PM_ALGO_AUTO: backward scan for shallow traffic, forward DFA when a sample shows deep walks; exact either way."""
+    torch, dev = torch_dev()
+    n = 4 << 20
+    for kind, expect in (("planted", pm.ALGO_SFX), ("ascii", pm.ALGO_SFX), ("almost", 4)):   # 4 = DFA, flat variant
+        stream = oracle_merged.gen(kind, 0, n)
+        want = want_pids(oracle_merged, stream)
+        got = gpu_scan(engine_merged, stream, pm.ALGO_AUTO)
+        assert engine_merged.auto_choice == expect, (kind, engine_merged.auto_choice)
+        assert np.array_equal(got, want), kind
+    # small-alphabet adversarial dictionary: the whole automaton fits in shared memory -> DFA with hot rows
+    pats = [b"a" * k for k in range(1, 65)]
+    for L in range(1, 9):
+        for v in range(1 << L):
+            pats.append(bytes(ord("a") + ((v >> i) & 1) for i in range(L)))
+    lines = b"\n".join(pats) + b"\n"
+    d = pm.Dictionary().add_bytes(lines).compile()
+    o = Oracle(); o.add_dict_bytes(lines); o.compile()
+    eng = pm.Engine(d)
+    stream = o.gen("ab", 0, n)
+    got = gpu_scan(eng, stream, pm.ALGO_AUTO)
+    assert eng.auto_choice == pm.ALGO_DFA
+    assert np.array_equal(got, want_pids(o, stream))
+    # the host path decides once per stream and keeps the decision until reset
+    eng.reset()
+    got = eng.scan_host(stream, algo=pm.ALGO_AUTO)
+    assert eng.auto_choice == pm.ALGO_DFA and np.array_equal(got, want_pids(o, stream))
+    eng.reset()
+    assert eng.auto_choice == -1
