@@ -96,7 +96,7 @@ def reference_arm(args, rank, world):
     times = []
     for _ in range(args.steps_ref):
         r = ref.scan_parallel(stream, cores)
-        times.append(r["wall_seconds"])
+        times.append(r["max_loop_seconds"])     # slowest worker's read_char loop (what measure.c:290-297 times), fork excluded
     t = sum(times) / len(times)
     gbs = sample / t / 1e9
     one = ref.scan(stream[: 32 << 20], want_ids=False)[0]
@@ -111,7 +111,17 @@ def reference_arm(args, rank, world):
                              "sample": f"{sample >> 20} MiB of the S-{args.stream} stream, all {cores} host threads"},
             "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else a library prints (NCCL's version banner
+    on communicator creation, ...) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -146,7 +156,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"              # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     d = pm.Dictionary()
@@ -280,10 +289,10 @@ def main():
             host = buf[lead:lead + sample].cpu().numpy()
             ref = Reference(DICTS, algo_mask=1)
             r = ref.scan_parallel(host, cores)
-            line["cpu_baseline"] = {"value": sample / r["wall_seconds"] / 1e9, "unit": "GB/s", "cores": cores,
+            line["cpu_baseline"] = {"value": sample / r["max_loop_seconds"] / 1e9, "unit": "GB/s", "cores": cores,
                                     "kind": "reference",
                                     "sample": f"first {sample >> 20} MiB of this rank's stream, reference ac_read_char loop "
-                                              f"(gcc -O2), fork per core with halo"}
+                                              f"(gcc -O2), fork per core with halo; time = slowest worker's loop"}
             # the GPU result on the same sample must carry the reference's digest
             sg = eng.summarize(out, sample, pos_base=off)
             line["cpu_baseline"]["gpu_matches_reference"] = bool(
@@ -291,7 +300,7 @@ def main():
                 sg["hsum_longest"] == r["hsum_longest"] and sg["hsum_all"] == r["hsum_all"]) if rank == 0 and off == 0 else None
         except Exception as e:
             line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
