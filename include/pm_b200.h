@@ -50,6 +50,15 @@ uint32_t pm_dict_add_pattern(pm_dict* d, const uint8_t* pat, size_t len, uint32_
  * and convert_fpt_to_patterns_tree (PatternsTree.c:416-428) for the suffix-parent relation. */
 int pm_dict_compile(pm_dict* d);
 
+/* Compiled-automaton cache (the reference rebuilds its structures on every run: 6-7 s PatternsTree,
+ * PatternsTree.c:186-214, + 4-5 s ac_compile, mpac.c:282-291).  pm_dict_save writes a compiled dictionary to one
+ * binary file, pm_dict_load reads it back (NULL + pm_last_error on a foreign / truncated file);
+ * pm_dict_compile_files_cached keys the file by a hash of the dictionary files' contents and order
+ * (<cache_dir>/pmdict-<hash>.bin): load when present, else ingest + compile + save. */
+int pm_dict_save(const pm_dict* d, const char* path);
+pm_dict* pm_dict_load(const char* path);
+pm_dict* pm_dict_compile_files_cached(const char* const* paths, int n, const char* cache_dir);
+
 typedef struct {
     uint64_t n_lines, n_rejected, n_duplicates; /* ingest accounting */
     uint32_t n_patterns;                        /* unique patterns P */

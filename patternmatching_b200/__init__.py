@@ -71,6 +71,9 @@ def lib():
         "pm_dict_add_pattern": (u32, [vp, vp, sz, u32, u32, u64]),
         "pm_dict_compile": (C.c_int, [vp]),
         "pm_dict_get_info": (C.c_int, [vp, C.POINTER(DictInfo)]),
+        "pm_dict_save": (C.c_int, [vp, C.c_char_p]),
+        "pm_dict_load": (vp, [C.c_char_p]),
+        "pm_dict_compile_files_cached": (vp, [C.POINTER(C.c_char_p), C.c_int, C.c_char_p]),
         "pm_dict_pattern": (C.c_int, [vp, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64), C.POINTER(u32),
                                       C.POINTER(u32), C.POINTER(C.POINTER(C.c_ubyte))]),
         "pm_dict_is_pattern_suffix": (C.c_int, [vp, u32, u32]),
@@ -149,6 +152,32 @@ class Dictionary:
                 self.h = None
         except Exception:
             pass
+
+    def save(self, path):
+        if self.L.pm_dict_save(self.h, os.fsencode(path)) != 0:
+            raise _err(self.L, "pm_dict_save")
+
+    @classmethod
+    def load(cls, path):
+        self = cls.__new__(cls)
+        self.L = lib()
+        self.h = self.L.pm_dict_load(os.fsencode(path))
+        if not self.h:
+            raise _err(self.L, "pm_dict_load")
+        self.compiled = True
+        return self
+
+    @classmethod
+    def from_files_cached(cls, paths, cache_dir):
+        """Load the compiled tables from <cache_dir>/pmdict-<hash of the files>.bin, or compile and store them."""
+        self = cls.__new__(cls)
+        self.L = lib()
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        self.h = self.L.pm_dict_compile_files_cached(arr, len(paths), os.fsencode(cache_dir))
+        if not self.h:
+            raise _err(self.L, "pm_dict_compile_files_cached")
+        self.compiled = True
+        return self
 
     def add_file(self, path):
         if self.L.pm_dict_add_file(self.h, os.fsencode(path)) != 0:

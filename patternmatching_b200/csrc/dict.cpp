@@ -322,6 +322,13 @@ int Dict::compile() {
 // delta(s,c) = goto(s,c) if present else delta(fail(s),c); longest(s) = id[suffix_link(s)].
 void Dict::build_dfa() {
     if (dfa.built) return;
+    if (fwd_->size() == 1 && !pats.empty()) {  // loaded from a cache file: the forward trie is rebuilt from the patterns
+        for (uint32_t i = 0; i < pats.size(); ++i) {
+            uint32_t st = 0;
+            for (uint32_t k = 0; k < pats[i].len; ++k) st = fwd_->child_or_add(st, bytes[pats[i].off + k]);
+            fwd_->term[st] = i + 1;
+        }
+    }
     Bfs t(fwd_->edge, fwd_->term);
     DfaTables& d = dfa;
     d.n_states = t.n;
@@ -353,6 +360,68 @@ void Dict::build_dfa() {
         }
     }
     d.built = true;
+}
+
+// ---- compiled-automaton cache -----------------------------------------------------------------
+namespace {
+constexpr char kMagic[8] = {'P', 'M', 'B', '2', 'D', 'I', 'C', '1'};
+template <class T>
+bool put(FILE* f, const std::vector<T>& v) {
+    const uint64_t n = v.size();
+    return fwrite(&n, 8, 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n);
+}
+template <class T>
+bool get(FILE* f, std::vector<T>& v) {
+    uint64_t n = 0;
+    if (fread(&n, 8, 1, f) != 1 || n > (uint64_t(1) << 32)) return false;
+    v.resize(n);
+    return n == 0 || fread(v.data(), sizeof(T), n, f) == n;
+}
+struct Scalars {
+    uint64_t n_lines, n_rejected, n_dups;
+    uint32_t n_files, max_len, n_ac_states;
+    uint32_t n_nodes, n_rows, n_tail_nodes, row2_base, n2_cont, cont_base, fits_u16, n_classes, log2_ncp;
+    uint8_t cls[256];
+};
+}  // namespace
+
+int Dict::save(const char* path) const {
+    if (!compiled) return -1;
+    FILE* f = fopen(path, "wb");
+    if (!f) return -1;
+    Scalars sc{};
+    sc.n_lines = n_lines; sc.n_rejected = n_rejected; sc.n_dups = n_dups;
+    sc.n_files = n_files; sc.max_len = max_len; sc.n_ac_states = n_ac_states;
+    sc.n_nodes = sfx.n_nodes; sc.n_rows = sfx.n_rows; sc.n_tail_nodes = sfx.n_tail_nodes; sc.row2_base = sfx.row2_base;
+    sc.n2_cont = sfx.n2_cont; sc.cont_base = sfx.cont_base; sc.fits_u16 = sfx.fits_u16; sc.n_classes = sfx.n_classes;
+    sc.log2_ncp = sfx.log2_ncp;
+    memcpy(sc.cls, sfx.cls, 256);
+    bool ok = fwrite(kMagic, 8, 1, f) == 1 && fwrite(&sc, sizeof(sc), 1, f) == 1 && put(f, pats) && put(f, bytes) &&
+              put(f, anc_off) && put(f, anc_list) && put(f, sfx.root2) && put(f, sfx.l3f) && put(f, sfx.root1) &&
+              put(f, sfx.rows) && put(f, sfx.row_best) && put(f, sfx.tail_rec) && put(f, sfx.depth_hist);
+    ok = (fclose(f) == 0) && ok;
+    return ok ? 0 : -1;
+}
+
+int Dict::load(const char* path) {
+    if (compiled || !pats.empty()) { error = "load needs an empty dictionary"; return -1; }
+    FILE* f = fopen(path, "rb");
+    if (!f) { error = std::string("cannot open ") + path; return -1; }
+    char magic[8];
+    Scalars sc{};
+    bool ok = fread(magic, 8, 1, f) == 1 && memcmp(magic, kMagic, 8) == 0 && fread(&sc, sizeof(sc), 1, f) == 1 &&
+              get(f, pats) && get(f, bytes) && get(f, anc_off) && get(f, anc_list) && get(f, sfx.root2) && get(f, sfx.l3f) &&
+              get(f, sfx.root1) && get(f, sfx.rows) && get(f, sfx.row_best) && get(f, sfx.tail_rec) && get(f, sfx.depth_hist);
+    fclose(f);
+    if (!ok) { error = std::string("not a compiled dictionary (or truncated): ") + path; return -1; }
+    n_lines = sc.n_lines; n_rejected = sc.n_rejected; n_dups = sc.n_dups;
+    n_files = sc.n_files; max_len = sc.max_len; n_ac_states = sc.n_ac_states;
+    sfx.n_nodes = sc.n_nodes; sfx.n_rows = sc.n_rows; sfx.n_tail_nodes = sc.n_tail_nodes; sfx.row2_base = sc.row2_base;
+    sfx.n2_cont = sc.n2_cont; sfx.cont_base = sc.cont_base; sfx.fits_u16 = sc.fits_u16 != 0; sfx.n_classes = sc.n_classes;
+    sfx.log2_ncp = sc.log2_ncp;
+    memcpy(sfx.cls, sc.cls, 256);
+    compiled = true;
+    return 0;
 }
 
 void Dict::build_kr(uint64_t seed) {

@@ -100,6 +100,9 @@ class Dict {
     void build_dfa();                 // lazily, the table is large (n_states * 256 * 4 bytes)
     void build_kr(uint64_t seed);
     bool is_pattern_suffix(uint32_t first, uint32_t second) const;
+    // compiled-automaton cache: the compiled dictionary as one binary file
+    int save(const char* path) const;
+    int load(const char* path);
 
     // ---- data ----
     std::vector<Pattern> pats;        // pats[pid-1]

@@ -306,6 +306,47 @@ int pm_dict_compile(pm_dict* d) {
     if (!d->d.sfx.fits_u16) return fail("dictionary too large for dense uint16 results (needs P + #2-byte-continuations < 65536)");
     return 0;
 }
+int pm_dict_save(const pm_dict* d, const char* path) {
+    if (d->d.save(path)) return fail(std::string("pm_dict_save: cannot write ") + path);
+    return 0;
+}
+pm_dict* pm_dict_load(const char* path) {
+    pm_dict* d = new (std::nothrow) pm_dict();
+    if (!d) return nullptr;
+    if (d->d.load(path)) { fail(d->d.error); delete d; return nullptr; }
+    return d;
+}
+// FNV-1a over the names' order, sizes and contents of the dictionary files: the cache key
+static uint64_t hash_files(const char* const* paths, int n, bool* ok) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t len) { const uint8_t* b = static_cast<const uint8_t*>(p); for (size_t i = 0; i < len; ++i) { h ^= b[i]; h *= 1099511628211ull; } };
+    *ok = true;
+    for (int i = 0; i < n; ++i) {
+        FILE* f = fopen(paths[i], "rb");
+        if (!f) { *ok = false; return 0; }
+        uint8_t buf[1 << 16];
+        size_t got; uint64_t total = 0;
+        while ((got = fread(buf, 1, sizeof(buf), f)) > 0) { mix(buf, got); total += got; }
+        fclose(f);
+        mix(&total, 8); mix(&i, sizeof(i));
+    }
+    return h;
+}
+pm_dict* pm_dict_compile_files_cached(const char* const* paths, int n, const char* cache_dir) {
+    bool ok = false;
+    const uint64_t key = hash_files(paths, n, &ok);
+    if (!ok) { fail("pm_dict_compile_files_cached: cannot read a dictionary file"); return nullptr; }
+    char name[64];
+    snprintf(name, sizeof(name), "/pmdict-%016llx.bin", (unsigned long long)key);
+    const std::string file = std::string(cache_dir ? cache_dir : ".") + name;
+    if (pm_dict* d = pm_dict_load(file.c_str())) return d;
+    pm_dict* d = pm_dict_create();
+    for (int i = 0; i < n; ++i) if (pm_dict_add_file(d, paths[i])) { pm_dict_free(d); return nullptr; }
+    if (pm_dict_compile(d)) { pm_dict_free(d); return nullptr; }
+    d->d.save(file.c_str());  // best effort: an unwritable cache directory only costs the next compile
+    g_err.clear();
+    return d;
+}
 int pm_dict_get_info(const pm_dict* d, pm_dict_info* info) {
     const pm::Dict& x = d->d;
     memset(info, 0, sizeof(*info));

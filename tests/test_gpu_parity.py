@@ -318,3 +318,39 @@ def test_auto_picks_the_kernel_from_a_sample(oracle_merged, engine_merged):
     assert eng.auto_choice == pm.ALGO_DFA and np.array_equal(got, want_pids(o, stream))
     eng.reset()
     assert eng.auto_choice == -1
+
+
+def test_edge_dictionaries():
+    """Single-byte patterns, NUL bytes, all 256 byte values, the longest supported pattern, repetitive streams."""
+    rng = np.random.default_rng(11)
+    cases = []
+    cases.append([b"\x00"])                                              # one 1-byte pattern, the NUL byte
+    cases.append([bytes([b]) for b in range(256) if b != 10])           # every byte value (newline is the line separator)
+    cases.append([b"\x00" * k for k in (1, 2, 3, 7, 8, 9, 64, 353)])    # nested NUL runs up to the supported maximum (353)
+    cases.append([b"abcabcabc", b"bcabc", b"cabca", b"abc", b"c", bytes(rng.integers(0, 256, 353, dtype=np.uint8)).replace(b"\n", b"x")])
+    for pats in cases:
+        d = pm.Dictionary(); o = Oracle()
+        for i, p in enumerate(pats):
+            d.add_pattern(p, 0, i + 1); o.add_pattern(p, 0, i + 1)
+        d.compile(); o.compile()
+        eng = pm.Engine(d)
+        streams = [np.zeros(5000, np.uint8), np.frombuffer(b"abc" * 3000, np.uint8),
+                   rng.integers(0, 4, 20000, dtype=np.uint8), np.concatenate([np.frombuffer(p, np.uint8) for p in pats] * 3)]
+        for stream in streams:
+            want = want_pids(o, stream)
+            for algo in EXACT + [pm.ALGO_AUTO]:
+                assert np.array_equal(gpu_scan(eng, stream, algo), want)
+
+
+def test_cached_dictionary_scans_identically(tmp_path, dict_merged, oracle_merged):
+    """A dictionary loaded from the compiled-automaton cache drives all three kernels like a freshly compiled one
+    (the DFA and KR tables are rebuilt lazily from the cached patterns)."""
+    f = tmp_path / "merged.bin"
+    dict_merged.save(str(f))
+    eng = pm.Engine(pm.Dictionary.load(str(f)))
+    stream = oracle_merged.gen("planted", 4096 * 11, 1 << 20)
+    want = want_pids(oracle_merged, stream)
+    for algo in EXACT:
+        assert np.array_equal(gpu_scan(eng, stream, algo), want)
+    kr = gpu_scan(eng, stream, pm.ALGO_KR)
+    assert np.array_equal(kr, (oracle_merged.kr_scan(stream, 0xF1A90003) + 1).astype(np.uint16))

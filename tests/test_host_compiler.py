@@ -93,3 +93,40 @@ def test_tiny_dictionary_shape():
     o = Oracle(); o.add_dict_bytes(TINY_DICT); o.compile()
     assert d.n_patterns == 11 and d.info.n_rejected == 2 and d.info.n_ac_states == o.n_states
     assert d.info.n_classes < 256                           # alphabet compression: unused bytes share class 0
+
+
+def test_limits_are_reported_not_silently_truncated():
+    d = pm.Dictionary()
+    d.add_pattern(b"x" * 354, 0, 1)                                      # one byte over the supported maximum
+    with pytest.raises(pm.PmError, match="longer than the supported maximum"):
+        d.compile()
+    d = pm.Dictionary()                                                  # more patterns than dense uint16 results can name
+    for i in range(66000):
+        d.add_pattern(b"%07d" % i, 0, i + 1)
+    with pytest.raises(pm.PmError, match="too large for dense uint16"):
+        d.compile()
+
+
+def test_compiled_dictionary_cache_round_trip(tmp_path, dict_merged):
+    """the compiled tables survive a save/load round trip and the content-keyed cache is reused."""
+    import time
+    f = tmp_path / "merged.bin"
+    dict_merged.save(str(f))
+    d2 = pm.Dictionary.load(str(f))
+    a, b = dict_merged.info, d2.info
+    for field, _ in pm.DictInfo._fields_:
+        assert getattr(a, field) == getattr(b, field), field
+    for pid in (1, 2, 777, 40000, a.n_patterns):
+        assert dict_merged.pattern(pid) == d2.pattern(pid)
+    paths = dict_paths("merged")
+    t0 = time.time(); d3 = pm.Dictionary.from_files_cached(paths, str(tmp_path)); t_cold = time.time() - t0
+    t0 = time.time(); d4 = pm.Dictionary.from_files_cached(paths, str(tmp_path)); t_warm = time.time() - t0
+    assert d3.info.n_patterns == d4.info.n_patterns == a.n_patterns and d4.info.n_sfx_rows == a.n_sfx_rows
+    assert len([x for x in os.listdir(tmp_path) if x.startswith("pmdict-")]) == 1
+    assert d4.pattern(31337) == dict_merged.pattern(31337)
+    # a different file order is a different dictionary (file numbers differ): different key
+    pm.Dictionary.from_files_cached(paths[::-1], str(tmp_path))
+    assert len([x for x in os.listdir(tmp_path) if x.startswith("pmdict-")]) == 2
+    with pytest.raises(pm.PmError):
+        bad = tmp_path / "bad.bin"; bad.write_bytes(b"not a dictionary"); pm.Dictionary.load(str(bad))
+    print(f"cold {t_cold:.2f}s warm {t_warm:.2f}s")
