@@ -234,6 +234,7 @@ int Dict::compile() {
     uint32_t next_cls = (n_used == 256) ? 0 : 1;
     for (int b = 0; b < 256; ++b) x.cls[b] = used[b] ? uint8_t(next_cls++) : 0;
     x.n_classes = next_cls ? next_cls : 1;
+    x.cls_identity = (n_used == 256);
     x.log2_ncp = 0;
     while ((1u << x.log2_ncp) < x.n_classes) ++x.log2_ncp;
 
@@ -420,6 +421,8 @@ int Dict::load(const char* path) {
     sfx.n2_cont = sc.n2_cont; sfx.cont_base = sc.cont_base; sfx.fits_u16 = sc.fits_u16 != 0; sfx.n_classes = sc.n_classes;
     sfx.log2_ncp = sc.log2_ncp;
     memcpy(sfx.cls, sc.cls, 256);
+    sfx.cls_identity = true;
+    for (int b = 0; b < 256; ++b) sfx.cls_identity = sfx.cls_identity && sfx.cls[b] == b;
     compiled = true;
     return 0;
 }

@@ -45,6 +45,7 @@ struct SfxTables {
     uint32_t n_classes = 0;      // byte classes used by the rows (class 0 = "byte occurs in no pattern" if any)
     uint32_t log2_ncp = 0;       // row stride = 1 << log2_ncp >= n_classes
     uint8_t cls[256] = {0};
+    bool cls_identity = false;   // cls[b] == b for every byte (all 256 byte values occur in patterns)
     std::vector<uint16_t> root2; // [c_i << 8 | c_{i-1}] -> final pid, or continue code
     // level-3 filter, one word per depth-2 row (index = continue code - cont_base): high half = deepest terminal
     // at the depth-2 node (the answer when c[i-2] leads nowhere), low half = 16-bit Bloom of the bytes that DO

@@ -231,7 +231,7 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
         pm::SfxParams p{};
         p.stream = d_stream; p.n = n; p.hist_valid = hist_valid; p.out = d_out;
         if (fill_sfx_params(e, &p, n, slot)) return -1;
-        const bool ident = d.sfx.n_classes == 256;
+        const bool ident = d.sfx.cls_identity;
         cudaEvent_t* ev = nullptr;
         if (e->profiling) {
             if (e->prof_used + 3 > e->prof_events.size()) {
@@ -256,7 +256,7 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
         p.warm = d.max_len ? d.max_len - 1 : 0;
         pm::dfa_plan_hot(d.dfa.n_states, d.dfa.log2_ncp, d.dfa.depth_count.data(), uint32_t(d.dfa.depth_count.size()),
                          &p.hot_rows, &p.hot_long);
-        cudaError_t ce = pm::dfa_scan_launch(p, d.dfa.n_classes == 256, force_flat || getenv("PM_DFA_FLAT") != nullptr, e->n_sms, st, &e->launches);
+        cudaError_t ce = pm::dfa_scan_launch(p, d.sfx.cls_identity, force_flat || getenv("PM_DFA_FLAT") != nullptr, e->n_sms, st, &e->launches);
         if (ce != cudaSuccess) return cuda_fail(ce, "dfa_scan_launch");
         return 0;
     }
@@ -267,7 +267,7 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
         pm::SfxParams p{};
         p.stream = d_stream; p.n = n; p.hist_valid = hist_valid; p.out = d_out;
         if (fill_sfx_params(e, &p, n, slot)) return -1;
-        cudaError_t ce = pm::sfx_scan_launch(p, d.sfx.n_classes == 256, e->n_sms, d.max_len, st, &e->launches);
+        cudaError_t ce = pm::sfx_scan_launch(p, d.sfx.cls_identity, e->n_sms, d.max_len, st, &e->launches);
         if (ce != cudaSuccess) return cuda_fail(ce, "sfx_scan_launch");
         ce = pm::kr_scan_launch(e->kr, d_stream, n, hist_valid, d_out, e->pt, e->n_sms, st, &e->launches);
         if (ce != cudaSuccess) return cuda_fail(ce, "kr_scan_launch");

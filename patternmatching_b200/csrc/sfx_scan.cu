@@ -374,10 +374,13 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
 // and pulls its next item the moment its current one ends; one pass of the loop = at most one dependent
 // memory step (a row lookup, an 8-byte tail compare, or a step up the PatternsTree chain).
 __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
-    // CTA b drains the strip of scan CTA b, its threads round-robin over the items
-    const uint64_t* q_strip = p.queue + size_t(blockIdx.x) * p.q_per_cta;
-    const uint32_t count = p.qcount[blockIdx.x];
-    uint32_t q = threadIdx.x;
+    // CTAs 2b and 2b+1 drain the strip of scan CTA b (two 1024-thread CTAs per SM: twice the walks in flight),
+    // their threads round-robin over the items
+    const uint32_t strip = blockIdx.x >> 1;
+    const uint64_t* q_strip = p.queue + size_t(strip) * p.q_per_cta;
+    const uint32_t count = p.qcount[strip];
+    const uint32_t q_stride = 2 * blockDim.x;
+    uint32_t q = threadIdx.x + (blockIdx.x & 1) * blockDim.x;
     enum { kFetch = 0, kRow = 1, kTailCmp = 2, kChain = 3 };
     int state = kFetch;
     uint32_t v = 0, len = 0, next_term = 0, best_start = 0, cand = 0;
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
         if (state == kFetch) {
             if (q >= count) break;  // this lane has run out of items
             const uint64_t item = q_strip[q];
-            q += blockDim.x;
+            q += q_stride;
             pos = item >> 25;
             v = ((item >> 24) & 1 ? kTail : kCont) | uint32_t(item & 0xFFFFFFu);
             k = 4;
@@ -478,7 +481,7 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     {
-        sfx_deep_kernel<<<grid, 1024, 0, st>>>(p);  // CTA b drains the strip of scan CTA b
+        sfx_deep_kernel<<<grid * 2, 1024, 0, st>>>(p);  // CTAs 2b, 2b+1 drain the strip of scan CTA b
         ++*launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
