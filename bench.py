@@ -216,6 +216,23 @@ def main():
     from patternmatching_b200 import multi
     red = multi.reduce_summary(s, dist, dev)       # sums over ranks (NCCL all_reduce): the only collective
 
+    # the multi-GPU gather of SURVEY 8(e), on a bounded slice (first 16 MiB of every rank's result): compact the
+    # dense slice to position-sorted (pos << 24 | pid) records on the device, all-gather the counts, then the
+    # variable-length record lists (NCCL when N > 1); rank order is position order.
+    ng = min(16 << 20, n)
+    cap = ng
+    rec = torch.empty(cap, dtype=torch.int64, device=dev)
+    cnt = eng.compact(out, ng, rec, cap, pos_base=off)
+    torch.cuda.synchronize()
+    tg0 = time.perf_counter()
+    allrec = multi.gather_records(rec[:cnt], dist, dev)
+    torch.cuda.synchronize()
+    gather_ms = (time.perf_counter() - tg0) * 1e3
+    pos_all = allrec >> 24
+    gather_info = {"records": int(allrec.numel()), "slice_bytes_per_rank": ng, "ms": round(gather_ms, 3),
+                   "position_sorted": bool((pos_all[1:] > pos_all[:-1]).all().item()) if allrec.numel() > 1 else True}
+    del rec, allrec, pos_all
+
     # end to end through the public host-buffer call: pinned input, H2D, scan, D2H of the dense result
     ne = min(args.e2e_mib << 20, n)
     hin = pm.PinnedBuffer(ne); hout = pm.PinnedBuffer(2 * ne)
@@ -279,6 +296,7 @@ def main():
         "result_check": {"positions_with_match": red["positions"], "matches_with_ancestors": red["matches"],
                          "digest_sum_longest": "%016x" % red["hsum_longest"], "digest_sum_all": "%016x" % red["hsum_all"],
                          "note": "sums over all ranks; equal to one continuous scan of the whole stream"},
+        "record_gather": gather_info,
     }
     if not args.no_cpu_baseline:
         try:

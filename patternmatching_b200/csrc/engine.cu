@@ -50,7 +50,11 @@ cudaError_t upload(const std::vector<T>& v, T** dptr, size_t* total) {
 }
 constexpr size_t kMaxCtas = 1024;  // upper bound of scan CTAs per launch (one per SM)
 constexpr size_t kPatPad = 16;  // zero bytes in front of the device copy of the pattern text (8-byte windows)
-constexpr size_t kHostChunk = size_t(16) << 20;  // bytes per pipeline slot of pm_engine_scan_host
+const size_t kHostChunk = [] {  // bytes per pipeline slot of pm_engine_scan_host (PM_HOST_CHUNK_MIB, default 16)
+    const char* v = getenv("PM_HOST_CHUNK_MIB");
+    const long m = v ? atol(v) : 16;
+    return size_t(m >= 1 && m <= 1024 ? m : 16) << 20;
+}();
 }  // namespace
 
 struct pm_engine {
