@@ -13,7 +13,7 @@
 //   2. builds the prefix fingerprints PHI(x) = sum_{t<=x} s[t] r^t mod p with a block-wide modular
 //      prefix sum (per-thread serial part, warp-shuffle scan, cross-warp scan),
 //   3. for every position forms the fingerprint of the last 8 bytes, (PHI(x)-PHI(x-8)) r^-(x-7),
-//      tests it against a 64 KiB Bloom bitmap in shared memory, and only on a hit probes the
+//      tests it against a 64 KiB two-hash Bloom bitmap in shared memory, and only on a hit probes the
 //      open-addressing table of 8-byte-suffix fingerprints in global memory and verifies the
 //      candidates stage by stage (16, 32, ... bytes, then the full length), longest first.
 // A pattern > 8 bytes is reported iff ALL its stage fingerprints agree; a false positive needs a
@@ -24,7 +24,7 @@
 namespace pm {
 namespace {
 
-constexpr int kThreads = 1024;
+constexpr int kThreads = 512;                                  // two CTAs per SM: one computes while the other waits at a barrier
 constexpr int kSpan = kHalo + kKrTile;                        // staged bytes
 constexpr int kElems = (kSpan + kThreads - 1) / kThreads;     // elements per thread in the prefix sum (9)
 constexpr int kPosPer = kKrTile / kThreads;                   // reported positions per thread (8)
@@ -72,7 +72,7 @@ __device__ __noinline__ uint32_t kr_verify(const KrDevTables& t, const uint32_t*
     return 0;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) {
+__global__ void __launch_bounds__(kThreads, 2) kr_scan_kernel(const KrParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* s_bloom = reinterpret_cast<uint32_t*>(smem + kOffBloom);
     uint32_t* s_phi = reinterpret_cast<uint32_t*>(smem + kOffPhi);
@@ -99,19 +99,34 @@ __global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) 
             mbar_arrive_expect_tx(bar, bytes);
             if (bytes) bulk_g2s(s_bytes + (halo ? 0 : kHalo), p.stream + s0 - (halo ? kHalo : 0), bytes, bar);
         }
+        // exact results of this tile's positions -> "longest pattern of <= 8 bytes" (two dependent global loads):
+        // issued now, consumed after the prefix sum, so their latency hides behind the tile load and the scan
+        uint32_t short_pid[kPosPer];
+#pragma unroll
+        for (int k = 0; k < kPosPer; ++k) {
+            const uint32_t q = uint32_t(k) * kThreads + tid;
+            short_pid[k] = q < len ? uint32_t(p.out[s0 + q]) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < kPosPer; ++k) short_pid[k] = __ldg(p.t.short_of + short_pid[k]);
         if (!halo) for (int i = tid; i < kHalo; i += kThreads) s_bytes[i] = 0;
         if (uint32_t(tid) < (len & 15u)) s_bytes[kHalo + body + tid] = p.stream[s0 + body + tid];
         mbar_wait(bar, it & 1);
         __syncthreads();
 
         // ---- block-wide modular prefix sum of s[x] * r^x ----
+        // pass 1, interleaved mapping (coalesced reads of the power table): the terms go to s_phi[x + 1]
+        for (int x = tid; x < kSpan; x += kThreads) s_phi[x + 1] = kr_mulmod(s_bytes[x], __ldg(p.t.rpow + x));
+        __syncthreads();
+        // pass 2, blocked mapping: every thread sums its kElems consecutive terms (stride-kElems reads, kElems odd:
+        // conflict-free), then the thread totals are scanned across the block
         uint32_t loc[kElems];
         uint32_t acc = 0;
         const int x0 = tid * kElems;
 #pragma unroll
         for (int k = 0; k < kElems; ++k) {
             const int x = x0 + k;
-            const uint32_t term = x < kSpan ? kr_mulmod(s_bytes[x], __ldg(p.t.rpow + x)) : 0u;
+            const uint32_t term = x < kSpan ? s_phi[x + 1] : 0u;
             acc = kr_addmod(acc, term);
             loc[k] = acc;
         }
@@ -144,36 +159,26 @@ __global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) 
         __syncthreads();
 
         // ---- per position: stage-8 fingerprint, Bloom test, verification ----
-        const int q0 = tid * kPosPer;
-        if (uint32_t(q0) < len) {
-            const uint64_t i0 = s0 + q0;
-            uint32_t res[kPosPer];
+        // position k * kThreads + tid: consecutive lanes take consecutive positions, so the PHI reads are
+        // conflict-free (a blocked mapping would be an 8- or 16-way bank conflict) and the result stores coalesce
 #pragma unroll
-            for (int k = 0; k < kPosPer; ++k) {
-                res[k] = 0;
-                if (uint32_t(q0 + k) < len) {
-                    const uint32_t exact = p.out[i0 + k];
-                    uint32_t r = __ldg(p.t.short_of + exact);
-                    const uint64_t avail = i0 + k + p.hist_valid + 1;  // bytes of the stream up to and incl. c[i]
-                    if (avail >= 9) {
-                        const int x = kHalo + q0 + k;
-                        const uint32_t f8 = win_fp(s_phi, p.t.rinvpow, x, 8);
-                        const uint32_t bit = f8 & ((1u << 19) - 1);
-                        if ((s_bloom[bit >> 5] >> (bit & 31)) & 1u) {
-                            const uint32_t hit = kr_verify(p.t, s_phi, x, f8, avail);
-                            if (hit) r = hit;
-                        }
+        for (int k = 0; k < kPosPer; ++k) {
+            const uint32_t q = uint32_t(k) * kThreads + tid;
+            if (q < len) {
+                const uint64_t i = s0 + q;
+                uint32_t r = short_pid[k];
+                const uint64_t avail = i + p.hist_valid + 1;  // bytes of the stream up to and incl. c[i]
+                if (avail >= 9) {
+                    const int x = kHalo + int(q);
+                    const uint32_t f8 = win_fp(s_phi, p.t.rinvpow, x, 8);
+                    const uint32_t bit = f8 & ((1u << 19) - 1);
+                    const uint32_t bit2 = (f8 >> 12) & ((1u << 19) - 1);
+                    if (((s_bloom[bit >> 5] >> (bit & 31)) & 1u) && ((s_bloom[bit2 >> 5] >> (bit2 & 31)) & 1u)) {
+                        const uint32_t hit = kr_verify(p.t, s_phi, x, f8, avail);
+                        if (hit) r = hit;
                     }
-                    res[k] = r;
                 }
-            }
-            if (uint32_t(q0 + kPosPer) <= len) {
-                uint4 v;
-                v.x = res[0] | (res[1] << 16); v.y = res[2] | (res[3] << 16);
-                v.z = res[4] | (res[5] << 16); v.w = res[6] | (res[7] << 16);
-                *reinterpret_cast<uint4*>(p.out + i0) = v;
-            } else {
-                for (int k = 0; k < kPosPer; ++k) if (uint32_t(q0 + k) < len) p.out[i0 + k] = uint16_t(res[k]);
+                p.out[i] = uint16_t(r);
             }
         }
         __syncthreads();  // s_bytes / s_phi are rewritten by the next tile
@@ -229,7 +234,7 @@ cudaError_t kr_scan_launch(const KrDevTables& t, const uint8_t* stream, uint64_t
     p.n_tiles = uint32_t((n + kKrTile - 1) / kKrTile);
     cudaError_t e = cudaFuncSetAttribute(kr_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return e;
-    const uint32_t grid = p.n_tiles < uint32_t(n_sms) ? p.n_tiles : uint32_t(n_sms);
+    const uint32_t grid = p.n_tiles < uint32_t(2 * n_sms) ? p.n_tiles : uint32_t(2 * n_sms);
     kr_scan_kernel<<<grid, kThreads, kSmem, st>>>(p);
     ++*launches;
     return cudaGetLastError();
