@@ -373,6 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
 // 90% of the lanes idle behind the longest chain of their warp.  Instead every lane runs a small state machine
 // and pulls its next item the moment its current one ends; one pass of the loop = at most one dependent
 // memory step (a row lookup, an 8-byte tail compare, or a step up the PatternsTree chain).
+template <bool kIdentCls>
 __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
     // CTAs 2b and 2b+1 drain the strip of scan CTA b (two 1024-thread CTAs per SM: twice the walks in flight),
     // their threads round-robin over the items
@@ -383,8 +384,9 @@ __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
     uint32_t q = threadIdx.x + (blockIdx.x & 1) * blockDim.x;
     enum { kFetch = 0, kRow = 1, kTailCmp = 2, kChain = 3 };
     int state = kFetch;
-    uint32_t v = 0, len = 0, next_term = 0, best_start = 0, cand = 0;
+    uint32_t v = 0, len = 0, next_term = 0, best_start = 0, cand = 0, hist_left = 0;
     uint64_t pos = 0, k = 0, avail = 0, lim = 0;
+    uint64_t hist = 0;  // the next stream bytes of the walk, c[i-k] in the top byte: one 8-byte load per 8 row steps
     const uint8_t* ci = nullptr;
     const uint8_t* text = nullptr;
     for (;;) {
@@ -398,6 +400,7 @@ __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
             ci = p.stream + pos;
             avail = pos + p.hist_valid + 1;
             state = (v & kCont) ? kRow : kTailCmp;
+            if (state == kRow && avail > 4) { hist = load8_ending_at(ci - 4, ci - (avail - 1)); hist_left = 8; }
             if (state == kTailCmp) {
                 const uint4 rec = __ldg(p.tail_rec + (v & 0xFFFFu));
                 text = p.pat_bytes + rec.x; len = rec.y; next_term = rec.z; best_start = rec.w;
@@ -409,7 +412,11 @@ __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
                 p.out[pos] = uint16_t(__ldg(p.row_best + row));
                 state = kFetch;
             } else {
-                v = __ldg(p.rows + ((size_t(row) << p.log2_ncp) | __ldg(p.cls + *(ci - k))));
+                if (hist_left == 0) { hist = load8_ending_at(ci - k, ci - (avail - 1)); hist_left = 8; }
+                uint32_t c = uint32_t(hist >> 56);
+                hist <<= 8; --hist_left;
+                if constexpr (!kIdentCls) c = __ldg(p.cls + c);
+                v = __ldg(p.rows + ((size_t(row) << p.log2_ncp) | c));
                 ++k;
                 if (v & kTail) {
                     const uint4 rec = __ldg(p.tail_rec + (v & 0xFFFFu));
@@ -481,7 +488,8 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     {
-        sfx_deep_kernel<<<grid * 2, 1024, 0, st>>>(p);  // CTAs 2b, 2b+1 drain the strip of scan CTA b
+        auto deep = ident_cls ? sfx_deep_kernel<true> : sfx_deep_kernel<false>;
+        deep<<<grid * 2, 1024, 0, st>>>(p);  // CTAs 2b, 2b+1 drain the strip of scan CTA b
         ++*launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
