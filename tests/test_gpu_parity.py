@@ -354,3 +354,36 @@ def test_cached_dictionary_scans_identically(tmp_path, dict_merged, oracle_merge
         assert np.array_equal(gpu_scan(eng, stream, algo), want)
     kr = gpu_scan(eng, stream, pm.ALGO_KR)
     assert np.array_equal(kr, (oracle_merged.kr_scan(stream, 0xF1A90003) + 1).astype(np.uint16))
+
+
+def test_full_size_16gib_properties(engine_merged):
+    """BASELINE.json configs[2] at full size (16 GiB, S-planted): properties that do not need the CPU oracle --
+    (1) the digest sums of a 4-way sharded scan with halo equal the single scan's (linearity; shards invisible),
+    (2) on four 64 MiB windows the forward-DFA kernel reproduces the backward scan bit for bit,
+    (3) counts are in the range the generator implies (>= 0.70 of the positions match on uniform bytes)."""
+    torch, dev = torch_dev()
+    free, _ = torch.cuda.mem_get_info()
+    n = 16 << 30
+    if free < 3 * n + (8 << 30):
+        pytest.skip("not enough free device memory for the 16 GiB configuration")
+    buf = torch.empty(n, dtype=torch.uint8, device=dev)
+    engine_merged.generate("planted", 0, n, buf)
+    out = torch.empty(n, dtype=torch.int16, device=dev)
+    engine_merged.scan_device(buf, n, out, algo=pm.ALGO_SFX)
+    whole = engine_merged.summarize(out, n)
+    assert 0.70 * n < whole["positions"] < 0.72 * n and whole["matches"] > whole["positions"]
+    acc = dict(positions=0, matches=0, hsum_longest=0, hsum_all=0)
+    part = torch.empty(n // 4, dtype=torch.int16, device=dev)
+    for k in range(4):
+        lo = k * (n // 4)
+        engine_merged.scan_device(buf.data_ptr() + lo, n // 4, part, hist_valid=min(lo, pm.HALO), algo=pm.ALGO_SFX)
+        s = engine_merged.summarize(part, n // 4, pos_base=lo)
+        for key in acc:
+            acc[key] = (acc[key] + s[key]) % (1 << 64)
+        assert bool(torch.equal(part, out[lo:lo + n // 4]))
+    assert acc == whole
+    w = 64 << 20
+    chk = torch.empty(w, dtype=torch.int16, device=dev)
+    for lo in (0, 5 * w + 4096, n // 2, n - w):
+        engine_merged.scan_device(buf.data_ptr() + lo, w, chk, hist_valid=min(lo, pm.HALO), algo=pm.ALGO_DFA)
+        assert bool(torch.equal(chk, out[lo:lo + w])), lo

@@ -130,3 +130,22 @@ def test_compiled_dictionary_cache_round_trip(tmp_path, dict_merged):
     with pytest.raises(pm.PmError):
         bad = tmp_path / "bad.bin"; bad.write_bytes(b"not a dictionary"); pm.Dictionary.load(str(bad))
     print(f"cold {t_cold:.2f}s warm {t_warm:.2f}s")
+
+
+def test_plugin_registration_fills_an_mpselem():
+    """mps_gpu_register_into fills a struct laid out like MpsElem (Core/src/mps.h:71-80) with the seven callbacks."""
+    L = pm.lib()
+    for fn, name in ((L.mps_gpu_register_into, b"B200 exact dictionary scan"),
+                     (L.mps_gpu_dfa_register_into, b"B200 Aho-Corasick DFA"),
+                     (L.mps_gpu_kr_register_into, b"B200 Karp-Rabin stages")):
+        e = pm.MpsElemStruct()
+        fn(C.byref(e))
+        assert e.name == name
+        for field in ("create", "add_pattern", "compile", "read_char", "total_mem", "reset", "free"):
+            assert C.cast(getattr(e, field), C.c_void_p).value, field
+    # create / add_pattern work without a GPU (compile needs the device)
+    e = pm.MpsElemStruct(); L.mps_gpu_register_into(C.byref(e))
+    obj = e.create()
+    e.add_pattern(obj, b"a\x00b", 3, 0x1234)
+    assert e.total_mem(obj) == 0
+    e.free(obj)
