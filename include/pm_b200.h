@@ -96,7 +96,10 @@ enum {
     PM_STREAM_ASCII   = 4  /* uniform printable ASCII 0x20..0x7E (text-like traffic) */
 };
 
-/* Upload the compiled tables to CUDA device `device`.  NULL (and pm_last_error) when there is no
+/* Thread safety: a pm_dict is read-only once compiled; the pm_engine entry points are serialised per engine by an
+ * internal mutex (an engine holds ONE stream state and shared scratch buffers) -- use one engine per concurrent
+ * stream; engines of the same dictionary share nothing on the device but cost only 61 MB each.
+ * Upload the compiled tables to CUDA device `device`.  NULL (and pm_last_error) when there is no
  * usable device: there is no CPU fallback. */
 pm_engine* pm_engine_create(const pm_dict* d, int device);
 void pm_engine_free(pm_engine* e);

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -58,6 +59,7 @@ const size_t kHostChunk = [] {  // bytes per pipeline slot of pm_engine_scan_hos
 }  // namespace
 
 struct pm_engine {
+    std::mutex mu;  // the entry points below are serialised per engine (one stream state, shared scratch buffers)
     const pm::Dict* dict = nullptr;
     pm_dict* dict_owner = nullptr;
     int device = 0, n_sms = 0;
@@ -490,18 +492,21 @@ int pm_engine_set_kr_seed(pm_engine* e, uint64_t seed) {
 
 int pm_engine_scan_device(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid,
                           uint16_t* d_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lock(e->mu);
     CU(cudaSetDevice(e->device));
     if (algo == PM_ALGO_AUTO) e->auto_choice = -1;  // device scans are independent calls: decide per call
     return scan_device_impl(e, algo, d_stream, n, hist_valid, d_out, static_cast<cudaStream_t>(cuda_stream));
 }
 
 void pm_engine_reset(pm_engine* e) {
+    std::lock_guard<std::mutex> lock(e->mu);
     e->auto_choice = -1;  // a new stream: PM_ALGO_AUTO samples again
     e->hist_valid = 0;
     memset(e->h_hist, 0, sizeof(e->h_hist));
 }
 
 int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n, uint16_t* out) {
+    std::lock_guard<std::mutex> lock(e->mu);
     CU(cudaSetDevice(e->device));
     if (ensure_pipe(e)) return -1;
     if (algo == PM_ALGO_DFA && ensure_dfa(e)) return -1;
@@ -555,6 +560,7 @@ int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n,
 }
 
 int pm_engine_summarize(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t pos_base, uint64_t out4[4], void* cuda_stream) {
+    std::lock_guard<std::mutex> lock(e->mu);
     CU(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     cudaError_t ce = pm::summarize_launch(d_out, n, pos_base, e->pt, e->d_acc, e->n_sms, st, &e->launches);
@@ -568,6 +574,7 @@ int pm_engine_summarize(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t 
 
 int pm_engine_compact(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t pos_base, int expand_ancestors,
                       uint64_t* d_records, size_t cap, uint64_t* n_records, void* cuda_stream) {
+    std::lock_guard<std::mutex> lock(e->mu);
     CU(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     unsigned long long* d_counts = nullptr;
@@ -584,6 +591,7 @@ int pm_engine_compact(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t po
 }
 
 int pm_engine_generate(pm_engine* e, int kind, uint64_t off, size_t n, uint8_t* d_dst, void* cuda_stream) {
+    std::lock_guard<std::mutex> lock(e->mu);
     CU(cudaSetDevice(e->device));
     if ((off & 4095) || (n & 4095)) return fail("pm_engine_generate: off and n must be multiples of 4096");
     cudaError_t ce = pm::generate_launch(kind, off, n, d_dst, e->pt, static_cast<cudaStream_t>(cuda_stream), &e->launches);
@@ -593,6 +601,7 @@ int pm_engine_generate(pm_engine* e, int kind, uint64_t off, size_t n, uint8_t* 
 
 int pm_engine_time_scan(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid, uint16_t* d_out,
                         int iters, float* ms_per_scan, void* cuda_stream) {
+    std::lock_guard<std::mutex> lock(e->mu);
     CU(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     cudaEvent_t a, b;
