@@ -125,6 +125,12 @@ int pm_engine_scan_device(pm_engine* e, int algo, const uint8_t* d_stream, size_
  * synchronous.  State is carried across calls exactly like consecutive read_char calls until
  * pm_engine_reset().  replaces: the chunk loop of measure_single_instance_stats (measure.c:281-304). */
 int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n, uint16_t* out);
+/* Same pipeline, sparse result: only the positions whose longest match is a pattern of at least min_len bytes
+ * come back, as position-sorted records (pos << 24 | pid), pos counted from the last pm_engine_reset().  The dense
+ * result never crosses PCIe (2 B per stream byte down to 8 B per reported match).  At most `cap` records are
+ * written; *n_records is the number found.  State is carried across calls like pm_engine_scan_host. */
+int pm_engine_scan_host_records(pm_engine* e, int algo, const uint8_t* stream, size_t n, uint32_t min_len,
+                                uint64_t* records, size_t cap, uint64_t* n_records);
 /* replaces: MpsElem.reset (Core/src/mps.h:78; ac_reset mpac.c:339-342) */
 void pm_engine_reset(pm_engine* e);
 

@@ -83,6 +83,7 @@ def lib():
         "pm_engine_set_kr_seed": (C.c_int, [vp, u64]),
         "pm_engine_scan_device": (C.c_int, [vp, C.c_int, vp, sz, sz, vp, vp]),
         "pm_engine_scan_host": (C.c_int, [vp, C.c_int, vp, sz, vp]),
+        "pm_engine_scan_host_records": (C.c_int, [vp, C.c_int, vp, sz, u32, vp, sz, C.POINTER(u64)]),
         "pm_engine_reset": (None, [vp]),
         "pm_engine_summarize": (C.c_int, [vp, vp, sz, u64, C.POINTER(u64), vp]),
         "pm_engine_compact": (C.c_int, [vp, vp, sz, u64, C.c_int, vp, sz, C.POINTER(u64), vp]),
@@ -295,6 +296,22 @@ class Engine:
         self._check(self.L.pm_engine_scan_host(self.h, algo, a.ctypes.data if a.size else None, a.size,
                                                 out.ctypes.data if a.size else None), "pm_engine_scan_host")
         return out
+
+    def scan_host_records(self, buf, min_len=1, cap=None, algo=ALGO_SFX, src_ptr=None, n=None, dst_ptr=None):
+        """Sparse result: (pos << 24 | pid) records of the positions whose longest match has >= min_len bytes."""
+        cnt = C.c_uint64()
+        if src_ptr is None:
+            a = _u8(buf)
+            n, src_ptr = a.size, (a.ctypes.data if a.size else None)
+        if cap is None:
+            cap = n
+        out = None
+        if dst_ptr is None:
+            out = np.empty(max(cap, 1), np.uint64)
+            dst_ptr = out.ctypes.data
+        self._check(self.L.pm_engine_scan_host_records(self.h, algo, src_ptr, n, min_len, dst_ptr, cap, C.byref(cnt)),
+                    "pm_engine_scan_host_records")
+        return (out[:min(cnt.value, cap)] if out is not None else None), cnt.value
 
     def scan_host_ptr(self, src_ptr, n, dst_ptr, algo=ALGO_SFX):
         self._check(self.L.pm_engine_scan_host(self.h, algo, src_ptr, n, dst_ptr), "pm_engine_scan_host")

@@ -119,18 +119,20 @@ __global__ void __launch_bounds__(256) summarize_kernel(const uint16_t* __restri
 constexpr int kCompactChunk = 2048;  // positions per CTA
 constexpr int kCompactThreads = 256;
 
-__device__ __forceinline__ uint32_t recs_at(uint32_t pid, bool expand, const PatTables& t) {
-    return pid ? (expand ? t.anc_off[pid + 1] - t.anc_off[pid] : 1u) : 0u;
+// records position i contributes: none without a match or when the matched pattern is shorter than min_len
+__device__ __forceinline__ uint32_t recs_at(uint32_t pid, bool expand, uint32_t min_len, const PatTables& t) {
+    if (!pid || (min_len > 1 && t.len[pid - 1] < min_len)) return 0u;
+    return expand ? t.anc_off[pid + 1] - t.anc_off[pid] : 1u;
 }
 
 __global__ void __launch_bounds__(kCompactThreads) compact_count_kernel(const uint16_t* __restrict__ out, uint64_t n,
-                                                                         bool expand, PatTables t,
+                                                                         bool expand, uint32_t min_len, PatTables t,
                                                                          unsigned long long* __restrict__ block_counts) {
     const uint64_t base = uint64_t(blockIdx.x) * kCompactChunk;
     uint32_t c = 0;
     for (int k = threadIdx.x; k < kCompactChunk; k += kCompactThreads) {
         const uint64_t i = base + k;
-        if (i < n) c += recs_at(out[i], expand, t);
+        if (i < n) c += recs_at(out[i], expand, min_len, t);
     }
     __shared__ uint32_t sh[kCompactThreads / 32];
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(1024) compact_scan_kernel(unsigned long long* 
 }
 
 __global__ void __launch_bounds__(kCompactThreads) compact_write_kernel(const uint16_t* __restrict__ out, uint64_t n,
-                                                                         uint64_t pos_base, bool expand, PatTables t,
+                                                                         uint64_t pos_base, bool expand, uint32_t min_len, PatTables t,
                                                                          const unsigned long long* __restrict__ block_offs,
                                                                          unsigned long long* __restrict__ recs, uint64_t cap) {
     // each thread owns 8 consecutive positions so that records stay position-sorted
@@ -191,7 +193,8 @@ __global__ void __launch_bounds__(kCompactThreads) compact_write_kernel(const ui
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
         pid[k] = (base + k < n) ? out[base + k] : 0;
-        c += recs_at(pid[k], expand, t);
+        if (!recs_at(pid[k], expand, min_len, t)) pid[k] = 0;
+        c += recs_at(pid[k], expand, min_len, t);
     }
     // exclusive scan of c over the CTA
     __shared__ uint32_t sh[kCompactThreads / 32];
@@ -269,14 +272,14 @@ cudaError_t summarize_launch(const uint16_t* out, uint64_t n, uint64_t pos_base,
 
 size_t compact_blocks(uint64_t n) { return size_t((n + kCompactChunk - 1) / kCompactChunk); }
 
-cudaError_t compact_launch(const uint16_t* out, uint64_t n, uint64_t pos_base, bool expand, const PatTables& t,
+cudaError_t compact_launch(const uint16_t* out, uint64_t n, uint64_t pos_base, bool expand, uint32_t min_len, const PatTables& t,
                            unsigned long long* d_block_counts, unsigned long long* d_total, unsigned long long* recs,
                            uint64_t cap, cudaStream_t st, uint64_t* launches) {
     const uint64_t nb = compact_blocks(n);
     if (nb == 0) return cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st);
-    compact_count_kernel<<<uint32_t(nb), kCompactThreads, 0, st>>>(out, n, expand, t, d_block_counts);
+    compact_count_kernel<<<uint32_t(nb), kCompactThreads, 0, st>>>(out, n, expand, min_len, t, d_block_counts);
     compact_scan_kernel<<<1, 1024, 0, st>>>(d_block_counts, nb, d_total);
-    compact_write_kernel<<<uint32_t(nb), kCompactThreads, 0, st>>>(out, n, pos_base, expand, t, d_block_counts, recs, cap);
+    compact_write_kernel<<<uint32_t(nb), kCompactThreads, 0, st>>>(out, n, pos_base, expand, min_len, t, d_block_counts, recs, cap);
     *launches += 3;
     return cudaGetLastError();
 }

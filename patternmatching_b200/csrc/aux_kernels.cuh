@@ -24,7 +24,8 @@ cudaError_t generate_launch(int kind, uint64_t off, uint64_t n, uint8_t* dst, co
 cudaError_t summarize_launch(const uint16_t* out, uint64_t n, uint64_t pos_base, const PatTables& t,
                              unsigned long long* d_acc4, int n_sms, cudaStream_t st, uint64_t* launches);
 size_t compact_blocks(uint64_t n);
-cudaError_t compact_launch(const uint16_t* out, uint64_t n, uint64_t pos_base, bool expand, const PatTables& t,
+// min_len > 1: only matches whose (longest) pattern has at least min_len bytes produce records
+cudaError_t compact_launch(const uint16_t* out, uint64_t n, uint64_t pos_base, bool expand, uint32_t min_len, const PatTables& t,
                            unsigned long long* d_block_counts, unsigned long long* d_total, unsigned long long* recs,
                            uint64_t cap, cudaStream_t st, uint64_t* launches);
 

@@ -110,6 +110,10 @@ struct pm_engine {
     uint16_t* h_out[2] = {nullptr, nullptr};
     cudaStream_t st[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr};
+    // record path of the host pipeline (lazy)
+    uint64_t* d_rec[2] = {nullptr, nullptr};
+    unsigned long long* d_rec_counts[2] = {nullptr, nullptr};
+    unsigned long long* h_rec_total[2] = {nullptr, nullptr};
     // stream state carried between pm_engine_scan_host calls (== ac->current_state of the reference)
     uint8_t h_hist[pm::kHalo];
     size_t hist_valid = 0;
@@ -446,6 +450,9 @@ void pm_engine_free(pm_engine* e) {
     pm::kr_free_tables(&e->kr);
     for (cudaEvent_t x : e->prof_events) cudaEventDestroy(x);
     for (int b = 0; b < 2; ++b) {
+        if (e->d_rec[b]) cudaFree(e->d_rec[b]);
+        if (e->d_rec_counts[b]) cudaFree(e->d_rec_counts[b]);
+        if (e->h_rec_total[b]) cudaFreeHost(e->h_rec_total[b]);
         if (e->h_in[b]) cudaFreeHost(e->h_in[b]);
         if (e->h_out[b]) cudaFreeHost(e->h_out[b]);
         if (e->st[b]) cudaStreamDestroy(e->st[b]);
@@ -559,6 +566,72 @@ int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n,
     return 0;
 }
 
+int pm_engine_scan_host_records(pm_engine* e, int algo, const uint8_t* stream, size_t n, uint32_t min_len,
+                                uint64_t* records, size_t cap, uint64_t* n_records) {
+    std::lock_guard<std::mutex> lock(e->mu);
+    CU(cudaSetDevice(e->device));
+    if (ensure_pipe(e)) return -1;
+    if (algo == PM_ALGO_DFA && ensure_dfa(e)) return -1;
+    if (algo == PM_ALGO_KR && ensure_kr(e)) return -1;
+    if (algo == PM_ALGO_AUTO && e->auto_choice < 0 && n < 4 * kSampleWin) algo = PM_ALGO_SFX;
+    const size_t blocks = pm::compact_blocks(kHostChunk) + 1;
+    if (!e->d_rec[0]) {
+        for (int b = 0; b < 2; ++b) {
+            CU(cudaMalloc(reinterpret_cast<void**>(&e->d_rec[b]), kHostChunk * sizeof(uint64_t)));
+            CU(cudaMalloc(reinterpret_cast<void**>(&e->d_rec_counts[b]), (blocks + 1) * sizeof(unsigned long long)));
+            CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_rec_total[b]), sizeof(unsigned long long)));
+        }
+    }
+    const bool in_pinned = is_pinned(stream);
+    const size_t n_chunks = (n + kHostChunk - 1) / kHostChunk;
+    uint64_t produced = 0;
+    auto drain = [&](size_t k) -> int {  // chunk k: fetch its record count, then exactly that many records
+        const int b = int(k & 1);
+        CU(cudaEventSynchronize(e->done[b]));
+        const uint64_t cnt = *e->h_rec_total[b];
+        const uint64_t room = produced < cap ? cap - produced : 0;
+        const uint64_t take = cnt < room ? cnt : room;
+        if (take) CU(cudaMemcpyAsync(records + produced, e->d_rec[b], take * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->st[b]));
+        CU(cudaStreamSynchronize(e->st[b]));
+        produced += cnt;
+        return 0;
+    };
+    for (size_t k = 0; k < n_chunks; ++k) {
+        const int b = int(k & 1);
+        if (k >= 2 && drain(k - 2)) return -1;
+        const size_t o = k * kHostChunk, len = std::min(kHostChunk, n - o);
+        const size_t from_call = std::min<size_t>(o, pm::kHalo);
+        const size_t hist_total = std::min<size_t>(e->hist_valid + o, pm::kHalo);
+        uint8_t* din = e->d_in[b];
+        if (from_call < size_t(pm::kHalo))
+            CU(cudaMemcpyAsync(din, e->h_hist + from_call, pm::kHalo - from_call, cudaMemcpyHostToDevice, e->st[b]));
+        if (in_pinned) {
+            CU(cudaMemcpyAsync(din + pm::kHalo - from_call, stream + o - from_call, from_call + len, cudaMemcpyHostToDevice, e->st[b]));
+        } else {
+            memcpy(e->h_in[b], stream + o - from_call, from_call + len);
+            CU(cudaMemcpyAsync(din + pm::kHalo - from_call, e->h_in[b], from_call + len, cudaMemcpyHostToDevice, e->st[b]));
+        }
+        if (scan_device_impl(e, algo, din + pm::kHalo, len, hist_total, e->d_out[b], e->st[b], b)) return -1;
+        cudaError_t ce = pm::compact_launch(e->d_out[b], len, e->hist_valid + o, false, min_len, e->pt, e->d_rec_counts[b],
+                                            e->d_rec_counts[b] + blocks, reinterpret_cast<unsigned long long*>(e->d_rec[b]),
+                                            kHostChunk, e->st[b], &e->launches);
+        if (ce != cudaSuccess) return cuda_fail(ce, "compact_launch");
+        CU(cudaMemcpyAsync(e->h_rec_total[b], e->d_rec_counts[b] + blocks, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->st[b]));
+        CU(cudaEventRecord(e->done[b], e->st[b]));
+    }
+    for (size_t k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; ++k)
+        if (drain(k)) return -1;
+    if (n >= size_t(pm::kHalo)) {
+        memcpy(e->h_hist, stream + n - pm::kHalo, pm::kHalo);
+    } else if (n) {
+        memmove(e->h_hist, e->h_hist + n, pm::kHalo - n);
+        memcpy(e->h_hist + pm::kHalo - n, stream, n);
+    }
+    e->hist_valid += n;
+    *n_records = produced;
+    return 0;
+}
+
 int pm_engine_summarize(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t pos_base, uint64_t out4[4], void* cuda_stream) {
     std::lock_guard<std::mutex> lock(e->mu);
     CU(cudaSetDevice(e->device));
@@ -579,7 +652,7 @@ int pm_engine_compact(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t po
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     unsigned long long* d_counts = nullptr;
     CU(cudaMalloc(reinterpret_cast<void**>(&d_counts), (pm::compact_blocks(n) + 1) * sizeof(unsigned long long)));
-    cudaError_t ce = pm::compact_launch(d_out, n, pos_base, expand_ancestors != 0, e->pt, d_counts, e->d_acc + 4,
+    cudaError_t ce = pm::compact_launch(d_out, n, pos_base, expand_ancestors != 0, 1, e->pt, d_counts, e->d_acc + 4,
                                         reinterpret_cast<unsigned long long*>(d_records), cap, st, &e->launches);
     unsigned long long total = 0;
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(&total, e->d_acc + 4, sizeof(total), cudaMemcpyDeviceToHost, st);

@@ -387,3 +387,25 @@ def test_full_size_16gib_properties(engine_merged):
     for lo in (0, 5 * w + 4096, n // 2, n - w):
         engine_merged.scan_device(buf.data_ptr() + lo, w, chk, hist_valid=min(lo, pm.HALO), algo=pm.ALGO_DFA)
         assert bool(torch.equal(chk, out[lo:lo + w])), lo
+
+
+def test_scan_host_records_sparse_result(oracle_merged, engine_merged):
+    """pm_engine_scan_host_records: position-sorted (pos << 24 | pid) records of the matches with >= min_len bytes,
+    state carried across calls, identical to filtering the dense result."""
+    n = (20 << 20) + 777                     # more than one pipeline chunk
+    stream = oracle_merged.gen("planted", 0, ((n + 4095) // 4096) * 4096)[:n]
+    longest = oracle_merged.scan(stream)
+    lens = oracle_merged.lengths()
+    for min_len in (1, 4, 12):
+        keep = np.nonzero((longest >= 0) & (lens[np.maximum(longest, 0)] >= min_len))[0]
+        want = (keep.astype(np.uint64) << np.uint64(24)) | (longest[keep].astype(np.uint64) + np.uint64(1))
+        engine_merged.reset()
+        cut = 5 << 20
+        r1, c1 = engine_merged.scan_host_records(stream[:cut], min_len=min_len)
+        r2, c2 = engine_merged.scan_host_records(stream[cut:], min_len=min_len)
+        got = np.concatenate([r1, r2])
+        assert c1 + c2 == want.size and np.array_equal(got, want), min_len
+    engine_merged.reset()
+    r, c = engine_merged.scan_host_records(stream, min_len=4, cap=1000)       # capacity smaller than the result
+    assert c > 1000 and r.size == 1000
+    engine_merged.reset()
