@@ -185,7 +185,7 @@ int fill_sfx_params(pm_engine* e, pm::SfxParams* p, size_t n, int slot) {
         CU(cudaMalloc(reinterpret_cast<void**>(&e->d_queue[slot]), want * sizeof(uint64_t)));
         e->queue_cap[slot] = want;
     }
-    p->queue = e->d_queue[slot]; p->qcount = e->d_qcount + size_t(slot) * kMaxCtas;
+    p->queue = e->d_queue[slot]; p->qcount = e->d_qcount + size_t(slot) * 2 * kMaxCtas;
     p->q_per_cta = uint32_t(std::min<size_t>(e->queue_cap[slot] / ctas, 1u << 30));
     return 0;
 }
@@ -202,15 +202,15 @@ int choose_algo(pm_engine* e, const uint8_t* d_stream, size_t n, size_t hist_val
     if (n < 4 * kSampleWin) { e->auto_flat = false; return PM_ALGO_SFX; }
     if (!e->d_sample_out) CU(cudaMalloc(reinterpret_cast<void**>(&e->d_sample_out), kSampleWin * sizeof(uint16_t)));
     uint64_t deferred = 0;
-    std::vector<uint32_t> counts(kMaxCtas);
+    std::vector<uint32_t> counts(2 * kMaxCtas);
     for (int w = 0; w < 4; ++w) {
         const size_t off = (n / 4 * size_t(w)) & ~size_t(4095);
         if (scan_device_impl(e, PM_ALGO_SFX, d_stream + off, kSampleWin, std::min<size_t>(off + hist_valid, pm::kHalo),
                              e->d_sample_out, st, slot)) return -1;
         const size_t ctas = pm::sfx_scan_ctas(kSampleWin, e->n_sms);
-        CU(cudaMemcpyAsync(counts.data(), e->d_qcount + size_t(slot) * kMaxCtas, ctas * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(counts.data(), e->d_qcount + size_t(slot) * 2 * kMaxCtas, 2 * ctas * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        for (size_t i = 0; i < ctas; ++i) deferred += counts[i];
+        for (size_t i = 0; i < 2 * ctas; ++i) deferred += counts[i];
     }
     const bool deep = deferred * 32 > 4 * kSampleWin;     // more than 1/32 of the positions walk past level 4
     if (!deep) { e->auto_flat = false; return PM_ALGO_SFX; }
@@ -430,7 +430,7 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
               up(d.anc_off, &e->d_anc_off) && up(d.anc_list, &e->d_anc_list) &&
               up(chain, &e->d_chain) && up(pidhash, &e->d_pidhash);
     if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_acc), 8 * sizeof(unsigned long long)) != cudaSuccess) ok = false;
-    if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_qcount), 2 * kMaxCtas * sizeof(uint32_t)) != cudaSuccess) ok = false;
+    if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_qcount), 4 * kMaxCtas * sizeof(uint32_t)) != cudaSuccess) ok = false;
     if (!ok) { pm_engine_free(e); return nullptr; }
     e->pt.n_patterns = uint32_t(P);
     e->pt.off = e->d_pat_off; e->pt.len = e->d_pat_len; e->pt.bytes = e->d_pat_bytes + kPatPad;
@@ -465,11 +465,11 @@ size_t pm_engine_total_mem(const pm_engine* e) { return e ? e->table_bytes : 0; 
 uint64_t pm_engine_launch_count(const pm_engine* e) { return e ? e->launches : 0; }
 int pm_engine_auto_choice(const pm_engine* e) { return e->auto_choice < 0 ? -1 : (e->auto_choice == PM_ALGO_DFA && e->auto_flat ? 4 : e->auto_choice); }
 uint64_t pm_engine_last_deferred(pm_engine* e) {
-    std::vector<uint32_t> c(kMaxCtas);
+    std::vector<uint32_t> c(2 * kMaxCtas);
     cudaSetDevice(e->device);
-    if (cudaMemcpy(c.data(), e->d_qcount, kMaxCtas * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    if (cudaMemcpy(c.data(), e->d_qcount, 2 * kMaxCtas * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     uint64_t sum = 0;
-    for (size_t i = 0; i < size_t(e->n_sms) && i < kMaxCtas; ++i) sum += c[i];
+    for (size_t i = 0; i < 2 * size_t(e->n_sms) && i < 2 * kMaxCtas; ++i) sum += c[i];
     return sum;
 }
 int pm_engine_set_profiling(pm_engine* e, int on) {

@@ -31,7 +31,8 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kTile = kSfxTile;                  // bytes per warp tile
 constexpr int kVisits = kTile / 512;             // 512 positions per warp visit
 constexpr int kStages = kSfxStages;
-constexpr int kStageBuf = kHalo + kTile;         // staged bytes per stage
+constexpr int kMainHalo = 16;                    // staged left halo: levels 1-4 look back 3 bytes (bulk-copy granularity 16)
+constexpr int kStageBuf = kMainHalo + kTile;     // staged bytes per stage
 constexpr uint32_t kCont = 0x80000000u;   // entry: continue at row (entry & 0xFFFFFF)
 constexpr uint32_t kTail = 0x40000000u;   // entry: the rest of the path is the text of pattern (entry & 0xFFFF)
 constexpr uint32_t kAlive = kCont | kTail;
@@ -46,6 +47,7 @@ constexpr int kOffStages = kOffL3 + int(kSfxMaxL3) * 4;
 constexpr int kSmemBytes = kOffStages + kWarps * kStages * kStageBuf;
 static_assert(kOffStages % 16 == 0 && kStageBuf % 16 == 0, "bulk copies need 16-byte alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(kCont == 0x80000000u, "level4_group tests the sign bit");
 static_assert((kStages & (kStages - 1)) == 0, "kStages must be a power of two");
 
 // byte / 16-bit window extraction from the 12-byte register window W = {c[g-4..g-1], c[g..g+3], c[g+4..g+7]}
@@ -182,15 +184,25 @@ __device__ __forceinline__ bool lookup_group(const uint16_t* s_root2, const uint
 template <bool kIdentCls>
 __device__ __forceinline__ void level4_group(const uint32_t (&W)[3], const uint32_t* __restrict__ rows, uint32_t log2_ncp,
                                              const uint8_t* s_cls, uint32_t (&e)[8]) {
-    uint32_t c3[8];
-    c3[0] = win_u8<1>(W); c3[1] = win_u8<2>(W); c3[2] = win_u8<3>(W); c3[3] = win_u8<4>(W);
-    c3[4] = win_u8<5>(W); c3[5] = win_u8<6>(W); c3[6] = win_u8<7>(W); c3[7] = win_u8<8>(W);
+    if constexpr (kIdentCls) {
+        // (row << 8) | c[i-3] is one byte permute (it drops the flag byte of the entry); kCont is the sign bit
+        uint32_t idx[8];
+        idx[0] = win_row_index<1>(W, e[0]); idx[1] = win_row_index<2>(W, e[1]);
+        idx[2] = win_row_index<3>(W, e[2]); idx[3] = win_row_index<4>(W, e[3]);
+        idx[4] = win_row_index<5>(W, e[4]); idx[5] = win_row_index<6>(W, e[5]);
+        idx[6] = win_row_index<7>(W, e[6]); idx[7] = win_row_index<8>(W, e[7]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        uint32_t c = c3[j];
-        if constexpr (!kIdentCls) c = s_cls[c];
-        const uint32_t l2 = kIdentCls ? 8u : log2_ncp;
-        if (e[j] & kCont) e[j] = __ldg(rows + ((size_t(e[j] & 0xFFFFFFu) << l2) | c));
+        for (int j = 0; j < 8; ++j)
+            if (int32_t(e[j]) < 0) e[j] = __ldg(rows + idx[j]);
+    } else {
+        uint32_t c3[8];
+        c3[0] = win_u8<1>(W); c3[1] = win_u8<2>(W); c3[2] = win_u8<3>(W); c3[3] = win_u8<4>(W);
+        c3[4] = win_u8<5>(W); c3[5] = win_u8<6>(W); c3[6] = win_u8<7>(W); c3[7] = win_u8<8>(W);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t c = s_cls[c3[j]];
+            if (int32_t(e[j]) < 0) e[j] = __ldg(rows + ((size_t(e[j] & 0xFFFFFFu) << log2_ncp) | c));
+        }
     }
 }
 
@@ -216,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
     const int lane = tid & 31, warp = tid >> 5;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar) + warp * kStages;
     uint8_t* wbuf = smem + kOffStages + warp * (kStages * kStageBuf);
-    const bool have_halo = p.hist_valid >= uint64_t(kHalo);
+    const bool have_halo = p.hist_valid >= uint64_t(kMainHalo);
     const uint32_t cont_base = p.cont_base, log2_ncp = p.log2_ncp;
     const uintptr_t rows_adj = reinterpret_cast<uintptr_t>(p.rows) +
                                ((uintptr_t(p.row2_base) << log2_ncp) << 2) - ((uintptr_t(cont_base) << log2_ncp) << 2);
@@ -228,11 +240,11 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
     }
     // halo of stage 0 zeroed: the very first tile of a stream without history reads it (the fix-up pass
     // owns the positions that would need real history)
-    for (int i = lane; i < kHalo / 4; i += 32) reinterpret_cast<uint32_t*>(wbuf)[i] = 0;
+    if (lane < kMainHalo / 4) reinterpret_cast<uint32_t*>(wbuf)[lane] = 0;
     if (tid < 256) s_cls[tid] = p.cls[tid];
     uint32_t* s_qcnt = reinterpret_cast<uint32_t*>(smem + kOffQCnt);
     uint32_t* s_l3 = reinterpret_cast<uint32_t*>(smem + kOffL3);
-    if (tid == 0) *s_qcnt = 0;
+    if (tid == 0) { s_qcnt[0] = 0; s_qcnt[1] = 0; s_qcnt[2] = 0; }  // slots used / tail items / row items
     const bool have_l3 = p.l3f != nullptr;
     if (have_l3) for (uint32_t i = tid; i < p.n_l3; i += kThreads) s_l3[i] = __ldg(p.l3f + i);
     // Per-warp choice of the level-3 path, re-made every visit from a 32-position sample of the previous one:
@@ -243,24 +255,28 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
     __syncwarp();
 
     const uint64_t gw = uint64_t(blockIdx.x) * kWarps + warp;   // global warp id
-    const uint64_t G = uint64_t(gridDim.x) * kWarps;
+    const uint64_t stride = uint64_t(gridDim.x) * kWarps * kTile;   // stream bytes between two tiles of a warp
 
-    auto issue_tile = [&](uint64_t t, int s) {  // lane 0 only
-        const uint64_t s0 = t * uint64_t(kTile);
-        const uint32_t len = uint32_t(min(uint64_t(kTile), p.n - s0));
-        const uint32_t body = len & ~15u;
-        const bool halo = (t > 0) || have_halo;
-        const uint32_t bytes = body + (halo ? kHalo : 0);
+    // lane 0 only: stage the tile that starts at stream offset s0 (with its left halo unless it is the very
+    // first tile of a stream that comes without history)
+    auto issue_tile = [&](uint64_t s0, int s) {
+        const uint64_t left = p.n - s0;
+        const uint32_t body = (left < uint64_t(kTile) ? uint32_t(left) : uint32_t(kTile)) & ~15u;
         uint8_t* dst = wbuf + s * kStageBuf;
-        mbar_arrive_expect_tx(&bars[s], bytes);
-        if (bytes) bulk_g2s(dst + (halo ? 0 : kHalo), p.stream + s0 - (halo ? kHalo : 0), bytes, &bars[s]);
+        if (s0 != 0 || have_halo) {
+            mbar_arrive_expect_tx(&bars[s], body + kMainHalo);
+            bulk_g2s(dst, p.stream + s0 - kMainHalo, body + kMainHalo, &bars[s]);
+        } else {
+            mbar_arrive_expect_tx(&bars[s], body);
+            if (body) bulk_g2s(dst + kMainHalo, p.stream, body, &bars[s]);
+        }
     };
 
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
-            const uint64_t t = gw + uint64_t(s) * G;
-            if (t < p.n_tiles) issue_tile(t, s);
+            const uint64_t s0 = gw * uint64_t(kTile) + uint64_t(s) * stride;
+            if (s0 < p.n) issue_tile(s0, s);
         }
     }
 
@@ -274,14 +290,14 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
 
     uint64_t* q_strip = p.queue + size_t(blockIdx.x) * p.q_per_cta;  // this CTA's strip of the deferred-walk queue
     uint32_t it = 0;
-    for (uint64_t t = gw; t < p.n_tiles; t += G, ++it) {
+    for (uint64_t s0 = gw * uint64_t(kTile); s0 < p.n; s0 += stride, ++it) {
         const int s = it & (kStages - 1);
-        const uint64_t s0 = t * uint64_t(kTile);
-        const uint32_t len = uint32_t(min(uint64_t(kTile), p.n - s0));
+        const uint64_t left = p.n - s0;
+        const uint32_t len = left < uint64_t(kTile) ? uint32_t(left) : uint32_t(kTile);
         uint8_t* stage = wbuf + s * kStageBuf;
         if (len & 15u) {  // ragged end of the stream: the last <16 bytes come in with plain loads
             const uint32_t body = len & ~15u;
-            if (uint32_t(lane) < (len & 15u)) stage[kHalo + body + lane] = p.stream[s0 + body + lane];
+            if (uint32_t(lane) < (len & 15u)) stage[kMainHalo + body + lane] = p.stream[s0 + body + lane];
             __syncwarp();
         }
         mbar_wait(&bars[s], (it / kStages) & 1);
@@ -290,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
         for (int v = 0; v < kVisits; ++v) {
             const int base_off = v * 512;
             if (uint32_t(base_off) >= len) break;
-            const uint8_t* vb = stage + kHalo + base_off;
+            const uint8_t* vb = stage + kMainHalo + base_off;
             // group A: positions base_off + 8*lane .. +8 ; group B: base_off + 256 + 8*lane .. +8
             const uint2 a = *reinterpret_cast<const uint2*>(vb + 8 * lane);
             const uint2 b = *reinterpret_cast<const uint2*>(vb + 256 + 8 * lane);
@@ -315,44 +331,47 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
                 lookup_group<kIdentCls, false>(s_root2, s_l3, WB, rows_adj, cont_base, log2_ncp, s_cls, vbn, eb);
             }
             use_l3 = have_l3 && __popc(__ballot_sync(0xFFFFFFFFu, sample_cont)) >= 8;
-            const uint32_t anya = (ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7]) & kCont;
-            const uint32_t anyb = (eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7]) & kCont;
-            if (__any_sync(0xFFFFFFFFu, (anya | anyb) != 0)) {
+            const uint32_t anya = ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7];
+            const uint32_t anyb = eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7];
+            if (__any_sync(0xFFFFFFFFu, ((anya | anyb) & kAlive) != 0)) {
                 // Some walk of this visit is still alive after level 3 (~40% of the visits on random bytes, one
                 // or two positions each).  Level 4 is taken here with one more round of predicated loads (c[i-3]
                 // is still in the register window); that ends ~99% of them.
                 level4_group<kIdentCls>(WA, p.rows, log2_ncp, s_cls, ea);
                 level4_group<kIdentCls>(WB, p.rows, log2_ncp, s_cls, eb);
-            }
-            const uint32_t any5a = (ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7]) & kAlive;
-            const uint32_t any5b = (eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7]) & kAlive;
-            if ((any5a | any5b) != 0) {
-                // Still alive after level 4 (planted / real matches, ~1e-5 of random positions): hand the walk to
-                // the deep kernel.  Every CTA owns a strip of the queue and hands out its slots with a shared-memory
-                // counter: no global atomics (one hot global counter cost 1.9 ms per GiB) and no warp-wide scans.
+                const uint32_t any5a = (ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7]) & kAlive;
+                const uint32_t any5b = (eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7]) & kAlive;
+                if ((any5a | any5b) != 0) {
+                    // Still alive after level 4 (planted / real matches, ~1e-5 of random positions): hand the walk to
+                    // the deep kernel.  Every CTA owns a strip of the queue and hands out its slots with a shared-memory
+                    // counter: no global atomics (one hot global counter cost 1.9 ms per GiB) and no warp-wide scans.
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (ea[j] & kAlive) {
-                        const uint64_t pos = s0 + ga + j;
-                        const uint32_t slot = atomicAdd(s_qcnt, 1u);
-                        if (slot < p.q_per_cta) {
-                            q_strip[slot] = (pos << 25) | (uint64_t((ea[j] & kTail) != 0) << 24) | (ea[j] & 0xFFFFFFu);
-                            ea[j] = 0;  // placeholder; sfx_deep_kernel writes the result
-                        } else {
-                            ea[j] = sfx_finish(p, ea[j], 4, p.stream + pos, pos + p.hist_valid + 1);
+                    for (int j = 0; j < 8; ++j) {
+                        if (ea[j] & kAlive) {
+                            const uint64_t pos = s0 + ga + j;
+                            if (atomicAdd(s_qcnt, 1u) < p.q_per_cta) {
+                                // "continue at row" items fill the strip from the front, "tail of pattern" items from the back
+                                const bool tail = (ea[j] & kTail) != 0;
+                                const uint32_t slot = tail ? p.q_per_cta - 1 - atomicAdd(s_qcnt + 1, 1u) : atomicAdd(s_qcnt + 2, 1u);
+                                q_strip[slot] = (pos << 25) | (tail ? (4u << 16) | (ea[j] & 0xFFFFu) : (ea[j] & 0xFFFFFFu));
+                                ea[j] = 0;  // placeholder; sfx_deep_kernel writes the result
+                            } else {
+                                ea[j] = sfx_finish(p, ea[j], 4, p.stream + pos, pos + p.hist_valid + 1);
+                            }
                         }
                     }
-                }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (eb[j] & kAlive) {
-                        const uint64_t pos = s0 + gb + j;
-                        const uint32_t slot = atomicAdd(s_qcnt, 1u);
-                        if (slot < p.q_per_cta) {
-                            q_strip[slot] = (pos << 25) | (uint64_t((eb[j] & kTail) != 0) << 24) | (eb[j] & 0xFFFFFFu);
-                            eb[j] = 0;
-                        } else {
-                            eb[j] = sfx_finish(p, eb[j], 4, p.stream + pos, pos + p.hist_valid + 1);
+                    for (int j = 0; j < 8; ++j) {
+                        if (eb[j] & kAlive) {
+                            const uint64_t pos = s0 + gb + j;
+                            if (atomicAdd(s_qcnt, 1u) < p.q_per_cta) {
+                                const bool tail = (eb[j] & kTail) != 0;
+                                const uint32_t slot = tail ? p.q_per_cta - 1 - atomicAdd(s_qcnt + 1, 1u) : atomicAdd(s_qcnt + 2, 1u);
+                                q_strip[slot] = (pos << 25) | (tail ? (4u << 16) | (eb[j] & 0xFFFFu) : (eb[j] & 0xFFFFFFu));
+                                eb[j] = 0;
+                            } else {
+                                eb[j] = sfx_finish(p, eb[j], 4, p.stream + pos, pos + p.hist_valid + 1);
+                            }
                         }
                     }
                 }
@@ -361,92 +380,147 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
             if (vbn > 0) store_group(p.out, s0 + gb, eb, vbn);
         }
         __syncwarp();  // every lane is done reading the stage before it is refilled
-        const uint64_t tn = t + uint64_t(kStages) * G;
-        if (lane == 0 && tn < p.n_tiles) issue_tile(tn, s);
+        const uint64_t sn = s0 + uint64_t(kStages) * stride;
+        if (lane == 0 && sn < p.n) issue_tile(sn, s);
     }
     __syncthreads();  // every warp of the CTA has finished its tiles
-    if (tid == 0) p.qcount[blockIdx.x] = min(*s_qcnt, p.q_per_cta);
+    if (tid == 0) { p.qcount[2 * blockIdx.x] = s_qcnt[2]; p.qcount[2 * blockIdx.x + 1] = s_qcnt[1]; }
 }
 
 // Deferred walks (levels >= 5).  The items are independent but their dependent chains differ wildly in length
-// (one lookup ... hundreds for a long repetitive pattern), so "one item per thread, loop until done" leaves
-// 90% of the lanes idle behind the longest chain of their warp.  Instead every lane runs a small state machine
-// and pulls its next item the moment its current one ends; one pass of the loop = at most one dependent
-// memory step (a row lookup, an 8-byte tail compare, or a step up the PatternsTree chain).
+// (one lookup ... hundreds for a long repetitive pattern), so every lane pulls its next item the moment its current
+// one ends.  One CTA drains the strip of one scan CTA in two phases, so that the lanes of a warp do the SAME kind of
+// step and differ only in how many of them their item needs:
+//   phase A, "continue at row" items (front of the strip; payload = row): row lookups, the stream bytes coming
+//            from an 8-byte history register; a walk that reaches a tail entry is appended to the tail items;
+//   phase B, "tail of pattern" items (back of the strip; payload = pid | depth << 16): 8-byte compares of the
+//            stream against the pattern text, then (rarely) a few steps up the PatternsTree chain.
+// A step is one dependent memory round trip and nothing hides it but the other warps, so each lane keeps a
+// two-deep software pipeline: the item after next is in flight, and for the next item so are the loads that
+// depend only on the item (its first 8 stream bytes, its tail record).
 template <bool kIdentCls>
 __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
-    // CTAs 2b and 2b+1 drain the strip of scan CTA b (two 1024-thread CTAs per SM: twice the walks in flight),
-    // their threads round-robin over the items
-    const uint32_t strip = blockIdx.x >> 1;
-    const uint64_t* q_strip = p.queue + size_t(strip) * p.q_per_cta;
-    const uint32_t count = p.qcount[strip];
-    const uint32_t q_stride = 2 * blockDim.x;
-    uint32_t q = threadIdx.x + (blockIdx.x & 1) * blockDim.x;
-    enum { kFetch = 0, kRow = 1, kTailCmp = 2, kChain = 3 };
-    int state = kFetch;
-    uint32_t v = 0, len = 0, next_term = 0, best_start = 0, cand = 0, hist_left = 0;
-    uint64_t pos = 0, k = 0, avail = 0, lim = 0;
-    uint64_t hist = 0;  // the next stream bytes of the walk, c[i-k] in the top byte: one 8-byte load per 8 row steps
-    const uint8_t* ci = nullptr;
-    const uint8_t* text = nullptr;
-    for (;;) {
-        if (state == kFetch) {
-            if (q >= count) break;  // this lane has run out of items
-            const uint64_t item = q_strip[q];
-            q += q_stride;
-            pos = item >> 25;
-            v = ((item >> 24) & 1 ? kTail : kCont) | uint32_t(item & 0xFFFFFFu);
-            k = 4;
-            ci = p.stream + pos;
-            avail = pos + p.hist_valid + 1;
-            state = (v & kCont) ? kRow : kTailCmp;
-            if (state == kRow && avail > 4) { hist = load8_ending_at(ci - 4, ci - (avail - 1)); hist_left = 8; }
-            if (state == kTailCmp) {
-                const uint4 rec = __ldg(p.tail_rec + (v & 0xFFFFu));
-                text = p.pat_bytes + rec.x; len = rec.y; next_term = rec.z; best_start = rec.w;
-                lim = uint64_t(len) < avail ? uint64_t(len) : avail;
+    __shared__ uint32_t s_tails;
+    uint64_t* q_strip = p.queue + size_t(blockIdx.x) * p.q_per_cta;
+    const uint32_t n_rows = p.qcount[2 * blockIdx.x];
+    const uint32_t cap_tails = p.q_per_cta - n_rows;
+    const uint8_t* const floor_s = p.stream - p.hist_valid;  // first readable stream byte
+    if (threadIdx.x == 0) s_tails = p.qcount[2 * blockIdx.x + 1];
+    __syncthreads();
+
+    // ---- phase A ----
+    {
+        uint32_t q = threadIdx.x;
+        bool v1 = q < n_rows, v2 = q + 1024 < n_rows;
+        uint64_t it1 = v1 ? q_strip[q] : 0, it2 = v2 ? q_strip[q + 1024] : 0, h1 = 0;
+        q += 2048;
+        if (v1 && (it1 >> 25) + p.hist_valid >= 4) h1 = load8_ending_at(p.stream + (it1 >> 25) - 4, floor_s);
+        bool busy = false;
+        uint32_t v = 0, hist_left = 0;
+        uint64_t pos = 0, k = 0, avail = 0, hist = 0;
+        const uint8_t* ci = nullptr;
+        for (;;) {
+            if (!busy) {
+                if (!v1) break;
+                pos = it1 >> 25;
+                v = kCont | uint32_t(it1 & 0xFFFFFFu);
+                k = 4;
+                ci = p.stream + pos;
+                avail = pos + p.hist_valid + 1;
+                hist = h1; hist_left = 8;
+                busy = true;
+                it1 = it2; v1 = v2;
+                if (v1 && (it1 >> 25) + p.hist_valid >= 4) h1 = load8_ending_at(p.stream + (it1 >> 25) - 4, floor_s);
+                v2 = q < n_rows;
+                if (v2) it2 = q_strip[q];
+                q += 1024;
             }
-        } else if (state == kRow) {
             const uint32_t row = v & 0xFFFFFFu;
-            if (k >= avail) {
+            if (k >= avail) {  // start of the stream: no byte left
                 p.out[pos] = uint16_t(__ldg(p.row_best + row));
-                state = kFetch;
-            } else {
-                if (hist_left == 0) { hist = load8_ending_at(ci - k, ci - (avail - 1)); hist_left = 8; }
-                uint32_t c = uint32_t(hist >> 56);
-                hist <<= 8; --hist_left;
-                if constexpr (!kIdentCls) c = __ldg(p.cls + c);
-                v = __ldg(p.rows + ((size_t(row) << p.log2_ncp) | c));
-                ++k;
-                if (v & kTail) {
-                    const uint4 rec = __ldg(p.tail_rec + (v & 0xFFFFu));
-                    text = p.pat_bytes + rec.x; len = rec.y; next_term = rec.z; best_start = rec.w;
-                    lim = uint64_t(len) < avail ? uint64_t(len) : avail;
-                    state = kTailCmp;
-                } else if (!(v & kCont)) {
-                    p.out[pos] = uint16_t(v);
-                    state = kFetch;
-                }
+                busy = false;
+                continue;
             }
-        } else if (state == kTailCmp) {
-            // k = bytes matched so far (the last k bytes of the pattern)
+            if (hist_left == 0) { hist = load8_ending_at(ci - k, floor_s); hist_left = 8; }
+            uint32_t c = uint32_t(hist >> 56);
+            hist <<= 8; --hist_left;
+            if constexpr (!kIdentCls) c = __ldg(p.cls + c);
+            v = __ldg(p.rows + ((size_t(row) << p.log2_ncp) | c));
+            ++k;
+            if (v & kTail) {  // hand over to phase B
+                const uint32_t t = atomicAdd(&s_tails, 1u);
+                if (t < cap_tails) q_strip[p.q_per_cta - 1 - t] = (pos << 25) | (uint32_t(k) << 16) | (v & 0xFFFFu);
+                else p.out[pos] = uint16_t(sfx_finish(p, v, k, ci, avail));  // strip full: finish here
+                busy = false;
+            } else if (!(v & kCont)) {
+                p.out[pos] = uint16_t(v);
+                busy = false;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B ----
+    {
+        const uint32_t n_tails = min(s_tails, cap_tails);
+        const uint64_t* q_back = q_strip + (p.q_per_cta - 1);  // item j sits at q_back[-j]
+        uint32_t q = threadIdx.x;
+        bool v1 = q < n_tails, v2 = q + 1024 < n_tails;
+        uint64_t it1 = v1 ? *(q_back - q) : 0, it2 = v2 ? *(q_back - (q + 1024)) : 0, a1 = 0;
+        q += 2048;
+        uint4 rec1 = make_uint4(0, 0, 0, 0);
+        if (v1) {
+            rec1 = __ldg(p.tail_rec + uint32_t(it1 & 0xFFFFu));
+            const uint64_t k1 = (it1 >> 16) & 0x1FFu;
+            if ((it1 >> 25) + p.hist_valid >= k1) a1 = load8_ending_at(p.stream + (it1 >> 25) - k1, floor_s);
+        }
+        bool busy = false, have_a = false;
+        uint32_t pid = 0, len = 0, next_term = 0, best_start = 0;
+        uint64_t pos = 0, k = 0, lim = 0, a = 0;
+        const uint8_t* ci = nullptr;
+        const uint8_t* text = nullptr;
+        for (;;) {
+            if (!busy) {
+                if (!v1) break;
+                pos = it1 >> 25;
+                pid = uint32_t(it1 & 0xFFFFu);
+                k = (it1 >> 16) & 0x1FFu;                    // bytes matched so far (the last k bytes of the pattern)
+                text = p.pat_bytes + rec1.x; len = rec1.y; next_term = rec1.z; best_start = rec1.w;
+                ci = p.stream + pos;
+                const uint64_t avail = pos + p.hist_valid + 1;
+                lim = uint64_t(len) < avail ? uint64_t(len) : avail;
+                a = a1; have_a = true;
+                busy = true;
+                it1 = it2; v1 = v2;
+                if (v1) {
+                    rec1 = __ldg(p.tail_rec + uint32_t(it1 & 0xFFFFu));
+                    const uint64_t k1 = (it1 >> 16) & 0x1FFu;
+                    if ((it1 >> 25) + p.hist_valid >= k1) a1 = load8_ending_at(p.stream + (it1 >> 25) - k1, floor_s);
+                }
+                v2 = q < n_tails;
+                if (v2) it2 = *(q_back - q);
+                q += 1024;
+            }
             bool done = k >= lim;
             if (!done) {
-                const uint64_t a = load8_ending_at(ci - k, ci - (avail - 1));
+                if (!have_a) a = load8_ending_at(ci - k, floor_s);
+                have_a = false;
                 const uint64_t b = load8_ending_at(text + (len - 1 - k), p.pat_bytes);
                 const uint64_t x = a ^ b;
-                const uint64_t same = x ? uint64_t(__clzll((long long)x) >> 3) : 8;
+                const uint64_t same = x ? uint64_t(__clzll((long long)x) >> 3) : 8;   // equal bytes from the top (= backwards)
                 const uint64_t left = lim - k;
                 k += same < left ? same : left;
                 done = same < 8 || k >= lim;
             }
             if (done) {
-                if (k < next_term) { p.out[pos] = uint16_t(best_start); state = kFetch; }
-                else { cand = v & 0xFFFFu; state = kChain; }
+                uint32_t cand = best_start;
+                if (k >= next_term) {  // some pattern of the chain fits: the longest one with length <= k
+                    cand = pid;
+                    while (cand && uint64_t(__ldg(p.pat_len + cand - 1)) > k) cand = __ldg(p.parent + cand);
+                }
+                p.out[pos] = uint16_t(cand);
+                busy = false;
             }
-        } else {  // kChain: longest of {pattern, its ancestors} that fits the k matched bytes
-            if (cand && uint64_t(__ldg(p.pat_len + cand - 1)) > k) cand = __ldg(p.parent + cand);
-            else { p.out[pos] = uint16_t(cand); state = kFetch; }
         }
     }
 }
@@ -489,7 +563,7 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
     if (e != cudaSuccess) return e;
     {
         auto deep = ident_cls ? sfx_deep_kernel<true> : sfx_deep_kernel<false>;
-        deep<<<grid * 2, 1024, 0, st>>>(p);  // CTAs 2b, 2b+1 drain the strip of scan CTA b
+        deep<<<grid, 1024, 0, st>>>(p);  // CTA b drains the strip of scan CTA b
         ++*launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

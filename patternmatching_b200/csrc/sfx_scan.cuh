@@ -6,7 +6,7 @@
 namespace pm {
 
 constexpr int kSfxThreads = 1024;
-constexpr int kSfxTile = 512;    // bytes of stream per warp tile (multiple of 512)
+constexpr int kSfxTile = 1024;   // bytes of stream per warp tile (multiple of 512)
 constexpr int kSfxStages = 2;    // private pipeline depth of a warp
 
 struct SfxParams {
@@ -28,7 +28,7 @@ struct SfxParams {
     uint32_t cont_base, row2_base, log2_ncp;
     uint64_t* queue;          // deferred deep walks: (position << 25) | (is_tail << 24) | row-or-pid;
                               // CTA b owns queue[b * q_per_cta .. (b+1) * q_per_cta)
-    uint32_t* qcount;         // [grid] items each CTA deferred
+    uint32_t* qcount;         // [2 * grid] per CTA: "continue at row" items (front of the strip), "tail" items (back)
     uint32_t q_per_cta;       // strip length; a CTA that fills its strip finishes further walks inline
     uint64_t n_tiles;         // filled by the launcher
 };
@@ -38,7 +38,7 @@ size_t sfx_smem_bytes();
 // ev[0..2], when non-null, are recorded on `st` before the main kernel, after it, and after the last kernel.
 // number of CTAs the launcher will use for n bytes: sizes the queue
 size_t sfx_scan_ctas(uint64_t n, int n_sms);
-constexpr uint32_t kSfxMaxL3 = 10240;  // filter words that fit beside root2 in shared memory
+constexpr uint32_t kSfxMaxL3 = 7168;   // filter words that fit beside root2 in shared memory
 cudaError_t sfx_scan_launch(const SfxParams& p, bool ident_cls, int n_sms, uint32_t max_pat_len, cudaStream_t st,
                             uint64_t* launches, cudaEvent_t* ev = nullptr);
 
