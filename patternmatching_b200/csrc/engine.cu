@@ -171,6 +171,8 @@ int fill_sfx_params(pm_engine* e, pm::SfxParams* p, size_t n, int slot) {
     p->root2 = e->d_root2; p->root1 = e->d_root1; p->rows = e->d_rows; p->row_best = e->d_row_best; p->cls = e->d_cls;
     p->cont_base = d.sfx.cont_base; p->row2_base = d.sfx.row2_base; p->log2_ncp = d.sfx.log2_ncp;
     p->l3f = getenv("PM_SFX_NO_L3") ? nullptr : e->d_l3f; p->n_l3 = uint32_t(d.sfx.l3f.size());
+    p->l3_min = getenv("PM_SFX_L3_MIN") ? uint32_t(atoi(getenv("PM_SFX_L3_MIN"))) : 4u;
+    p->l3_min_b = getenv("PM_SFX_L3_MIN_B") ? uint32_t(atoi(getenv("PM_SFX_L3_MIN_B"))) : p->l3_min;
     p->tail_rec = reinterpret_cast<const uint4*>(e->d_tail_rec); p->pat_bytes = e->d_pat_bytes + kPatPad;
     p->pat_len = e->d_pat_len; p->parent = e->d_parent;
     // Deferred-walk queue: one strip per scan CTA.  Random bytes defer ~1e-5 of the positions, C3 ~1.3e-3;

@@ -126,15 +126,11 @@ __device__ __noinline__ uint32_t sfx_finish(const SfxParams& p, uint32_t v, uint
 template <bool kIdentCls, bool kL3>
 __device__ __forceinline__ bool lookup_group(const uint16_t* s_root2, const uint32_t* s_l3, const uint32_t (&W)[3],
                                              uintptr_t rows_adj, uint32_t cont_base, uint32_t log2_ncp,
-                                             const uint8_t* s_cls, int valid, uint32_t (&e)[8]) {
+                                             const uint8_t* s_cls, uint32_t (&e)[8]) {
     e[0] = s_root2[win_u16<3>(W)]; e[1] = s_root2[win_u16<4>(W)];
     e[2] = s_root2[win_u16<5>(W)]; e[3] = s_root2[win_u16<6>(W)];
     e[4] = s_root2[win_u16<7>(W)]; e[5] = s_root2[win_u16<8>(W)];
     e[6] = s_root2[win_u16<9>(W)]; e[7] = s_root2[win_u16<10>(W)];
-    if (valid < 8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) if (j >= valid) e[j] = 0;  // stale bytes beyond the stream: never looked up
-    }
     const bool first_cont = e[0] >= cont_base;  // sample for the adaptive choice of the level-3 path
     uint32_t c2[8];
     c2[0] = win_u8<2>(W); c2[1] = win_u8<3>(W); c2[2] = win_u8<4>(W); c2[3] = win_u8<5>(W);
@@ -206,16 +202,11 @@ __device__ __forceinline__ void level4_group(const uint32_t (&W)[3], const uint3
     }
 }
 
-__device__ __forceinline__ void store_group(uint16_t* out, uint64_t gpos, const uint32_t (&e)[8], int valid) {
-    if (valid >= 8) {
-        uint4 r;
-        r.x = e[0] | (e[1] << 16); r.y = e[2] | (e[3] << 16);
-        r.z = e[4] | (e[5] << 16); r.w = e[6] | (e[7] << 16);
-        __stcs(reinterpret_cast<uint4*>(out + gpos), r);  // write-once result: streaming store
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) if (j < valid) out[gpos + j] = uint16_t(e[j]);
-    }
+__device__ __forceinline__ void store_group(uint16_t* out, uint64_t gpos, const uint32_t (&e)[8]) {
+    uint4 r;
+    r.x = __byte_perm(e[0], e[1], 0x5410); r.y = __byte_perm(e[2], e[3], 0x5410);  // low halves, one PRMT each
+    r.z = __byte_perm(e[4], e[5], 0x5410); r.w = __byte_perm(e[6], e[7], 0x5410);
+    __stcs(reinterpret_cast<uint4*>(out + gpos), r);  // write-once result: streaming store
 }
 
 template <bool kIdentCls>
@@ -250,25 +241,24 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
     // Per-warp choice of the level-3 path, re-made every visit from a 32-position sample of the previous one:
     // on binary / random bytes ~10% of the positions continue below root2 and the plain predicated L2 lookups
     // are cheapest; on text ~60% continue, and the shared-memory filter (2.1x faster there) takes over.
-    bool use_l3 = false;
+    bool use_l3a = false, use_l3b = false;
     fence_proxy_async();
     __syncwarp();
 
     const uint64_t gw = uint64_t(blockIdx.x) * kWarps + warp;   // global warp id
     const uint64_t stride = uint64_t(gridDim.x) * kWarps * kTile;   // stream bytes between two tiles of a warp
 
-    // lane 0 only: stage the tile that starts at stream offset s0 (with its left halo unless it is the very
-    // first tile of a stream that comes without history)
+    // lane 0 only: stage the (full) tile that starts at stream offset s0, with its left halo unless it is the
+    // very first tile of a stream that comes without history
+    const uint64_t n_main = p.n_tiles * uint64_t(kTile);   // the ragged end (< kTile bytes) belongs to sfx_edge_kernel
     auto issue_tile = [&](uint64_t s0, int s) {
-        const uint64_t left = p.n - s0;
-        const uint32_t body = (left < uint64_t(kTile) ? uint32_t(left) : uint32_t(kTile)) & ~15u;
         uint8_t* dst = wbuf + s * kStageBuf;
         if (s0 != 0 || have_halo) {
-            mbar_arrive_expect_tx(&bars[s], body + kMainHalo);
-            bulk_g2s(dst, p.stream + s0 - kMainHalo, body + kMainHalo, &bars[s]);
+            mbar_arrive_expect_tx(&bars[s], kTile + kMainHalo);
+            bulk_g2s(dst, p.stream + s0 - kMainHalo, kTile + kMainHalo, &bars[s]);
         } else {
-            mbar_arrive_expect_tx(&bars[s], body);
-            if (body) bulk_g2s(dst + kMainHalo, p.stream, body, &bars[s]);
+            mbar_arrive_expect_tx(&bars[s], kTile);
+            bulk_g2s(dst + kMainHalo, p.stream, kTile, &bars[s]);
         }
     };
 
@@ -276,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
             const uint64_t s0 = gw * uint64_t(kTile) + uint64_t(s) * stride;
-            if (s0 < p.n) issue_tile(s0, s);
+            if (s0 < n_main) issue_tile(s0, s);
         }
     }
 
@@ -290,22 +280,14 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
 
     uint64_t* q_strip = p.queue + size_t(blockIdx.x) * p.q_per_cta;  // this CTA's strip of the deferred-walk queue
     uint32_t it = 0;
-    for (uint64_t s0 = gw * uint64_t(kTile); s0 < p.n; s0 += stride, ++it) {
+    for (uint64_t s0 = gw * uint64_t(kTile); s0 < n_main; s0 += stride, ++it) {
         const int s = it & (kStages - 1);
-        const uint64_t left = p.n - s0;
-        const uint32_t len = left < uint64_t(kTile) ? uint32_t(left) : uint32_t(kTile);
         uint8_t* stage = wbuf + s * kStageBuf;
-        if (len & 15u) {  // ragged end of the stream: the last <16 bytes come in with plain loads
-            const uint32_t body = len & ~15u;
-            if (uint32_t(lane) < (len & 15u)) stage[kMainHalo + body + lane] = p.stream[s0 + body + lane];
-            __syncwarp();
-        }
         mbar_wait(&bars[s], (it / kStages) & 1);
 
 #pragma unroll 1
         for (int v = 0; v < kVisits; ++v) {
             const int base_off = v * 512;
-            if (uint32_t(base_off) >= len) break;
             const uint8_t* vb = stage + kMainHalo + base_off;
             // group A: positions base_off + 8*lane .. +8 ; group B: base_off + 256 + 8*lane .. +8
             const uint2 a = *reinterpret_cast<const uint2*>(vb + 8 * lane);
@@ -320,17 +302,17 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
                 WB[0] = a31;
             }
             const int ga = base_off + 8 * lane, gb = ga + 256;
-            const int va = int(len) - ga, vbn = int(len) - gb;   // positions of each group that exist (>= 8: all)
             uint32_t ea[8], eb[8];
             bool sample_cont;
-            if (use_l3) {
-                sample_cont = lookup_group<kIdentCls, true>(s_root2, s_l3, WA, rows_adj, cont_base, log2_ncp, s_cls, va, ea);
-                lookup_group<kIdentCls, true>(s_root2, s_l3, WB, rows_adj, cont_base, log2_ncp, s_cls, vbn, eb);
-            } else {
-                sample_cont = lookup_group<kIdentCls, false>(s_root2, s_l3, WA, rows_adj, cont_base, log2_ncp, s_cls, va, ea);
-                lookup_group<kIdentCls, false>(s_root2, s_l3, WB, rows_adj, cont_base, log2_ncp, s_cls, vbn, eb);
+            if (use_l3a) sample_cont = lookup_group<kIdentCls, true>(s_root2, s_l3, WA, rows_adj, cont_base, log2_ncp, s_cls, ea);
+            else sample_cont = lookup_group<kIdentCls, false>(s_root2, s_l3, WA, rows_adj, cont_base, log2_ncp, s_cls, ea);
+            if (use_l3b) lookup_group<kIdentCls, true>(s_root2, s_l3, WB, rows_adj, cont_base, log2_ncp, s_cls, eb);
+            else lookup_group<kIdentCls, false>(s_root2, s_l3, WB, rows_adj, cont_base, log2_ncp, s_cls, eb);
+            {
+                const uint32_t cnt = uint32_t(__popc(__ballot_sync(0xFFFFFFFFu, sample_cont)));
+                use_l3a = have_l3 && cnt >= p.l3_min;
+                use_l3b = have_l3 && cnt >= p.l3_min_b;
             }
-            use_l3 = have_l3 && __popc(__ballot_sync(0xFFFFFFFFu, sample_cont)) >= 8;
             const uint32_t anya = ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7];
             const uint32_t anyb = eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7];
             if (__any_sync(0xFFFFFFFFu, ((anya | anyb) & kAlive) != 0)) {
@@ -376,12 +358,12 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
                     }
                 }
             }
-            if (va > 0) store_group(p.out, s0 + ga, ea, va);
-            if (vbn > 0) store_group(p.out, s0 + gb, eb, vbn);
+            store_group(p.out, s0 + ga, ea);
+            store_group(p.out, s0 + gb, eb);
         }
         __syncwarp();  // every lane is done reading the stage before it is refilled
         const uint64_t sn = s0 + uint64_t(kStages) * stride;
-        if (lane == 0 && sn < p.n) issue_tile(sn, s);
+        if (lane == 0 && sn < n_main) issue_tile(sn, s);
     }
     __syncthreads();  // every warp of the CTA has finished its tiles
     if (tid == 0) { p.qcount[2 * blockIdx.x] = s_qcnt[2]; p.qcount[2 * blockIdx.x + 1] = s_qcnt[1]; }
@@ -525,12 +507,14 @@ __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
     }
 }
 
-// Positions whose history is shorter than max_pat_len-1 (only at the very start of a stream):
-// bounded walk straight from global memory.  avail(i) = i + hist_valid + 1 bytes exist up to c[i].
-__global__ void sfx_fixup_kernel(const SfxParams p, uint32_t count) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count || i >= p.n) return;
-    const uint64_t avail = uint64_t(i) + p.hist_valid + 1;
+// The two ragged ends of a stream, by a bounded walk straight from global memory (avail(i) = i + hist_valid + 1
+// bytes exist up to c[i]): the first `head` positions, whose look-back may cross the start of the stream, and the
+// last `tail` positions, which do not fill a whole warp tile.
+__global__ void sfx_edge_kernel(const SfxParams p, uint32_t head, uint32_t tail) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= head + tail) return;
+    const uint64_t i = t < head ? uint64_t(t) : p.n - tail + (t - head);
+    const uint64_t avail = i + p.hist_valid + 1;
     p.out[i] = uint16_t(sfx_finish(p, p.root1[p.stream[i]], 1, p.stream + i, avail));
 }
 
@@ -539,22 +523,21 @@ __global__ void sfx_fixup_kernel(const SfxParams p, uint32_t count) {
 size_t sfx_smem_bytes() { return kSmemBytes; }
 
 size_t sfx_scan_ctas(uint64_t n, int n_sms) {
-    const uint64_t tiles = (n + kTile - 1) / kTile;
+    const uint64_t tiles = n / kTile;  // full tiles
     const uint64_t ctas = (tiles + kWarps - 1) / kWarps;
-    return size_t(ctas < uint64_t(n_sms) ? ctas : uint64_t(n_sms));
+    return size_t(ctas < uint64_t(n_sms) ? (ctas ? ctas : 1) : uint64_t(n_sms));
 }
 
 cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, uint32_t max_pat_len, cudaStream_t st,
                             uint64_t* launches, cudaEvent_t* ev) {
     SfxParams p = p_in;
     if (p.n == 0) return cudaSuccess;
-    p.n_tiles = (p.n + kTile - 1) / kTile;
+    p.n_tiles = p.n / kTile;
     if (p.n_l3 > kSfxMaxL3) p.l3f = nullptr;  // the filter does not fit beside root2: plain L2 lookups only
     auto kern = ident_cls ? sfx_scan_kernel<true> : sfx_scan_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
-    const uint64_t ctas = (p.n_tiles + kWarps - 1) / kWarps;
-    const uint32_t grid = uint32_t(ctas < uint64_t(n_sms) ? ctas : uint64_t(n_sms));
+    const uint32_t grid = uint32_t(sfx_scan_ctas(p.n, n_sms));
     if (ev) cudaEventRecord(ev[0], st);
     kern<<<grid, kThreads, kSmemBytes, st>>>(p);
     if (ev) cudaEventRecord(ev[1], st);
@@ -568,12 +551,18 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    // Start of a stream: tile 0 is staged without its halo unless a full kHalo bytes of history exist, so
-    // every position that could look back past the tile start is redone by the bounded walker.
+    // Start of a stream: tile 0 is staged without its halo unless kMainHalo bytes of history exist, and a deferred
+    // walk is bounded by the bytes that exist; every position that could look back past the start of the readable
+    // stream is redone by the bounded walker -- together with the ragged end that does not fill a tile.
+    uint32_t head = 0;
     if (max_pat_len > 1 && p.hist_valid < uint64_t(kHalo)) {
         const uint64_t want = uint64_t(max_pat_len - 1);
-        const uint32_t count = uint32_t(p.n < want ? p.n : want);
-        sfx_fixup_kernel<<<(count + 127) / 128, 128, 0, st>>>(p, count);
+        head = uint32_t(p.n < want ? p.n : want);
+    }
+    uint32_t tail = uint32_t(p.n - p.n_tiles * uint64_t(kTile));
+    if (uint64_t(head) + tail > p.n) tail = uint32_t(p.n - head);
+    if (head + tail) {
+        sfx_edge_kernel<<<(head + tail + 127) / 128, 128, 0, st>>>(p, head, tail);
         ++*launches;
         e = cudaGetLastError();
     }

@@ -21,6 +21,8 @@ struct SfxParams {
     const uint8_t* cls;       // 256 entries (device)
     const uint32_t* l3f;      // level-3 filter words, n_l3 entries (see dict.hpp); nullptr = not used
     uint32_t n_l3;
+    uint32_t l3_min_b;        // same for the second half of a visit
+    uint32_t l3_min;          // a warp takes the filter path when >= l3_min of 32 sampled positions continue below root2
     const uint4* tail_rec;    // by pid: {text offset, length, next terminal length, best at tail start} (see dict.hpp)
     const uint8_t* pat_bytes; // pattern text (padded in front so that 8-byte windows never underrun)
     const uint32_t* pat_len;  // by canonical index (pid - 1)
