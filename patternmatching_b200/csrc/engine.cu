@@ -68,6 +68,7 @@ struct pm_engine {
     // sfx tables
     uint16_t* d_root2 = nullptr;
     uint32_t *d_root1 = nullptr, *d_rows = nullptr, *d_row_best = nullptr;
+    cudaTextureObject_t rows_tex = 0;
     uint8_t* d_cls = nullptr;
     // pattern tables
     uint32_t *d_pat_off = nullptr, *d_pat_len = nullptr;
@@ -168,10 +169,11 @@ bool is_pinned(const void* p) {
 
 int fill_sfx_params(pm_engine* e, pm::SfxParams* p, size_t n, int slot) {
     const pm::Dict& d = *e->dict;
+    p->rows_tex = getenv("PM_SFX_NO_TEX") ? 0 : e->rows_tex;
     p->root2 = e->d_root2; p->root1 = e->d_root1; p->rows = e->d_rows; p->row_best = e->d_row_best; p->cls = e->d_cls;
     p->cont_base = d.sfx.cont_base; p->row2_base = d.sfx.row2_base; p->log2_ncp = d.sfx.log2_ncp;
     p->l3f = getenv("PM_SFX_NO_L3") ? nullptr : e->d_l3f; p->n_l3 = uint32_t(d.sfx.l3f.size());
-    p->l3_min = getenv("PM_SFX_L3_MIN") ? uint32_t(atoi(getenv("PM_SFX_L3_MIN"))) : 4u;
+    p->l3_min = getenv("PM_SFX_L3_MIN") ? uint32_t(atoi(getenv("PM_SFX_L3_MIN"))) : 5u;
     p->l3_min_b = getenv("PM_SFX_L3_MIN_B") ? uint32_t(atoi(getenv("PM_SFX_L3_MIN_B"))) : p->l3_min;
     p->tail_rec = reinterpret_cast<const uint4*>(e->d_tail_rec); p->pat_bytes = e->d_pat_bytes + kPatPad;
     p->pat_len = e->d_pat_len; p->parent = e->d_parent;
@@ -431,6 +433,12 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
               up(d.sfx.tail_rec, &e->d_tail_rec) && up(d.sfx.l3f, &e->d_l3f) &&
               up(d.anc_off, &e->d_anc_off) && up(d.anc_list, &e->d_anc_list) &&
               up(chain, &e->d_chain) && up(pidhash, &e->d_pidhash);
+    if (ok) {  // the rows table as a linear texture (experiment: level-3 lookups through the TEX pipe)
+        cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = e->d_rows;
+        rd.res.linear.desc = cudaCreateChannelDesc<unsigned int>(); rd.res.linear.sizeInBytes = d.sfx.rows.size() * sizeof(uint32_t);
+        cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
+        if (cudaCreateTextureObject(&e->rows_tex, &rd, &td, nullptr) != cudaSuccess) { e->rows_tex = 0; cudaGetLastError(); }
+    }
     if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_acc), 8 * sizeof(unsigned long long)) != cudaSuccess) ok = false;
     if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_qcount), 4 * kMaxCtas * sizeof(uint32_t)) != cudaSuccess) ok = false;
     if (!ok) { pm_engine_free(e); return nullptr; }

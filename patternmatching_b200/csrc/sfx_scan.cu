@@ -28,11 +28,8 @@ namespace {
 
 constexpr int kThreads = kSfxThreads;
 constexpr int kWarps = kThreads / 32;
-constexpr int kTile = kSfxTile;                  // bytes per warp tile
-constexpr int kVisits = kTile / 512;             // 512 positions per warp visit
-constexpr int kStages = kSfxStages;
-constexpr int kMainHalo = 16;                    // staged left halo: levels 1-4 look back 3 bytes (bulk-copy granularity 16)
-constexpr int kStageBuf = kMainHalo + kTile;     // staged bytes per stage
+constexpr int kTile = kSfxTile;                  // positions per warp visit
+static_assert(kTile == 512, "a visit is 2 groups of 8 positions per lane");
 constexpr uint32_t kCont = 0x80000000u;   // entry: continue at row (entry & 0xFFFFFF)
 constexpr uint32_t kTail = 0x40000000u;   // entry: the rest of the path is the text of pattern (entry & 0xFFFF)
 constexpr uint32_t kAlive = kCont | kTail;
@@ -40,15 +37,11 @@ constexpr uint32_t kAlive = kCont | kTail;
 // shared memory carve-up (bytes)
 constexpr int kOffRoot2 = 0;                     // 131072
 constexpr int kOffCls = 131072;                  // 256
-constexpr int kOffBar = kOffCls + 256;           // kWarps * kStages * 8
-constexpr int kOffQCnt = kOffBar + kWarps * kStages * 8;           // 16 (one counter, padded)
-constexpr int kOffL3 = kOffQCnt + 16;                             // kSfxMaxL3 * 4
-constexpr int kOffStages = kOffL3 + int(kSfxMaxL3) * 4;
-constexpr int kSmemBytes = kOffStages + kWarps * kStages * kStageBuf;
-static_assert(kOffStages % 16 == 0 && kStageBuf % 16 == 0, "bulk copies need 16-byte alignment");
+constexpr int kOffQCnt = kOffCls + 256;          // 16 (three counters, padded)
+constexpr int kOffL3 = kOffQCnt + 16;            // kSfxMaxL3 * 4
+constexpr int kSmemBytes = kOffL3 + int(kSfxMaxL3) * 4;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 static_assert(kCont == 0x80000000u, "level4_group tests the sign bit");
-static_assert((kStages & (kStages - 1)) == 0, "kStages must be a power of two");
 
 // byte / 16-bit window extraction from the 12-byte register window W = {c[g-4..g-1], c[g..g+3], c[g+4..g+7]}
 template <int O>
@@ -117,40 +110,70 @@ __device__ __noinline__ uint32_t sfx_finish(const SfxParams& p, uint32_t v, uint
     return v;
 }
 
+// Where the main kernel finds its tables.  The 2-byte root table sits in shared memory (LSU pipe); the rows of
+// levels 3 and 4 are read through the TEXTURE pipe when the table fits a linear texture (kTex): the kernel is bound
+// by the LSU data pipe of the L1 (shared-memory gathers with ~3.5-way bank conflicts), and the TEX pipe is a
+// second, otherwise idle, path into the same cache -- sparse predicated fetches cost it ~1.5 cycles each.
+struct MainTabs {
+    const uint16_t* s_root2;
+    const uint32_t* s_l3;
+    const uint8_t* s_cls;
+    const uint32_t* rows;
+    const uint32_t* rows_l3;        // rows + l3_off: indexed by (root2 entry << log2_ncp) | class
+    cudaTextureObject_t rows_tex;
+    uint32_t l3_off;                // ((row2_base - cont_base) << log2_ncp), modulo 2^32
+    uint32_t cont_base, log2_ncp;
+};
+template <bool kTex>
+__device__ __forceinline__ uint32_t fetch_l3(const MainTabs& t, uint32_t idx) {   // idx = (root2 entry << log2_ncp) | class
+    if constexpr (kTex) return tex1Dfetch<unsigned int>(t.rows_tex, int(idx + t.l3_off));
+    else return __ldg(t.rows_l3 + idx);
+}
+template <bool kTex>
+__device__ __forceinline__ uint32_t fetch_row(const MainTabs& t, uint32_t idx) {  // idx = (row << log2_ncp) | class
+    if constexpr (kTex) return tex1Dfetch<unsigned int>(t.rows_tex, int(idx));
+    else return __ldg(t.rows + idx);
+}
+
 // Levels 1-3 for one group of 8 consecutive positions whose bytes sit in the register window W.
-// Phase A: 8 shared-memory gathers from root2.  Phase B: an entry that continues below the 2-byte table
-// (~10% on random bytes, ~60% on text) first consults the level-3 filter word of its row in SHARED memory:
-// unless the Bloom bit of c[i-2] is set the answer is the row's own best pid; only Bloom hits (true children
-// 0.9%, false positives ~14% of the continuing entries) fetch their row entry from L2, with PREDICATED loads --
-// no branch and no use of the loaded value here, so all loads of a visit are in flight together.
-template <bool kIdentCls, bool kL3>
-__device__ __forceinline__ bool lookup_group(const uint16_t* s_root2, const uint32_t* s_l3, const uint32_t (&W)[3],
-                                             uintptr_t rows_adj, uint32_t cont_base, uint32_t log2_ncp,
-                                             const uint8_t* s_cls, uint32_t (&e)[8]) {
+// Phase A: 8 shared-memory gathers from root2.  Phase B, plain path (!kL3): an
+// entry that continues below the 2-byte table fetches its row entry with a PREDICATED load -- no branch and no use of
+// the loaded value here, so all loads of a visit are in flight together.  Filter path (kL3): it first consults the
+// level-3 filter word of its row in SHARED memory: unless the Bloom bit of c[i-2] is set the answer is the row's own
+// best pid; only Bloom hits (true children 0.9%, false positives ~14% of the continuing entries) fetch the row entry.
+template <bool kIdentCls, bool kL3, bool kTex>
+__device__ __forceinline__ bool lookup_group(const MainTabs& t, const uint32_t (&W)[3], uint32_t (&e)[8]) {
+    const uint16_t* s_root2 = t.s_root2;
+    const uint32_t cont_base = t.cont_base;
     e[0] = s_root2[win_u16<3>(W)]; e[1] = s_root2[win_u16<4>(W)];
     e[2] = s_root2[win_u16<5>(W)]; e[3] = s_root2[win_u16<6>(W)];
     e[4] = s_root2[win_u16<7>(W)]; e[5] = s_root2[win_u16<8>(W)];
     e[6] = s_root2[win_u16<9>(W)]; e[7] = s_root2[win_u16<10>(W)];
     const bool first_cont = e[0] >= cont_base;  // sample for the adaptive choice of the level-3 path
-    uint32_t c2[8];
-    c2[0] = win_u8<2>(W); c2[1] = win_u8<3>(W); c2[2] = win_u8<4>(W); c2[3] = win_u8<5>(W);
-    c2[4] = win_u8<6>(W); c2[5] = win_u8<7>(W); c2[6] = win_u8<8>(W); c2[7] = win_u8<9>(W);
     if constexpr (kL3) {
+        // idx = (entry << 8) | c[i-2]: one byte permute; its low nibble picks the Bloom bit
+        uint32_t idx[8];
+        idx[0] = win_row_index<2>(W, e[0]); idx[1] = win_row_index<3>(W, e[1]);
+        idx[2] = win_row_index<4>(W, e[2]); idx[3] = win_row_index<5>(W, e[3]);
+        idx[4] = win_row_index<6>(W, e[4]); idx[5] = win_row_index<7>(W, e[5]);
+        idx[6] = win_row_index<8>(W, e[6]); idx[7] = win_row_index<9>(W, e[7]);
+        const uint32_t* l3_adj = t.s_l3 - cont_base;   // indexed by the root2 entry itself
         uint32_t f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             f[j] = 0;
-            if (e[j] >= cont_base) f[j] = s_l3[e[j] - cont_base];
+            if (e[j] >= cont_base) f[j] = l3_adj[e[j]];
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            uint32_t c = c2[j];
             const bool cont = e[j] >= cont_base;
-            const bool hit = ((f[j] >> (c & 15u)) & 1u) != 0;   // f == 0 when the entry does not continue
-            if constexpr (!kIdentCls) c = s_cls[c];
-            const uint32_t* addr = reinterpret_cast<const uint32_t*>(rows_adj + ((uintptr_t((e[j] << log2_ncp) | c)) << 2));
+            const bool hit = ((f[j] >> (idx[j] & 15u)) & 1u) != 0;   // f == 0 when the entry does not continue
+            uint32_t ix = idx[j];
+            if constexpr (!kIdentCls) {
+                if (hit) ix = (e[j] << t.log2_ncp) | t.s_cls[idx[j] & 0xFFu];
+            }
             if (cont) e[j] = f[j] >> 16;
-            if (hit) e[j] = __ldg(addr);
+            if (hit) e[j] = fetch_l3<false>(t, ix);   // ~1.5% of the lanes: not worth a TEX instruction
         }
     } else if constexpr (kIdentCls) {
         // 256 byte classes: the row index (e << 8 | c[i-2]) is ONE byte permute of the entry and the window word
@@ -160,26 +183,23 @@ __device__ __forceinline__ bool lookup_group(const uint16_t* s_root2, const uint
         idx[4] = win_row_index<6>(W, e[4]); idx[5] = win_row_index<7>(W, e[5]);
         idx[6] = win_row_index<8>(W, e[6]); idx[7] = win_row_index<9>(W, e[7]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            // rows_adj = &rows[(row2_base - cont_base) << 8]: entry e addresses row (e - cont_base + row2_base)
-            const uint32_t* addr = reinterpret_cast<const uint32_t*>(rows_adj + (uintptr_t(idx[j]) << 2));
-            if (e[j] >= cont_base) e[j] = __ldg(addr);
-        }
+        for (int j = 0; j < 8; ++j)
+            if (e[j] >= cont_base) e[j] = fetch_l3<kTex>(t, idx[j]);
     } else {
+        uint32_t c2[8];
+        c2[0] = win_u8<2>(W); c2[1] = win_u8<3>(W); c2[2] = win_u8<4>(W); c2[3] = win_u8<5>(W);
+        c2[4] = win_u8<6>(W); c2[5] = win_u8<7>(W); c2[6] = win_u8<8>(W); c2[7] = win_u8<9>(W);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const uint32_t c = s_cls[c2[j]];
-            const uint32_t* addr = reinterpret_cast<const uint32_t*>(rows_adj + ((uintptr_t((e[j] << log2_ncp) | c)) << 2));
-            if (e[j] >= cont_base) e[j] = __ldg(addr);
+            if (e[j] >= cont_base) e[j] = fetch_l3<kTex>(t, (e[j] << t.log2_ncp) | t.s_cls[c2[j]]);
         }
     }
     return first_cont;
 }
 
 // Level 4 for the entries of a group that are still "continue" after level 3: c[i-3] is byte 1+j of W.
-template <bool kIdentCls>
-__device__ __forceinline__ void level4_group(const uint32_t (&W)[3], const uint32_t* __restrict__ rows, uint32_t log2_ncp,
-                                             const uint8_t* s_cls, uint32_t (&e)[8]) {
+template <bool kIdentCls, bool kTex>
+__device__ __forceinline__ void level4_group(const MainTabs& t, const uint32_t (&W)[3], uint32_t (&e)[8]) {
     if constexpr (kIdentCls) {
         // (row << 8) | c[i-3] is one byte permute (it drops the flag byte of the entry); kCont is the sign bit
         uint32_t idx[8];
@@ -189,15 +209,14 @@ __device__ __forceinline__ void level4_group(const uint32_t (&W)[3], const uint3
         idx[6] = win_row_index<7>(W, e[6]); idx[7] = win_row_index<8>(W, e[7]);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (int32_t(e[j]) < 0) e[j] = __ldg(rows + idx[j]);
+            if (int32_t(e[j]) < 0) e[j] = fetch_row<kTex>(t, idx[j]);
     } else {
         uint32_t c3[8];
         c3[0] = win_u8<1>(W); c3[1] = win_u8<2>(W); c3[2] = win_u8<3>(W); c3[3] = win_u8<4>(W);
         c3[4] = win_u8<5>(W); c3[5] = win_u8<6>(W); c3[6] = win_u8<7>(W); c3[7] = win_u8<8>(W);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const uint32_t c = s_cls[c3[j]];
-            if (int32_t(e[j]) < 0) e[j] = __ldg(rows + ((size_t(e[j] & 0xFFFFFFu) << log2_ncp) | c));
+            if (int32_t(e[j]) < 0) e[j] = fetch_row<kTex>(t, ((e[j] & 0xFFFFFFu) << t.log2_ncp) | t.s_cls[c3[j]]);
         }
     }
 }
@@ -209,7 +228,24 @@ __device__ __forceinline__ void store_group(uint16_t* out, uint64_t gpos, const 
     __stcs(reinterpret_cast<uint4*>(out + gpos), r);  // write-once result: streaming store
 }
 
-template <bool kIdentCls>
+// 8 stream bytes straight to registers: read-only path, not allocated in L1 (every byte is read exactly once)
+__device__ __forceinline__ uint2 ldg_stream8(const uint8_t* ptr) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(ptr));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_stream4(const uint8_t* ptr) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(ptr));
+    return v;
+}
+
+// One visit = 512 consecutive positions of one warp: lane l resolves positions 8l..8l+7 (group A, bytes in `a`) and
+// 256+8l.. (group B, bytes in `b`), so that the two 16-byte result stores of a warp are fully coalesced.  The
+// stream bytes go from global memory straight into registers, one visit ahead of their use: staging them in shared
+// memory (bulk async copies, the round-1 design) cost one L1 data-pipe wavefront per 32 bytes written plus the
+// wavefronts of reading them back -- 14% of the pipe this kernel is bound by -- against 1 per 128 bytes here.
+template <bool kIdentCls, bool kTex>
 __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint16_t* s_root2 = reinterpret_cast<uint16_t*>(smem + kOffRoot2);
@@ -217,58 +253,41 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar) + warp * kStages;
-    uint8_t* wbuf = smem + kOffStages + warp * (kStages * kStageBuf);
-    const bool have_halo = p.hist_valid >= uint64_t(kMainHalo);
-    const uint32_t cont_base = p.cont_base, log2_ncp = p.log2_ncp;
-    const uintptr_t rows_adj = reinterpret_cast<uintptr_t>(p.rows) +
-                               ((uintptr_t(p.row2_base) << log2_ncp) << 2) - ((uintptr_t(cont_base) << log2_ncp) << 2);
-
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
-        fence_mbar_init();
-    }
-    // halo of stage 0 zeroed: the very first tile of a stream without history reads it (the fix-up pass
-    // owns the positions that would need real history)
-    if (lane < kMainHalo / 4) reinterpret_cast<uint32_t*>(wbuf)[lane] = 0;
-    if (tid < 256) s_cls[tid] = p.cls[tid];
     uint32_t* s_qcnt = reinterpret_cast<uint32_t*>(smem + kOffQCnt);
     uint32_t* s_l3 = reinterpret_cast<uint32_t*>(smem + kOffL3);
+    MainTabs t;
+    t.s_root2 = s_root2; t.s_l3 = s_l3; t.s_cls = s_cls; t.rows = p.rows;
+    t.rows_l3 = p.rows + (ptrdiff_t(p.row2_base) - ptrdiff_t(p.cont_base)) * (ptrdiff_t(1) << p.log2_ncp);
+    t.rows_tex = p.rows_tex;
+    t.l3_off = (p.row2_base - p.cont_base) << p.log2_ncp;
+    t.cont_base = p.cont_base; t.log2_ncp = p.log2_ncp;
+
+    if (tid < 256) s_cls[tid] = p.cls[tid];
     if (tid == 0) { s_qcnt[0] = 0; s_qcnt[1] = 0; s_qcnt[2] = 0; }  // slots used / tail items / row items
     const bool have_l3 = p.l3f != nullptr;
     if (have_l3) for (uint32_t i = tid; i < p.n_l3; i += kThreads) s_l3[i] = __ldg(p.l3f + i);
-    // Per-warp choice of the level-3 path, re-made every visit from a 32-position sample of the previous one:
-    // on binary / random bytes ~10% of the positions continue below root2 and the plain predicated L2 lookups
-    // are cheapest; on text ~60% continue, and the shared-memory filter (2.1x faster there) takes over.
+    // Per-warp choice of the level-3 path, re-made every visit from a 32-position sample of the previous one.
+    // The plain path (predicated L2 lookups) loads the L1 data pipe, the filter path (a shared-memory Bloom word
+    // first) the ALU; on binary bytes (~10% of the positions continue below root2) the threshold sends ~40% of the
+    // visits through the filter, which balances the two pipes; on text (~60% continue) all of them.
     bool use_l3a = false, use_l3b = false;
-    fence_proxy_async();
-    __syncwarp();
 
     const uint64_t gw = uint64_t(blockIdx.x) * kWarps + warp;   // global warp id
-    const uint64_t stride = uint64_t(gridDim.x) * kWarps * kTile;   // stream bytes between two tiles of a warp
+    const uint64_t G = uint64_t(gridDim.x) * kWarps;
+    const uint64_t n_vis = p.n_tiles;                           // full visits; the ragged end belongs to sfx_edge_kernel
+    const bool hist4 = p.hist_valid >= 4;
 
-    // lane 0 only: stage the (full) tile that starts at stream offset s0, with its left halo unless it is the
-    // very first tile of a stream that comes without history
-    const uint64_t n_main = p.n_tiles * uint64_t(kTile);   // the ragged end (< kTile bytes) belongs to sfx_edge_kernel
-    auto issue_tile = [&](uint64_t s0, int s) {
-        uint8_t* dst = wbuf + s * kStageBuf;
-        if (s0 != 0 || have_halo) {
-            mbar_arrive_expect_tx(&bars[s], kTile + kMainHalo);
-            bulk_g2s(dst, p.stream + s0 - kMainHalo, kTile + kMainHalo, &bars[s]);
-        } else {
-            mbar_arrive_expect_tx(&bars[s], kTile);
-            bulk_g2s(dst + kMainHalo, p.stream, kTile, &bars[s]);
-        }
+    // the visit's bytes: a = [8l, 8l+8), b = [256+8l, ..), h (lane 0) = the 4 bytes before the visit
+    auto load_visit = [&](uint64_t v, uint2& a, uint2& b, uint32_t& h) {
+        const uint8_t* base = p.stream + v * uint64_t(kTile);
+        a = ldg_stream8(base + 8 * lane);
+        b = ldg_stream8(base + 256 + 8 * lane);
+        h = 0;
+        if (lane == 0 && (v != 0 || hist4)) h = ldg_stream4(base - 4);
     };
-
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) {
-            const uint64_t s0 = gw * uint64_t(kTile) + uint64_t(s) * stride;
-            if (s0 < n_main) issue_tile(s0, s);
-        }
-    }
+    uint2 a = make_uint2(0, 0), b = make_uint2(0, 0);
+    uint32_t h = 0;
+    if (gw < n_vis) load_visit(gw, a, b, h);
 
     // root2 -> shared memory (once per CTA; coalesced 16-byte loads, L2 hits after the first CTA)
     {
@@ -276,96 +295,81 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
         int4* dst = reinterpret_cast<int4*>(s_root2);
         for (int i = tid; i < 131072 / 16; i += kThreads) dst[i] = __ldg(src + i);
     }
-    __syncthreads();  // the only CTA-wide barrier
+    __syncthreads();  // the only CTA-wide barrier before the end
 
     uint64_t* q_strip = p.queue + size_t(blockIdx.x) * p.q_per_cta;  // this CTA's strip of the deferred-walk queue
-    uint32_t it = 0;
-    for (uint64_t s0 = gw * uint64_t(kTile); s0 < n_main; s0 += stride, ++it) {
-        const int s = it & (kStages - 1);
-        uint8_t* stage = wbuf + s * kStageBuf;
-        mbar_wait(&bars[s], (it / kStages) & 1);
-
+    const int ga = 8 * lane, gb = ga + 256;
 #pragma unroll 1
-        for (int v = 0; v < kVisits; ++v) {
-            const int base_off = v * 512;
-            const uint8_t* vb = stage + kMainHalo + base_off;
-            // group A: positions base_off + 8*lane .. +8 ; group B: base_off + 256 + 8*lane .. +8
-            const uint2 a = *reinterpret_cast<const uint2*>(vb + 8 * lane);
-            const uint2 b = *reinterpret_cast<const uint2*>(vb + 256 + 8 * lane);
-            uint32_t WA[3], WB[3];
-            WA[1] = a.x; WA[2] = a.y; WB[1] = b.x; WB[2] = b.y;
-            WA[0] = __shfl_up_sync(0xFFFFFFFFu, a.y, 1);
-            WB[0] = __shfl_up_sync(0xFFFFFFFFu, b.y, 1);
-            const uint32_t a31 = __shfl_sync(0xFFFFFFFFu, a.y, 31);
-            if (lane == 0) {
-                WA[0] = *reinterpret_cast<const uint32_t*>(vb - 4);
-                WB[0] = a31;
-            }
-            const int ga = base_off + 8 * lane, gb = ga + 256;
-            uint32_t ea[8], eb[8];
-            bool sample_cont;
-            if (use_l3a) sample_cont = lookup_group<kIdentCls, true>(s_root2, s_l3, WA, rows_adj, cont_base, log2_ncp, s_cls, ea);
-            else sample_cont = lookup_group<kIdentCls, false>(s_root2, s_l3, WA, rows_adj, cont_base, log2_ncp, s_cls, ea);
-            if (use_l3b) lookup_group<kIdentCls, true>(s_root2, s_l3, WB, rows_adj, cont_base, log2_ncp, s_cls, eb);
-            else lookup_group<kIdentCls, false>(s_root2, s_l3, WB, rows_adj, cont_base, log2_ncp, s_cls, eb);
-            {
-                const uint32_t cnt = uint32_t(__popc(__ballot_sync(0xFFFFFFFFu, sample_cont)));
-                use_l3a = have_l3 && cnt >= p.l3_min;
-                use_l3b = have_l3 && cnt >= p.l3_min_b;
-            }
-            const uint32_t anya = ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7];
-            const uint32_t anyb = eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7];
-            if (__any_sync(0xFFFFFFFFu, ((anya | anyb) & kAlive) != 0)) {
-                // Some walk of this visit is still alive after level 3 (~40% of the visits on random bytes, one
-                // or two positions each).  Level 4 is taken here with one more round of predicated loads (c[i-3]
-                // is still in the register window); that ends ~99% of them.
-                level4_group<kIdentCls>(WA, p.rows, log2_ncp, s_cls, ea);
-                level4_group<kIdentCls>(WB, p.rows, log2_ncp, s_cls, eb);
-                const uint32_t any5a = (ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7]) & kAlive;
-                const uint32_t any5b = (eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7]) & kAlive;
-                if ((any5a | any5b) != 0) {
-                    // Still alive after level 4 (planted / real matches, ~1e-5 of random positions): hand the walk to
-                    // the deep kernel.  Every CTA owns a strip of the queue and hands out its slots with a shared-memory
-                    // counter: no global atomics (one hot global counter cost 1.9 ms per GiB) and no warp-wide scans.
+    for (uint64_t v = gw; v < n_vis; v += G) {
+        const uint64_t s0 = v * uint64_t(kTile);
+        uint32_t WA[3], WB[3];
+        WA[1] = a.x; WA[2] = a.y; WB[1] = b.x; WB[2] = b.y;
+        WA[0] = __shfl_up_sync(0xFFFFFFFFu, a.y, 1);
+        WB[0] = __shfl_up_sync(0xFFFFFFFFu, b.y, 1);
+        const uint32_t a31 = __shfl_sync(0xFFFFFFFFu, a.y, 31);
+        if (lane == 0) { WA[0] = h; WB[0] = a31; }
+        if (v + G < n_vis) load_visit(v + G, a, b, h);   // next visit's bytes, in flight during this one
+
+        uint32_t ea[8], eb[8];
+        bool sample_cont;
+        if (use_l3a) sample_cont = lookup_group<kIdentCls, true, kTex>(t, WA, ea);
+        else sample_cont = lookup_group<kIdentCls, false, kTex>(t, WA, ea);
+        if (use_l3b) lookup_group<kIdentCls, true, kTex>(t, WB, eb);
+        else lookup_group<kIdentCls, false, kTex>(t, WB, eb);
+        {
+            const uint32_t cnt = uint32_t(__popc(__ballot_sync(0xFFFFFFFFu, sample_cont)));
+            use_l3a = have_l3 && cnt >= p.l3_min;
+            use_l3b = have_l3 && cnt >= p.l3_min_b;
+        }
+        const uint32_t anya = ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7];
+        const uint32_t anyb = eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7];
+        if (__any_sync(0xFFFFFFFFu, ((anya | anyb) & kAlive) != 0)) {
+            // Some walk of this visit is still alive after level 3 (~40% of the visits on random bytes, one
+            // or two positions each).  Level 4 is taken here with one more round of predicated loads (c[i-3]
+            // is still in the register window); that ends ~99% of them.
+            level4_group<kIdentCls, false>(t, WA, ea);
+            level4_group<kIdentCls, false>(t, WB, eb);
+            const uint32_t any5a = (ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7]) & kAlive;
+            const uint32_t any5b = (eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7]) & kAlive;
+            if ((any5a | any5b) != 0) {
+                // Still alive after level 4 (planted / real matches, ~1e-5 of random positions): hand the walk to
+                // the deep kernel.  Every CTA owns a strip of the queue and hands out its slots with a shared-memory
+                // counter: no global atomics (one hot global counter cost 1.9 ms per GiB) and no warp-wide scans.
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (ea[j] & kAlive) {
-                            const uint64_t pos = s0 + ga + j;
-                            if (atomicAdd(s_qcnt, 1u) < p.q_per_cta) {
-                                // "continue at row" items fill the strip from the front, "tail of pattern" items from the back
-                                const bool tail = (ea[j] & kTail) != 0;
-                                const uint32_t slot = tail ? p.q_per_cta - 1 - atomicAdd(s_qcnt + 1, 1u) : atomicAdd(s_qcnt + 2, 1u);
-                                q_strip[slot] = (pos << 25) | (tail ? (4u << 16) | (ea[j] & 0xFFFFu) : (ea[j] & 0xFFFFFFu));
-                                ea[j] = 0;  // placeholder; sfx_deep_kernel writes the result
-                            } else {
-                                ea[j] = sfx_finish(p, ea[j], 4, p.stream + pos, pos + p.hist_valid + 1);
-                            }
+                for (int j = 0; j < 8; ++j) {
+                    if (ea[j] & kAlive) {
+                        const uint64_t pos = s0 + ga + j;
+                        if (atomicAdd(s_qcnt, 1u) < p.q_per_cta) {
+                            // "continue at row" items fill the strip from the front, "tail of pattern" items from the back
+                            const bool tail = (ea[j] & kTail) != 0;
+                            const uint32_t slot = tail ? p.q_per_cta - 1 - atomicAdd(s_qcnt + 1, 1u) : atomicAdd(s_qcnt + 2, 1u);
+                            q_strip[slot] = (pos << 25) | (tail ? (4u << 16) | (ea[j] & 0xFFFFu) : (ea[j] & 0xFFFFFFu));
+                            ea[j] = 0;  // placeholder; sfx_deep_kernel writes the result
+                        } else {
+                            ea[j] = sfx_finish(p, ea[j], 4, p.stream + pos, pos + p.hist_valid + 1);
                         }
                     }
+                }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (eb[j] & kAlive) {
-                            const uint64_t pos = s0 + gb + j;
-                            if (atomicAdd(s_qcnt, 1u) < p.q_per_cta) {
-                                const bool tail = (eb[j] & kTail) != 0;
-                                const uint32_t slot = tail ? p.q_per_cta - 1 - atomicAdd(s_qcnt + 1, 1u) : atomicAdd(s_qcnt + 2, 1u);
-                                q_strip[slot] = (pos << 25) | (tail ? (4u << 16) | (eb[j] & 0xFFFFu) : (eb[j] & 0xFFFFFFu));
-                                eb[j] = 0;
-                            } else {
-                                eb[j] = sfx_finish(p, eb[j], 4, p.stream + pos, pos + p.hist_valid + 1);
-                            }
+                for (int j = 0; j < 8; ++j) {
+                    if (eb[j] & kAlive) {
+                        const uint64_t pos = s0 + gb + j;
+                        if (atomicAdd(s_qcnt, 1u) < p.q_per_cta) {
+                            const bool tail = (eb[j] & kTail) != 0;
+                            const uint32_t slot = tail ? p.q_per_cta - 1 - atomicAdd(s_qcnt + 1, 1u) : atomicAdd(s_qcnt + 2, 1u);
+                            q_strip[slot] = (pos << 25) | (tail ? (4u << 16) | (eb[j] & 0xFFFFu) : (eb[j] & 0xFFFFFFu));
+                            eb[j] = 0;
+                        } else {
+                            eb[j] = sfx_finish(p, eb[j], 4, p.stream + pos, pos + p.hist_valid + 1);
                         }
                     }
                 }
             }
-            store_group(p.out, s0 + ga, ea);
-            store_group(p.out, s0 + gb, eb);
         }
-        __syncwarp();  // every lane is done reading the stage before it is refilled
-        const uint64_t sn = s0 + uint64_t(kStages) * stride;
-        if (lane == 0 && sn < n_main) issue_tile(sn, s);
+        store_group(p.out, s0 + ga, ea);
+        store_group(p.out, s0 + gb, eb);
     }
-    __syncthreads();  // every warp of the CTA has finished its tiles
+    __syncthreads();  // every warp of the CTA has finished its visits
     if (tid == 0) { p.qcount[2 * blockIdx.x] = s_qcnt[2]; p.qcount[2 * blockIdx.x + 1] = s_qcnt[1]; }
 }
 
@@ -534,7 +538,9 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
     if (p.n == 0) return cudaSuccess;
     p.n_tiles = p.n / kTile;
     if (p.n_l3 > kSfxMaxL3) p.l3f = nullptr;  // the filter does not fit beside root2: plain L2 lookups only
-    auto kern = ident_cls ? sfx_scan_kernel<true> : sfx_scan_kernel<false>;
+    const bool tex = p.rows_tex != 0;
+    auto kern = ident_cls ? (tex ? sfx_scan_kernel<true, true> : sfx_scan_kernel<true, false>)
+                          : (tex ? sfx_scan_kernel<false, true> : sfx_scan_kernel<false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
     const uint32_t grid = uint32_t(sfx_scan_ctas(p.n, n_sms));

@@ -6,7 +6,7 @@
 namespace pm {
 
 constexpr int kSfxThreads = 1024;
-constexpr int kSfxTile = 1024;   // bytes of stream per warp tile (multiple of 512)
+constexpr int kSfxTile = 512;    // bytes of stream per warp tile (multiple of 512)
 constexpr int kSfxStages = 2;    // private pipeline depth of a warp
 
 struct SfxParams {
@@ -21,6 +21,7 @@ struct SfxParams {
     const uint8_t* cls;       // 256 entries (device)
     const uint32_t* l3f;      // level-3 filter words, n_l3 entries (see dict.hpp); nullptr = not used
     uint32_t n_l3;
+    cudaTextureObject_t rows_tex;  // rows as a linear texture (u32 texels), 0 = read rows with plain loads
     uint32_t l3_min_b;        // same for the second half of a visit
     uint32_t l3_min;          // a warp takes the filter path when >= l3_min of 32 sampled positions continue below root2
     const uint4* tail_rec;    // by pid: {text offset, length, next terminal length, best at tail start} (see dict.hpp)
@@ -40,7 +41,7 @@ size_t sfx_smem_bytes();
 // ev[0..2], when non-null, are recorded on `st` before the main kernel, after it, and after the last kernel.
 // number of CTAs the launcher will use for n bytes: sizes the queue
 size_t sfx_scan_ctas(uint64_t n, int n_sms);
-constexpr uint32_t kSfxMaxL3 = 7168;   // filter words that fit beside root2 in shared memory
+constexpr uint32_t kSfxMaxL3 = 16384;  // filter words that fit beside root2 in shared memory
 cudaError_t sfx_scan_launch(const SfxParams& p, bool ident_cls, int n_sms, uint32_t max_pat_len, cudaStream_t st,
                             uint64_t* launches, cudaEvent_t* ev = nullptr);
 
