@@ -323,12 +323,14 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
         }
         const uint32_t anya = ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7];
         const uint32_t anyb = eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7];
-        if (__any_sync(0xFFFFFFFFu, ((anya | anyb) & kAlive) != 0)) {
-            // Some walk of this visit is still alive after level 3 (~40% of the visits on random bytes, one
+        const bool alive_a = __any_sync(0xFFFFFFFFu, (anya & kAlive) != 0);
+        const bool alive_b = __any_sync(0xFFFFFFFFu, (anyb & kAlive) != 0);
+        if (alive_a || alive_b) {
+            // Some walk of this visit is still alive after level 3 (~45% of the visits on random bytes, one
             // or two positions each).  Level 4 is taken here with one more round of predicated loads (c[i-3]
-            // is still in the register window); that ends ~99% of them.
-            level4_group<kIdentCls, false>(t, WA, ea);
-            level4_group<kIdentCls, false>(t, WB, eb);
+            // is still in the register window), per group of 256 positions; that ends ~99% of them.
+            if (alive_a) level4_group<kIdentCls, false>(t, WA, ea);
+            if (alive_b) level4_group<kIdentCls, false>(t, WB, eb);
             const uint32_t any5a = (ea[0] | ea[1] | ea[2] | ea[3] | ea[4] | ea[5] | ea[6] | ea[7]) & kAlive;
             const uint32_t any5b = (eb[0] | eb[1] | eb[2] | eb[3] | eb[4] | eb[5] | eb[6] | eb[7]) & kAlive;
             if ((any5a | any5b) != 0) {
@@ -373,74 +375,104 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
     if (tid == 0) { p.qcount[2 * blockIdx.x] = s_qcnt[2]; p.qcount[2 * blockIdx.x + 1] = s_qcnt[1]; }
 }
 
-// Deferred walks (levels >= 5).  The items are independent but their dependent chains differ wildly in length
-// (one lookup ... hundreds for a long repetitive pattern), so every lane pulls its next item the moment its current
-// one ends.  One CTA drains the strip of one scan CTA in two phases, so that the lanes of a warp do the SAME kind of
-// step and differ only in how many of them their item needs:
+// Deferred walks (levels >= 5).  An item is a chain of dependent memory round trips (~900 cycles each: the stream
+// bytes come from DRAM, rows / pattern text from L2) whose length differs wildly between items (one lookup ...
+// hundreds for a long repetitive pattern), and nothing hides a round trip but other, independent, round trips.
+// So every lane runs kSlots independent state machines; one loop iteration first ISSUES the next load of every
+// slot (whatever its state) and only then CONSUMES them: one wait per iteration for all slots of all lanes, and a
+// slot pulls its next item the moment its current one ends.  One CTA drains the strip of one scan CTA in two phases:
 //   phase A, "continue at row" items (front of the strip; payload = row): row lookups, the stream bytes coming
-//            from an 8-byte history register; a walk that reaches a tail entry is appended to the tail items;
+//            from an 8-byte history word; a walk that reaches a tail entry is appended to the tail items;
 //   phase B, "tail of pattern" items (back of the strip; payload = pid | depth << 16): 8-byte compares of the
 //            stream against the pattern text, then (rarely) a few steps up the PatternsTree chain.
-// A step is one dependent memory round trip and nothing hides it but the other warps, so each lane keeps a
-// two-deep software pipeline: the item after next is in flight, and for the next item so are the loads that
-// depend only on the item (its first 8 stream bytes, its tail record).
+constexpr int kSlots = 2;
+
+// raw halves of load8_ending_at, so that issue and use can be separated
+__device__ __forceinline__ void load8_issue(const uint8_t* a, const uint8_t* floor, uint64_t& hi, uint64_t& lo) {
+    const uintptr_t ua = reinterpret_cast<uintptr_t>(a);
+    const uint64_t* hi_p = reinterpret_cast<const uint64_t*>(ua & ~uintptr_t(7));
+    hi = __ldg(hi_p);
+    lo = 0;
+    if ((ua & 7) != 7 && reinterpret_cast<const uint8_t*>(hi_p) > floor) lo = __ldg(hi_p - 1);
+}
+__device__ __forceinline__ uint64_t load8_merge(const uint8_t* a, uint64_t hi, uint64_t lo) {
+    const uint32_t sh = uint32_t(reinterpret_cast<uintptr_t>(a) & 7) * 8;
+    return sh == 56 ? hi : ((hi << (56 - sh)) | (lo >> (sh + 8)));
+}
+
 template <bool kIdentCls>
 __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
-    __shared__ uint32_t s_tails;
+    __shared__ uint32_t s_tails, s_next_a, s_next_b;   // tail items so far; next unclaimed item of each phase
     uint64_t* q_strip = p.queue + size_t(blockIdx.x) * p.q_per_cta;
     const uint32_t n_rows = p.qcount[2 * blockIdx.x];
     const uint32_t cap_tails = p.q_per_cta - n_rows;
     const uint8_t* const floor_s = p.stream - p.hist_valid;  // first readable stream byte
-    if (threadIdx.x == 0) s_tails = p.qcount[2 * blockIdx.x + 1];
+    if (threadIdx.x == 0) { s_tails = p.qcount[2 * blockIdx.x + 1]; s_next_a = 0; s_next_b = 0; }
     __syncthreads();
+    enum : uint32_t { kIdle, kItem, kHist, kRow, kRec, kCmp, kChain, kEnd };
 
     // ---- phase A ----
     {
-        uint32_t q = threadIdx.x;
-        bool v1 = q < n_rows, v2 = q + 1024 < n_rows;
-        uint64_t it1 = v1 ? q_strip[q] : 0, it2 = v2 ? q_strip[q + 1024] : 0, h1 = 0;
-        q += 2048;
-        if (v1 && (it1 >> 25) + p.hist_valid >= 4) h1 = load8_ending_at(p.stream + (it1 >> 25) - 4, floor_s);
-        bool busy = false;
-        uint32_t v = 0, hist_left = 0;
-        uint64_t pos = 0, k = 0, avail = 0, hist = 0;
-        const uint8_t* ci = nullptr;
+        uint32_t st[kSlots], v[kSlots], hist_left[kSlots], ld32[kSlots];
+        uint64_t pos[kSlots], k[kSlots], hist[kSlots], ld_hi[kSlots], ld_lo[kSlots];
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) { st[s] = kIdle; v[s] = 0; hist_left[s] = 0; ld32[s] = 0; pos[s] = 0; k[s] = 0; hist[s] = 0; ld_hi[s] = 0; ld_lo[s] = 0; }
         for (;;) {
-            if (!busy) {
-                if (!v1) break;
-                pos = it1 >> 25;
-                v = kCont | uint32_t(it1 & 0xFFFFFFu);
-                k = 4;
-                ci = p.stream + pos;
-                avail = pos + p.hist_valid + 1;
-                hist = h1; hist_left = 8;
-                busy = true;
-                it1 = it2; v1 = v2;
-                if (v1 && (it1 >> 25) + p.hist_valid >= 4) h1 = load8_ending_at(p.stream + (it1 >> 25) - 4, floor_s);
-                v2 = q < n_rows;
-                if (v2) it2 = q_strip[q];
-                q += 1024;
+            // issue
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                if (st[s] == kIdle) {
+                    // items are claimed one at a time: their cost differs by two orders of magnitude, and a fixed
+                    // share per lane left 2/3 of the lanes idle behind the stragglers
+                    const uint32_t q = n_rows ? atomicAdd(&s_next_a, 1u) : 0u;
+                    if (q < n_rows) { ld_hi[s] = q_strip[q]; st[s] = kItem; }
+                    else st[s] = kEnd;
+                } else if (st[s] == kHist) {
+                    load8_issue(p.stream + pos[s] - k[s], floor_s, ld_hi[s], ld_lo[s]);
+                } else if (st[s] == kRow) {
+                    uint32_t c = uint32_t(hist[s] >> 56);
+                    hist[s] <<= 8; --hist_left[s];
+                    if constexpr (!kIdentCls) c = __ldg(p.cls + c);
+                    ld32[s] = __ldg(p.rows + ((size_t(v[s] & 0xFFFFFFu) << p.log2_ncp) | c));
+                }
             }
-            const uint32_t row = v & 0xFFFFFFu;
-            if (k >= avail) {  // start of the stream: no byte left
-                p.out[pos] = uint16_t(__ldg(p.row_best + row));
-                busy = false;
-                continue;
-            }
-            if (hist_left == 0) { hist = load8_ending_at(ci - k, floor_s); hist_left = 8; }
-            uint32_t c = uint32_t(hist >> 56);
-            hist <<= 8; --hist_left;
-            if constexpr (!kIdentCls) c = __ldg(p.cls + c);
-            v = __ldg(p.rows + ((size_t(row) << p.log2_ncp) | c));
-            ++k;
-            if (v & kTail) {  // hand over to phase B
-                const uint32_t t = atomicAdd(&s_tails, 1u);
-                if (t < cap_tails) q_strip[p.q_per_cta - 1 - t] = (pos << 25) | (uint32_t(k) << 16) | (v & 0xFFFFu);
-                else p.out[pos] = uint16_t(sfx_finish(p, v, k, ci, avail));  // strip full: finish here
-                busy = false;
-            } else if (!(v & kCont)) {
-                p.out[pos] = uint16_t(v);
-                busy = false;
+            bool all_end = true;
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) all_end = all_end && st[s] == kEnd;
+            if (all_end) break;
+            // consume
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                if (st[s] == kItem) pos[s] = ld_hi[s] >> 25;
+                const uint64_t avail = pos[s] + p.hist_valid + 1;
+                if (st[s] == kItem) {
+                    v[s] = kCont | uint32_t(ld_hi[s] & 0xFFFFFFu);
+                    k[s] = 4;
+                    st[s] = kHist;
+                } else if (st[s] == kHist) {
+                    hist[s] = load8_merge(p.stream + pos[s] - k[s], ld_hi[s], ld_lo[s]);
+                    hist_left[s] = 8;
+                    st[s] = kRow;
+                } else if (st[s] == kRow) {
+                    v[s] = ld32[s];
+                    ++k[s];
+                    if (v[s] & kTail) {  // hand over to phase B
+                        const uint32_t t = atomicAdd(&s_tails, 1u);
+                        if (t < cap_tails) q_strip[p.q_per_cta - 1 - t] = (pos[s] << 25) | (uint32_t(k[s]) << 16) | (v[s] & 0xFFFFu);
+                        else p.out[pos[s]] = uint16_t(sfx_finish(p, v[s], k[s], p.stream + pos[s], avail));  // strip full
+                        st[s] = kIdle;
+                    } else if (!(v[s] & kCont)) {
+                        p.out[pos[s]] = uint16_t(v[s]);
+                        st[s] = kIdle;
+                    } else if (hist_left[s] == 0) {
+                        st[s] = kHist;
+                    }
+                }
+                // the walk needs a byte that does not exist (start of the stream): the row's own best pattern
+                if ((st[s] == kHist || st[s] == kRow) && k[s] >= avail) {
+                    p.out[pos[s]] = uint16_t(__ldg(p.row_best + (v[s] & 0xFFFFFFu)));
+                    st[s] = kIdle;
+                }
             }
         }
     }
@@ -450,62 +482,77 @@ __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
     {
         const uint32_t n_tails = min(s_tails, cap_tails);
         const uint64_t* q_back = q_strip + (p.q_per_cta - 1);  // item j sits at q_back[-j]
-        uint32_t q = threadIdx.x;
-        bool v1 = q < n_tails, v2 = q + 1024 < n_tails;
-        uint64_t it1 = v1 ? *(q_back - q) : 0, it2 = v2 ? *(q_back - (q + 1024)) : 0, a1 = 0;
-        q += 2048;
-        uint4 rec1 = make_uint4(0, 0, 0, 0);
-        if (v1) {
-            rec1 = __ldg(p.tail_rec + uint32_t(it1 & 0xFFFFu));
-            const uint64_t k1 = (it1 >> 16) & 0x1FFu;
-            if ((it1 >> 25) + p.hist_valid >= k1) a1 = load8_ending_at(p.stream + (it1 >> 25) - k1, floor_s);
+        uint32_t st[kSlots], pid[kSlots], len[kSlots], next_term[kSlots], best_start[kSlots], text_off[kSlots], k[kSlots], lim[kSlots];
+        uint32_t ld_len[kSlots], ld_par[kSlots];
+        uint64_t pos[kSlots], a_hi[kSlots], a_lo[kSlots], b_hi[kSlots], b_lo[kSlots];
+        uint4 rec[kSlots];
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+            st[s] = kIdle; pid[s] = len[s] = next_term[s] = best_start[s] = text_off[s] = k[s] = lim[s] = ld_len[s] = ld_par[s] = 0;
+            pos[s] = a_hi[s] = a_lo[s] = b_hi[s] = b_lo[s] = 0; rec[s] = make_uint4(0, 0, 0, 0);
         }
-        bool busy = false, have_a = false;
-        uint32_t pid = 0, len = 0, next_term = 0, best_start = 0;
-        uint64_t pos = 0, k = 0, lim = 0, a = 0;
-        const uint8_t* ci = nullptr;
-        const uint8_t* text = nullptr;
         for (;;) {
-            if (!busy) {
-                if (!v1) break;
-                pos = it1 >> 25;
-                pid = uint32_t(it1 & 0xFFFFu);
-                k = (it1 >> 16) & 0x1FFu;                    // bytes matched so far (the last k bytes of the pattern)
-                text = p.pat_bytes + rec1.x; len = rec1.y; next_term = rec1.z; best_start = rec1.w;
-                ci = p.stream + pos;
-                const uint64_t avail = pos + p.hist_valid + 1;
-                lim = uint64_t(len) < avail ? uint64_t(len) : avail;
-                a = a1; have_a = true;
-                busy = true;
-                it1 = it2; v1 = v2;
-                if (v1) {
-                    rec1 = __ldg(p.tail_rec + uint32_t(it1 & 0xFFFFu));
-                    const uint64_t k1 = (it1 >> 16) & 0x1FFu;
-                    if ((it1 >> 25) + p.hist_valid >= k1) a1 = load8_ending_at(p.stream + (it1 >> 25) - k1, floor_s);
+            // issue
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                if (st[s] == kIdle) {
+                    const uint32_t q = n_tails ? atomicAdd(&s_next_b, 1u) : 0u;
+                    if (q < n_tails) { a_hi[s] = *(q_back - q); st[s] = kItem; }
+                    else st[s] = kEnd;
+                } else if (st[s] == kRec) {
+                    rec[s] = __ldg(p.tail_rec + pid[s]);   // x = text offset, y = length, z = next terminal, w = best at the start
+                } else if (st[s] == kCmp) {
+                    load8_issue(p.stream + pos[s] - k[s], floor_s, a_hi[s], a_lo[s]);
+                    load8_issue(p.pat_bytes + text_off[s] + (len[s] - 1 - k[s]), p.pat_bytes, b_hi[s], b_lo[s]);
+                } else if (st[s] == kChain) {
+                    ld_len[s] = __ldg(p.pat_len + pid[s] - 1);
+                    ld_par[s] = __ldg(p.parent + pid[s]);
                 }
-                v2 = q < n_tails;
-                if (v2) it2 = *(q_back - q);
-                q += 1024;
             }
-            bool done = k >= lim;
-            if (!done) {
-                if (!have_a) a = load8_ending_at(ci - k, floor_s);
-                have_a = false;
-                const uint64_t b = load8_ending_at(text + (len - 1 - k), p.pat_bytes);
-                const uint64_t x = a ^ b;
-                const uint64_t same = x ? uint64_t(__clzll((long long)x) >> 3) : 8;   // equal bytes from the top (= backwards)
-                const uint64_t left = lim - k;
-                k += same < left ? same : left;
-                done = same < 8 || k >= lim;
-            }
-            if (done) {
-                uint32_t cand = best_start;
-                if (k >= next_term) {  // some pattern of the chain fits: the longest one with length <= k
-                    cand = pid;
-                    while (cand && uint64_t(__ldg(p.pat_len + cand - 1)) > k) cand = __ldg(p.parent + cand);
+            bool all_end = true;
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) all_end = all_end && st[s] == kEnd;
+            if (all_end) break;
+            // consume
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                if (st[s] == kItem) {
+                    pos[s] = a_hi[s] >> 25;
+                    pid[s] = uint32_t(a_hi[s] & 0xFFFFu);
+                    k[s] = uint32_t(a_hi[s] >> 16) & 0x1FFu;      // bytes matched so far (the last k bytes of the pattern)
+                    st[s] = kRec;
+                } else if (st[s] == kRec) {
+                    text_off[s] = rec[s].x; len[s] = rec[s].y; next_term[s] = rec[s].z; best_start[s] = rec[s].w;
+                    const uint64_t avail = pos[s] + p.hist_valid + 1;
+                    lim[s] = uint64_t(len[s]) < avail ? len[s] : uint32_t(avail);
+                    st[s] = kCmp;
+                } else if (st[s] == kCmp) {
+                    const uint64_t a = load8_merge(p.stream + pos[s] - k[s], a_hi[s], a_lo[s]);
+                    const uint64_t b = load8_merge(p.pat_bytes + text_off[s] + (len[s] - 1 - k[s]), b_hi[s], b_lo[s]);
+                    const uint64_t x = a ^ b;
+                    const uint32_t same = x ? uint32_t(__clzll((long long)x) >> 3) : 8u;   // equal bytes from the top (= backwards)
+                    const uint32_t left = lim[s] - k[s];
+                    k[s] += same < left ? same : left;
+                    if (same < 8 || k[s] >= lim[s]) {
+                        if (k[s] < next_term[s]) { p.out[pos[s]] = uint16_t(best_start[s]); st[s] = kIdle; }       // no further terminal reached
+                        else if (k[s] >= len[s]) { p.out[pos[s]] = uint16_t(pid[s]); st[s] = kIdle; }              // the whole pattern
+                        else st[s] = kChain;   // the longest pattern of the chain with length <= k
+                    }
+                } else if (st[s] == kChain) {
+                    if (ld_len[s] > k[s]) {
+                        pid[s] = ld_par[s];
+                        if (pid[s] == 0) { p.out[pos[s]] = 0; st[s] = kIdle; }
+                    } else {
+                        p.out[pos[s]] = uint16_t(pid[s]);
+                        st[s] = kIdle;
+                    }
                 }
-                p.out[pos] = uint16_t(cand);
-                busy = false;
+                // a tail item that cannot advance at all (k already at its limit) is resolved by the same rules
+                if (st[s] == kCmp && k[s] >= lim[s]) {
+                    if (k[s] < next_term[s]) { p.out[pos[s]] = uint16_t(best_start[s]); st[s] = kIdle; }
+                    else if (k[s] >= len[s]) { p.out[pos[s]] = uint16_t(pid[s]); st[s] = kIdle; }
+                    else st[s] = kChain;
+                }
             }
         }
     }
