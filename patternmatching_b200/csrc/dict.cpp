@@ -249,18 +249,32 @@ int Dict::compile() {
         else if (nc == 1 && single[t.child[t.off[v]]]) { single[v] = 1; leaf_pid[v] = leaf_pid[t.child[t.off[v]]]; }
     }
     auto in_tail = [&](uint32_t v) { return single[v] && t.depth[v] >= kTailMinDepth; };
-    // rows: internal nodes of depth >= 1 that are not folded into a tail, in BFS order
+    // rows: internal nodes of depth >= 1 that are not folded into a tail.  The rows of the depth-2 nodes sit at
+    // the row indices [cont_base, cont_base + n2c) so that a root2 "continue" code IS the row index (the scan
+    // kernel forms the table index with one byte permute and no offset); all other rows fill the indices below
+    // cont_base in BFS order and, if there are more of them, go on after the depth-2 block.
     std::vector<uint32_t> row_of(t.n, 0xFFFFFFFFu);
-    uint32_t n_rows = 0, n1r = 0, n2c = 0, n_tail = 0;
+    uint32_t n_other = 0, n2c = 0, n_tail = 0;
     for (uint32_t v = 1; v < t.n; ++v)
         if (t.internal(v)) {
             if (in_tail(v)) { ++n_tail; continue; }
-            row_of[v] = n_rows++;
-            if (t.depth[v] == 1) ++n1r;
-            if (t.depth[v] == 2) ++n2c;
+            if (t.depth[v] == 2) ++n2c; else ++n_other;
         }
-    x.n_rows = n_rows; x.row2_base = n1r; x.n2_cont = n2c; x.n_tail_nodes = n_tail;
-    x.cont_base = 65536 - n2c;
+    // continue codes must lie above every pattern id and below 65536
+    uint32_t cont_base = std::max<uint32_t>(P + 1, n_other);
+    if (uint64_t(cont_base) + n2c > 65536) cont_base = n2c < 65536 ? 65536 - n2c : 0;
+    {
+        uint32_t next_other = 0, next_d2 = cont_base;
+        for (uint32_t v = 1; v < t.n; ++v) {
+            if (!t.internal(v) || in_tail(v)) continue;
+            if (t.depth[v] == 2) { row_of[v] = next_d2++; continue; }
+            if (next_other == cont_base) next_other = cont_base + n2c;   // jump over the depth-2 block
+            row_of[v] = next_other++;
+        }
+    }
+    const uint32_t n_rows = std::max(cont_base, n_other > cont_base ? n_other : 0u) + n2c;  // incl. unused rows below cont_base
+    x.n_rows = n_rows; x.row2_base = cont_base; x.n2_cont = n2c; x.n_tail_nodes = n_tail;
+    x.cont_base = cont_base;
     x.fits_u16 = (n2c < 65536) && (uint64_t(P) + 1 <= x.cont_base) && n_rows < (1u << 24);
 
     auto entry_for_child = [&](uint32_t c) -> uint32_t {  // walk arrives at existing child c
@@ -294,7 +308,7 @@ int Dict::compile() {
         if (t.depth[v] != 2 || !t.internal(v)) continue;
         uint32_t bloom = 0;
         for (uint32_t k = t.off[v]; k < t.off[v + 1]; ++k) bloom |= 1u << (t.byte[k] & 15);
-        x.l3f[row_of[v] - n1r] = (best[v] << 16) | bloom;
+        x.l3f[row_of[v] - cont_base] = (best[v] << 16) | bloom;
     }
     x.root1.assign(256, 0);
     std::vector<uint32_t> d1(256, 0);
@@ -310,7 +324,7 @@ int Dict::compile() {
             for (uint32_t b = 0; b < 256; ++b) x.root2[(a << 8) | b] = uint16_t(best[v]);
             for (uint32_t k = t.off[v]; k < t.off[v + 1]; ++k) {
                 uint32_t c = t.child[k];
-                uint32_t code = t.internal(c) ? x.cont_base + (row_of[c] - x.row2_base) : best[c];
+                uint32_t code = t.internal(c) ? row_of[c] : best[c];   // a continue code is the row index itself
                 x.root2[(a << 8) | t.byte[k]] = uint16_t(code);
             }
         }
@@ -365,7 +379,7 @@ void Dict::build_dfa() {
 
 // ---- compiled-automaton cache -----------------------------------------------------------------
 namespace {
-constexpr char kMagic[8] = {'P', 'M', 'B', '2', 'D', 'I', 'C', '1'};
+constexpr char kMagic[8] = {'P', 'M', 'B', '2', 'D', 'I', 'C', '2'};
 template <class T>
 bool put(FILE* f, const std::vector<T>& v) {
     const uint64_t n = v.size();

@@ -119,16 +119,9 @@ struct MainTabs {
     const uint32_t* s_l3;
     const uint8_t* s_cls;
     const uint32_t* rows;
-    const uint32_t* rows_l3;        // rows + l3_off: indexed by (root2 entry << log2_ncp) | class
     cudaTextureObject_t rows_tex;
-    uint32_t l3_off;                // ((row2_base - cont_base) << log2_ncp), modulo 2^32
-    uint32_t cont_base, log2_ncp;
+    uint32_t cont_base, log2_ncp;   // a root2 entry >= cont_base is the index of the row to continue at
 };
-template <bool kTex>
-__device__ __forceinline__ uint32_t fetch_l3(const MainTabs& t, uint32_t idx) {   // idx = (root2 entry << log2_ncp) | class
-    if constexpr (kTex) return tex1Dfetch<unsigned int>(t.rows_tex, int(idx + t.l3_off));
-    else return __ldg(t.rows_l3 + idx);
-}
 template <bool kTex>
 __device__ __forceinline__ uint32_t fetch_row(const MainTabs& t, uint32_t idx) {  // idx = (row << log2_ncp) | class
     if constexpr (kTex) return tex1Dfetch<unsigned int>(t.rows_tex, int(idx));
@@ -173,7 +166,7 @@ __device__ __forceinline__ bool lookup_group(const MainTabs& t, const uint32_t (
                 if (hit) ix = (e[j] << t.log2_ncp) | t.s_cls[idx[j] & 0xFFu];
             }
             if (cont) e[j] = f[j] >> 16;
-            if (hit) e[j] = fetch_l3<false>(t, ix);   // ~1.5% of the lanes: not worth a TEX instruction
+            if (hit) e[j] = fetch_row<false>(t, ix);   // ~1.5% of the lanes: not worth a TEX instruction
         }
     } else if constexpr (kIdentCls) {
         // 256 byte classes: the row index (e << 8 | c[i-2]) is ONE byte permute of the entry and the window word
@@ -184,14 +177,14 @@ __device__ __forceinline__ bool lookup_group(const MainTabs& t, const uint32_t (
         idx[6] = win_row_index<8>(W, e[6]); idx[7] = win_row_index<9>(W, e[7]);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (e[j] >= cont_base) e[j] = fetch_l3<kTex>(t, idx[j]);
+            if (e[j] >= cont_base) e[j] = fetch_row<kTex>(t, idx[j]);
     } else {
         uint32_t c2[8];
         c2[0] = win_u8<2>(W); c2[1] = win_u8<3>(W); c2[2] = win_u8<4>(W); c2[3] = win_u8<5>(W);
         c2[4] = win_u8<6>(W); c2[5] = win_u8<7>(W); c2[6] = win_u8<8>(W); c2[7] = win_u8<9>(W);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            if (e[j] >= cont_base) e[j] = fetch_l3<kTex>(t, (e[j] << t.log2_ncp) | t.s_cls[c2[j]]);
+            if (e[j] >= cont_base) e[j] = fetch_row<kTex>(t, (e[j] << t.log2_ncp) | t.s_cls[c2[j]]);
         }
     }
     return first_cont;
@@ -257,9 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
     uint32_t* s_l3 = reinterpret_cast<uint32_t*>(smem + kOffL3);
     MainTabs t;
     t.s_root2 = s_root2; t.s_l3 = s_l3; t.s_cls = s_cls; t.rows = p.rows;
-    t.rows_l3 = p.rows + (ptrdiff_t(p.row2_base) - ptrdiff_t(p.cont_base)) * (ptrdiff_t(1) << p.log2_ncp);
     t.rows_tex = p.rows_tex;
-    t.l3_off = (p.row2_base - p.cont_base) << p.log2_ncp;
     t.cont_base = p.cont_base; t.log2_ncp = p.log2_ncp;
 
     if (tid < 256) s_cls[tid] = p.cls[tid];
