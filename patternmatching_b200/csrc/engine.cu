@@ -173,7 +173,7 @@ int fill_sfx_params(pm_engine* e, pm::SfxParams* p, size_t n, int slot) {
     p->root2 = e->d_root2; p->root1 = e->d_root1; p->rows = e->d_rows; p->row_best = e->d_row_best; p->cls = e->d_cls;
     p->cont_base = d.sfx.cont_base; p->row2_base = d.sfx.row2_base; p->log2_ncp = d.sfx.log2_ncp;
     p->l3f = getenv("PM_SFX_NO_L3") ? nullptr : e->d_l3f; p->n_l3 = uint32_t(d.sfx.l3f.size());
-    p->l3_min = getenv("PM_SFX_L3_MIN") ? uint32_t(atoi(getenv("PM_SFX_L3_MIN"))) : 5u;
+    p->l3_min = getenv("PM_SFX_L3_MIN") ? uint32_t(atoi(getenv("PM_SFX_L3_MIN"))) : 4u;
     p->l3_min_b = getenv("PM_SFX_L3_MIN_B") ? uint32_t(atoi(getenv("PM_SFX_L3_MIN_B"))) : p->l3_min;
     p->tail_rec = reinterpret_cast<const uint4*>(e->d_tail_rec); p->pat_bytes = e->d_pat_bytes + kPatPad;
     p->pat_len = e->d_pat_len; p->parent = e->d_parent;
@@ -433,7 +433,7 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
               up(d.sfx.tail_rec, &e->d_tail_rec) && up(d.sfx.l3f, &e->d_l3f) &&
               up(d.anc_off, &e->d_anc_off) && up(d.anc_list, &e->d_anc_list) &&
               up(chain, &e->d_chain) && up(pidhash, &e->d_pidhash);
-    if (ok) {  // the rows table as a linear texture (experiment: level-3 lookups through the TEX pipe)
+    if (ok) {  // the rows table also as a linear texture: the scan kernel reads level 3 through the TEX pipe (sfx_scan.cu)
         cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = e->d_rows;
         rd.res.linear.desc = cudaCreateChannelDesc<unsigned int>(); rd.res.linear.sizeInBytes = d.sfx.rows.size() * sizeof(uint32_t);
         cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
@@ -453,6 +453,7 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
 void pm_engine_free(pm_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    if (e->rows_tex) cudaDestroyTextureObject(e->rows_tex);
     void* ptrs[] = {e->d_root2, e->d_root1, e->d_rows, e->d_row_best, e->d_cls, e->d_pat_off, e->d_pat_len, e->d_pat_bytes,
                     e->d_parent, e->d_chain, e->d_pidhash, e->d_tail_rec, e->d_l3f, e->d_anc_off, e->d_anc_list, e->d_sample_out, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_acc,
                     e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1], e->d_queue[0], e->d_queue[1], e->d_qcount};
