@@ -583,7 +583,9 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
     if (e != cudaSuccess) return e;
     const uint32_t grid = uint32_t(sfx_scan_ctas(p.n, n_sms));
     if (ev) cudaEventRecord(ev[0], st);
-    kern<<<grid, kThreads, kSmemBytes, st>>>(p);
+    // shared memory actually needed (the rest of the 256 KB stays L1 / texture cache)
+    const size_t smem = size_t(kOffL3) + (p.l3f ? size_t(p.n_l3) * 4 : 0) + 16;
+    kern<<<grid, kThreads, smem, st>>>(p);
     if (ev) cudaEventRecord(ev[1], st);
     ++*launches;
     e = cudaGetLastError();
