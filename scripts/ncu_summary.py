@@ -23,12 +23,28 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w") as f:
             "per-launch times are cold-cache and serialised: compare SHARES.\n\n| kernel | launches | mean us | total us | share |\n|---|---|---|---|---|\n")
     for k, v in agg.items():
         f.write(f"| `{k[:90]}` | {len(v)} | {sum(v)/len(v):.1f} | {sum(v):.1f} | {100*sum(v)/tot:.1f}% |\n")
-    scan = {k: v for k, v in agg.items() if "sfx_" in k}
-    st = sum(sum(v) for v in scan.values())
-    if st:
-        f.write("\nShare within the scan step (sfx_* kernels only):\n\n")
-        for k, v in scan.items():
-            f.write(f"- `{k[:60]}`: {100*sum(v)/st:.1f}%\n")
+    # the timed step of bench.py = the device-resident scans: a scan-kernel launch of >= 1 ms and the deep / edge
+    # launches that follow it (the host-path chunks and the auto-mode samples are the short launches)
+    steps, cur = [], None
+    for r in rows[hi + 2:]:
+        if len(r) <= vi:
+            continue
+        name, us = r[ki], float(r[vi].replace(",", "")) / 1e3
+        if "sfx_scan_kernel" in name:
+            cur = {"scan": us, "deep": 0.0, "edge": 0.0} if us >= 1000 else None
+            if cur:
+                steps.append(cur)
+        elif cur and "sfx_deep_kernel" in name:
+            cur["deep"] += us
+        elif cur and "sfx_edge_kernel" in name:
+            cur["edge"] += us
+        elif "sfx_" not in name:
+            cur = None
+    if steps:
+        sc = sum(x["scan"] for x in steps); dp = sum(x["deep"] for x in steps); ed = sum(x["edge"] for x in steps)
+        f.write(f"\nDevice-resident steps ({len(steps)} scans of the full shard): scan kernel {sc/len(steps):.1f} us, deep kernel "
+                f"{dp/len(steps):.1f} us, edge kernel {ed/len(steps):.1f} us per step; **scan kernel share of the step "
+                f"{sc/(sc+dp+ed):.3f}** (bench.py reports `roofline.kernel_share_of_step` from CUDA events).\n")
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
