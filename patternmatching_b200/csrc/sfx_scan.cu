@@ -13,12 +13,12 @@
 //   level >=5 : same rows / pattern-text tails; real or planted matches, ~1e-5 of random positions --
 //               DEFERRED to a work queue and finished by sfx_deep_kernel, so that a long dependent
 //               chain never stalls a scanning warp
-// All positions are independent, so there is no per-thread warm-up.  Every WARP runs its own
-// software pipeline: lane 0 stages 1 KiB tiles plus a 352-byte left halo (>= max_pat_len-1,
-// SURVEY Q8) with bulk async copies (TMA engine, SASS UBLKCP) into a private double buffer behind
-// private mbarriers; there is no CTA-wide barrier after start-up, so warps hide each other's L2
-// latency.  A lane resolves 2 x 8 consecutive positions per 512-byte visit, arranged so that the
-// 16-byte result stores of a warp are fully coalesced.
+//   level 3   : rows[...], through the TEXTURE pipe (plain path) or behind a shared-memory Bloom word (filter path)
+// All positions are independent, so there is no per-thread warm-up and no CTA-wide barrier after
+// start-up.  A warp visits 512 consecutive positions at a time; a lane resolves 2 x 8 consecutive
+// positions per visit, arranged so that the 16-byte result stores of a warp are fully coalesced, and
+// gets its stream bytes with two 8-byte loads issued one visit ahead.  Kernels: sfx_scan_kernel (levels
+// 1-4, every position), sfx_deep_kernel (the parked walks), sfx_edge_kernel (the ragged ends).
 #include "pm_dev.cuh"
 #include "sfx_scan.cuh"
 
@@ -236,8 +236,8 @@ __device__ __forceinline__ uint32_t ldg_stream4(const uint8_t* ptr) {
 // One visit = 512 consecutive positions of one warp: lane l resolves positions 8l..8l+7 (group A, bytes in `a`) and
 // 256+8l.. (group B, bytes in `b`), so that the two 16-byte result stores of a warp are fully coalesced.  The
 // stream bytes go from global memory straight into registers, one visit ahead of their use: staging them in shared
-// memory (bulk async copies, the round-1 design) cost one L1 data-pipe wavefront per 32 bytes written plus the
-// wavefronts of reading them back -- 14% of the pipe this kernel is bound by -- against 1 per 128 bytes here.
+// memory (bulk async copies into a per-warp double buffer, the first design of round 1) made every byte cross the
+// LSU data pipe this kernel is bound by a second time, and cost ~56 warp instructions of bookkeeping per tile.
 template <bool kIdentCls, bool kTex>
 __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -597,7 +597,7 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    // Start of a stream: tile 0 is staged without its halo unless kMainHalo bytes of history exist, and a deferred
+    // Start of a stream: visit 0 reads no bytes before the stream unless 4 bytes of history exist, and a deferred
     // walk is bounded by the bytes that exist; every position that could look back past the start of the readable
     // stream is redone by the bounded walker -- together with the ragged end that does not fill a tile.
     uint32_t head = 0;

@@ -6,8 +6,7 @@
 namespace pm {
 
 constexpr int kSfxThreads = 1024;
-constexpr int kSfxTile = 512;    // bytes of stream per warp tile (multiple of 512)
-constexpr int kSfxStages = 2;    // private pipeline depth of a warp
+constexpr int kSfxTile = 512;    // positions per warp visit
 
 struct SfxParams {
     const uint8_t* stream;    // device, 16-byte aligned; first reported byte
@@ -28,16 +27,16 @@ struct SfxParams {
     const uint8_t* pat_bytes; // pattern text (padded in front so that 8-byte windows never underrun)
     const uint32_t* pat_len;  // by canonical index (pid - 1)
     const uint16_t* parent;   // by pid: PatternsTree parent
-    uint32_t cont_base, row2_base, log2_ncp;
-    uint64_t* queue;          // deferred deep walks: (position << 25) | (is_tail << 24) | row-or-pid;
+    uint32_t cont_base, row2_base, log2_ncp;   // a root2 entry >= cont_base is the index of the row to continue at (row2_base == cont_base)
+    uint64_t* queue;          // deferred deep walks: (position << 25) | row, or (position << 25) | (depth << 16) | pid;
                               // CTA b owns queue[b * q_per_cta .. (b+1) * q_per_cta)
     uint32_t* qcount;         // [2 * grid] per CTA: "continue at row" items (front of the strip), "tail" items (back)
     uint32_t q_per_cta;       // strip length; a CTA that fills its strip finishes further walks inline
-    uint64_t n_tiles;         // filled by the launcher
+    uint64_t n_tiles;         // full visits (n / kSfxTile); filled by the launcher
 };
 
 size_t sfx_smem_bytes();
-// Launches the scan (+ the start-of-stream fix-up when hist_valid < max_pat_len-1) on `st`.
+// Launches the scan, the deep kernel and (for ragged ends) the edge kernel on `st`.
 // ev[0..2], when non-null, are recorded on `st` before the main kernel, after it, and after the last kernel.
 // number of CTAs the launcher will use for n bytes: sizes the queue
 size_t sfx_scan_ctas(uint64_t n, int n_sms);
