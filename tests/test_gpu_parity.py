@@ -409,3 +409,44 @@ def test_scan_host_records_sparse_result(oracle_merged, engine_merged):
     r, c = engine_merged.scan_host_records(stream, min_len=4, cap=1000)       # capacity smaller than the result
     assert c > 1000 and r.size == 1000
     engine_merged.reset()
+
+SFX_VARIANTS = [
+    {},                                                   # default: texture-pipe level 3, adaptive filter path
+    {"PM_SFX_NO_TEX": "1"},                               # level 3 with plain loads
+    {"PM_SFX_NO_L3": "1"},                                # no filter path at all
+    {"PM_SFX_L3_MIN": "0"},                               # filter path on every visit
+    {"PM_SFX_L3_MIN": "0", "PM_SFX_L3_MIN_B": "99"},      # filter path for the first half of a visit only
+    {"PM_SFX_NO_TEX": "1", "PM_SFX_L3_MIN": "99"},        # plain loads, never the filter
+]
+
+
+@pytest.mark.parametrize("env", SFX_VARIANTS, ids=lambda e: "+".join(f"{k[7:]}={v}" for k, v in e.items()) or "default")
+def test_every_variant_of_the_scan_kernel_is_exact(env, oracle_merged, engine_merged, monkeypatch):
+    """The scan kernel has two level-3 paths (texture fetch / shared-memory filter), chosen per warp, and a
+    plain-load fallback: each combination, forced through the environment, equals the oracle -- on the merged
+    dictionary (256 byte classes) and on a dictionary with few byte classes (the class-mapped code paths)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n = 300_000 + 77     # ~586 visits + a ragged end
+    for kind in ("planted", "ascii", "almost"):
+        stream = oracle_merged.gen(kind, 12345, n)
+        assert np.array_equal(gpu_scan(engine_merged, stream, pm.ALGO_SFX), want_pids(oracle_merged, stream)), kind
+    # few byte classes: lower-case words with shared suffixes, depth up to 40
+    rng = np.random.default_rng(5)
+    pats = set()
+    while len(pats) < 3000:
+        L = int(rng.integers(1, 41))
+        pats.add(bytes(rng.integers(97, 105, L, dtype=np.uint8)))
+    d = pm.Dictionary(); o = Oracle()
+    for i, pt in enumerate(sorted(pats)):
+        d.add_pattern(pt, 0, i + 1); o.add_pattern(pt, 0, i + 1)
+    d.compile(); o.compile()
+    assert d.info.n_classes < 256
+    eng = pm.Engine(d)
+    stream = rng.integers(97, 106, n, dtype=np.uint8)
+    cut = [int(x) for x in rng.integers(0, n - 50, 200)]
+    srt = sorted(pats, key=len)
+    for j, c in enumerate(cut):                    # plant long patterns so that deep walks and tails occur
+        pt = srt[-1 - (j % 500)]
+        stream[c:c + len(pt)] = np.frombuffer(pt, np.uint8)[: n - c]
+    assert np.array_equal(gpu_scan(eng, stream, pm.ALGO_SFX), want_pids(o, stream))
