@@ -273,6 +273,40 @@ def main():
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_gbs = world * ne / float(t_e.item()) / 1e9
+    # informational: what the host link of THIS rank gives a plain pinned copy, so that e2e can be read against it
+    # (the dense result is 2 B per stream byte: e2e <= d2h / 2)
+    pcie = None
+    if rank == 0:
+        try:
+            mb = 256 << 20
+            h_a = torch.empty(mb, dtype=torch.uint8, pin_memory=True); h_b = torch.empty(mb, dtype=torch.uint8, pin_memory=True)
+            d_a = buf[:mb]; d_b = out.view(torch.uint8)[:mb]
+            s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+            def timed(fn, reps=4):
+                fn(); torch.cuda.synchronize()
+                t = time.perf_counter()
+                for _ in range(reps):
+                    fn()
+                torch.cuda.synchronize()
+                return (time.perf_counter() - t) / reps
+
+            def both():
+                with torch.cuda.stream(s1):
+                    h_b.copy_(d_b, non_blocking=True)
+                with torch.cuda.stream(s2):
+                    d_a.copy_(h_a, non_blocking=True)
+
+            h_a.copy_(d_a); torch.cuda.synchronize()   # keep the stream bytes intact: d_a gets back what it held
+            t_d2h = timed(lambda: h_b.copy_(d_b, non_blocking=True))
+            t_h2d = timed(lambda: d_a.copy_(h_a, non_blocking=True))
+            t_both = timed(both)
+            pcie = {"d2h_gbs": round(mb / t_d2h / 1e9, 1), "h2d_gbs": round(mb / t_h2d / 1e9, 1),
+                    "both_directions_gbs_each": round(mb / t_both / 1e9, 1), "bytes": mb,
+                    "note": "plain pinned cudaMemcpyAsync on rank 0, nothing else running"}
+            del h_a, h_b
+        except Exception as ex:  # measurement aid only
+            pcie = {"error": str(ex)[:120]}
 
     if rank != 0:
         if world > 1:
@@ -307,7 +341,7 @@ def main():
                      "peak_source": peak_src},
         "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": ne, "d2h_bytes_per_step": 2 * ne,
                 "call": "pm_engine_scan_host (pinned host buffers, 16 MiB double-buffered chunks)", "steps": e2e_steps,
-                "matches_device_result": e2e_ok},
+                "matches_device_result": e2e_ok, "host_link": pcie},
         "e2e_records": e2e_records,
         "gpu_launches": int(launches),
         "clocks": sampler.result(),
