@@ -12,8 +12,10 @@
 //   hot  (default): states are numbered breadth-first, so the hot ones are the first ones: the transition
 //         rows of the first `hot_rows` states (u16 entries) and the longest-pattern ids of the first
 //         `hot_long` states live in SHARED memory (snort+et: the root and all 256 depth-1 states = 88% of the
-//         steps on random bytes; a small-alphabet dictionary: the whole automaton); the rest is read from the
-//         flat u32 table in global memory.  One dependent shared-memory gather per byte on the hot path.
+//         steps on random bytes; a small-alphabet dictionary: the whole automaton).  The states of the NEXT
+//         level keep a {Bloom of child classes, failure state} word there: without a goto child on c their
+//         transition is the failure state's hot row, so 99% of the steps on random bytes stay in shared memory;
+//         the rest is read from the flat u32 table in global memory.
 //   flat (PM_DFA_FLAT=1): every lookup from global memory through L1/L2 at full occupancy -- better when
 //         most steps are deep (pattern-prefix soup), where occupancy and L1 matter more than hot rows.
 #include "dfa_scan.cuh"
@@ -74,12 +76,23 @@ __global__ void __launch_bounds__(kThreads) dfa_flat_kernel(const DfaParams p) {
 }
 
 
+// One transition.  Hot states: their u16 row in shared memory.  States of the first level below the hot rows
+// (snort+et: the depth-2 states, 11% of the steps on random bytes): their Bloom word says whether a goto child on
+// c can exist; if not (93% of those steps) the transition is the failure state's -- a hot row again, so the step
+// stays in shared memory; only Bloom hits and deeper states read the dense table in global memory.
 template <bool kIdentCls>
 __device__ __forceinline__ uint32_t dfa_step(uint32_t s, uint32_t c, const DfaParams& p, const uint16_t* s_hot,
-                                             const uint8_t* s_cls) {
+                                             const uint32_t* s_fb, const uint8_t* s_cls) {
     if constexpr (!kIdentCls) c = s_cls[c];
-    const uint32_t idx = (s << p.log2_ncp) | c;
-    return s < p.hot_rows ? uint32_t(s_hot[idx]) : __ldg(p.delta + idx);
+    const bool hot = s < p.hot_rows;
+    const uint32_t fbi = s - p.hot_rows;
+    const bool fb = fbi < p.fb_count;              // false for hot states (the subtraction wraps)
+    uint32_t m = 0xFFFFu;
+    if (fb) m = s_fb[fbi];
+    const bool via_fail = fb && !((m >> (c & 15u)) & 1u);
+    const uint32_t row = via_fail ? (m >> 16) : s;
+    const uint32_t idx = (row << p.log2_ncp) | c;
+    return (hot || via_fail) ? uint32_t(s_hot[idx]) : __ldg(p.delta + idx);
 }
 
 __device__ __forceinline__ uint32_t dfa_longest(uint32_t s, const DfaParams& p, const uint16_t* s_long) {
@@ -90,10 +103,12 @@ template <bool kIdentCls>
 __global__ void __launch_bounds__(kHotThreads, 1) dfa_hot_kernel(const DfaParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint16_t* s_hot = reinterpret_cast<uint16_t*>(smem);
-    uint16_t* s_long = s_hot + (size_t(p.hot_rows) << p.log2_ncp);
+    uint32_t* s_fb = reinterpret_cast<uint32_t*>(s_hot + (size_t(p.hot_rows) << p.log2_ncp));   // 4-byte aligned: rows are >= 2 entries
+    uint16_t* s_long = reinterpret_cast<uint16_t*>(s_fb + p.fb_count);
     uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_long + p.hot_long);
     // hot tables -> shared memory (u32 global entries narrowed to u16: the host guarantees they fit)
     for (uint32_t i = threadIdx.x; i < (p.hot_rows << p.log2_ncp); i += kHotThreads) s_hot[i] = uint16_t(__ldg(p.delta + i));
+    for (uint32_t i = threadIdx.x; i < p.fb_count; i += kHotThreads) s_fb[i] = __ldg(p.fb_meta + p.hot_rows + i);
     for (uint32_t i = threadIdx.x; i < p.hot_long; i += kHotThreads) s_long[i] = __ldg(p.longest + i);
     if (threadIdx.x < 256) s_cls[threadIdx.x] = p.cls[threadIdx.x];
     __syncthreads();
@@ -107,12 +122,12 @@ __global__ void __launch_bounds__(kHotThreads, 1) dfa_hot_kernel(const DfaParams
         if (w < -int64_t(p.hist_valid)) w = -int64_t(p.hist_valid);
         uint32_t s = 0;
         int64_t q0 = w;
-        for (; q0 < int64_t(s0) && (q0 & 15); ++q0) s = dfa_step<kIdentCls>(s, *(p.stream + q0), p, s_hot, s_cls);
+        for (; q0 < int64_t(s0) && (q0 & 15); ++q0) s = dfa_step<kIdentCls>(s, *(p.stream + q0), p, s_hot, s_fb, s_cls);
         for (; q0 < int64_t(s0); q0 += 16) {
             const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.stream + q0));
             const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int k = 0; k < 16; ++k) s = dfa_step<kIdentCls>(s, (ws[k >> 2] >> (8 * (k & 3))) & 0xFF, p, s_hot, s_cls);
+            for (int k = 0; k < 16; ++k) s = dfa_step<kIdentCls>(s, (ws[k >> 2] >> (8 * (k & 3))) & 0xFF, p, s_hot, s_fb, s_cls);
         }
         uint64_t q = s0;
         for (; q + 16 <= s1; q += 16) {
@@ -121,7 +136,7 @@ __global__ void __launch_bounds__(kHotThreads, 1) dfa_hot_kernel(const DfaParams
             uint32_t r[8];
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                s = dfa_step<kIdentCls>(s, (ws[k >> 2] >> (8 * (k & 3))) & 0xFF, p, s_hot, s_cls);
+                s = dfa_step<kIdentCls>(s, (ws[k >> 2] >> (8 * (k & 3))) & 0xFF, p, s_hot, s_fb, s_cls);
                 const uint32_t o = dfa_longest(s, p, s_long);
                 if (k & 1) r[k >> 1] |= o << 16; else r[k >> 1] = o;
             }
@@ -130,7 +145,7 @@ __global__ void __launch_bounds__(kHotThreads, 1) dfa_hot_kernel(const DfaParams
             __stcs(dst + 1, make_uint4(r[4], r[5], r[6], r[7]));
         }
         for (; q < s1; ++q) {  // ragged end
-            s = dfa_step<kIdentCls>(s, p.stream[q], p, s_hot, s_cls);
+            s = dfa_step<kIdentCls>(s, p.stream[q], p, s_hot, s_fb, s_cls);
             p.out[q] = uint16_t(dfa_longest(s, p, s_long));
         }
     }
@@ -139,20 +154,28 @@ __global__ void __launch_bounds__(kHotThreads, 1) dfa_hot_kernel(const DfaParams
 }  // namespace
 
 void dfa_plan_hot(uint32_t n_states, uint32_t log2_ncp, const uint32_t* depth_count, uint32_t n_depths,
-                  uint32_t* hot_rows, uint32_t* hot_long) {
+                  uint32_t* hot_rows, uint32_t* hot_long, uint32_t* fb_count) {
     // Hot rows: whole BFS levels while their transition targets (states of the next level) still fit u16 and
-    // the rows fit the shared-memory budget; hot longest-ids: as many leading states as fit in the rest.
+    // the rows fit the shared-memory budget.  The next level keeps one Bloom/failure word per state if those fit
+    // beside the longest-ids of all states up to and including that level; hot longest-ids: as many leading
+    // states as fit in the rest.
     const size_t budget = 200 * 1024, row_bytes = size_t(2) << log2_ncp;
-    uint32_t rows = 0, upto = 0;
+    uint32_t rows = 0, upto = 0, levels = 0;
     for (uint32_t d = 0; d < n_depths; ++d) {
         const uint32_t level_end = upto + depth_count[d];                       // states of depth <= d
         const uint64_t next_end = uint64_t(level_end) + (d + 1 < n_depths ? depth_count[d + 1] : 0);
         if (next_end > 65536 || size_t(level_end) * row_bytes > budget - 8192) break;
         rows = level_end;
         upto = level_end;
+        levels = d + 1;
     }
     *hot_rows = rows;
-    const size_t left = budget - size_t(rows) * row_bytes;
+    size_t left = budget - size_t(rows) * row_bytes;
+    *fb_count = 0;
+    if (rows > 0 && levels < n_depths) {
+        const size_t cnt = depth_count[levels];
+        if (cnt * 4 + (size_t(rows) + cnt) * 2 <= left) { *fb_count = uint32_t(cnt); left -= cnt * 4; }
+    }
     const uint64_t max_long = left / 2;
     *hot_long = uint32_t(n_states < max_long ? n_states : max_long);
 }
@@ -172,7 +195,7 @@ cudaError_t dfa_scan_launch(const DfaParams& p_in, bool ident_cls, bool flat, in
     uint32_t seg = 4096;
     while (seg < 16384 && p.n / (uint64_t(seg) * 2) >= uint64_t(n_sms) * kHotThreads * 2) seg *= 2;
     p.seg = seg;
-    const size_t smem = (size_t(p.hot_rows) << p.log2_ncp) * 2 + size_t(p.hot_long) * 2 + 256;
+    const size_t smem = (size_t(p.hot_rows) << p.log2_ncp) * 2 + size_t(p.fb_count) * 4 + size_t(p.hot_long) * 2 + 256;
     auto kern = ident_cls ? dfa_hot_kernel<true> : dfa_hot_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;

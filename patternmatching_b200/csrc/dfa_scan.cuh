@@ -17,12 +17,15 @@ struct DfaParams {
     uint32_t warm;           // max_pat_len - 1
     uint32_t hot_rows;       // leading states whose rows are kept in shared memory as u16 (hot variant)
     uint32_t hot_long;       // leading states whose longest-ids are kept in shared memory
+    const uint32_t* fb_meta; // [state] Bloom of the goto children | failure state << 16 (see dict.hpp)
+    uint32_t fb_count;       // states [hot_rows, hot_rows + fb_count) -- the first BFS level below the hot rows -- keep
+                             // their fb_meta word in shared memory: no child on c => the step is the failure state's hot row
     uint32_t seg;            // bytes reported per thread (filled by the launcher)
 };
 
 // how many leading states go to shared memory (whole BFS levels whose targets fit u16)
 void dfa_plan_hot(uint32_t n_states, uint32_t log2_ncp, const uint32_t* depth_count, uint32_t n_depths,
-                  uint32_t* hot_rows, uint32_t* hot_long);
+                  uint32_t* hot_rows, uint32_t* hot_long, uint32_t* fb_count);
 
 cudaError_t dfa_scan_launch(const DfaParams& p, bool ident_cls, bool flat, int n_sms, cudaStream_t st, uint64_t* launches);
 

@@ -374,6 +374,13 @@ void Dict::build_dfa() {
             row[cl] = c;
         }
     }
+    d.fb_meta.assign(t.n, 0xFFFFu);
+    for (uint32_t s = 1; s < t.n; ++s) {
+        if (fail[s] >= 65536) continue;
+        uint32_t bloom = 0;
+        for (uint32_t k = t.off[s]; k < t.off[s + 1]; ++k) bloom |= 1u << (d.cls[t.byte[k]] & 15);
+        d.fb_meta[s] = bloom | (fail[s] << 16);
+    }
     d.built = true;
 }
 

@@ -69,6 +69,9 @@ struct DfaTables {
     std::vector<uint32_t> delta;   // [state << log2_ncp | cls] -> next state
     std::vector<uint16_t> longest; // [state] -> pid of the longest pattern that is a suffix of the state string
     std::vector<uint32_t> depth_count; // states per depth
+    // per state: 16-bit Bloom of the classes of its goto children (bit = class & 15) | failure state << 16 (0xFFFF =
+    // no usable entry).  A state WITHOUT a goto child on c moves like its failure state: delta(s,c) = delta(fail(s),c).
+    std::vector<uint32_t> fb_meta;
     bool built = false;
 };
 

@@ -84,6 +84,7 @@ struct pm_engine {
     uint32_t* d_delta = nullptr;
     uint16_t* d_longest = nullptr;
     uint8_t* d_dfa_cls = nullptr;
+    uint32_t* d_fb_meta = nullptr;
     bool dfa_ready = false;
     // kr tables (lazy)
     pm::KrDevTables kr{};
@@ -128,6 +129,7 @@ int ensure_dfa(pm_engine* e) {
     d->build_dfa();
     CU(upload(d->dfa.delta, &e->d_delta, &e->table_bytes));
     CU(upload(d->dfa.longest, &e->d_longest, &e->table_bytes));
+    CU(upload(d->dfa.fb_meta, &e->d_fb_meta, &e->table_bytes));
     std::vector<uint8_t> cls(d->dfa.cls, d->dfa.cls + 256);
     CU(upload(cls, &e->d_dfa_cls, &e->table_bytes));
     e->dfa_ready = true;
@@ -219,9 +221,9 @@ int choose_algo(pm_engine* e, const uint8_t* d_stream, size_t n, size_t hist_val
     const bool deep = deferred * 32 > 4 * kSampleWin;     // more than 1/32 of the positions walk past level 4
     if (!deep) { e->auto_flat = false; return PM_ALGO_SFX; }
     if (ensure_dfa(e)) return -1;
-    uint32_t hot_rows = 0, hot_long = 0;
+    uint32_t hot_rows = 0, hot_long = 0, fb_count = 0;
     const pm::Dict& d = *e->dict;
-    pm::dfa_plan_hot(d.dfa.n_states, d.dfa.log2_ncp, d.dfa.depth_count.data(), uint32_t(d.dfa.depth_count.size()), &hot_rows, &hot_long);
+    pm::dfa_plan_hot(d.dfa.n_states, d.dfa.log2_ncp, d.dfa.depth_count.data(), uint32_t(d.dfa.depth_count.size()), &hot_rows, &hot_long, &fb_count);
     e->auto_flat = hot_rows < d.dfa.n_states;              // deep walks and an automaton that does not fit: occupancy + L1 win
     return PM_ALGO_DFA;
 }
@@ -269,7 +271,9 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
         p.delta = e->d_delta; p.longest = e->d_longest; p.cls = e->d_dfa_cls; p.log2_ncp = d.dfa.log2_ncp;
         p.warm = d.max_len ? d.max_len - 1 : 0;
         pm::dfa_plan_hot(d.dfa.n_states, d.dfa.log2_ncp, d.dfa.depth_count.data(), uint32_t(d.dfa.depth_count.size()),
-                         &p.hot_rows, &p.hot_long);
+                         &p.hot_rows, &p.hot_long, &p.fb_count);
+        p.fb_meta = e->d_fb_meta;
+        if (getenv("PM_DFA_NO_FB")) p.fb_count = 0;
         cudaError_t ce = pm::dfa_scan_launch(p, d.sfx.cls_identity, force_flat || getenv("PM_DFA_FLAT") != nullptr, e->n_sms, st, &e->launches);
         if (ce != cudaSuccess) return cuda_fail(ce, "dfa_scan_launch");
         return 0;
@@ -455,7 +459,7 @@ void pm_engine_free(pm_engine* e) {
     cudaSetDevice(e->device);
     if (e->rows_tex) cudaDestroyTextureObject(e->rows_tex);
     void* ptrs[] = {e->d_root2, e->d_root1, e->d_rows, e->d_row_best, e->d_cls, e->d_pat_off, e->d_pat_len, e->d_pat_bytes,
-                    e->d_parent, e->d_chain, e->d_pidhash, e->d_tail_rec, e->d_l3f, e->d_anc_off, e->d_anc_list, e->d_sample_out, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_acc,
+                    e->d_parent, e->d_chain, e->d_pidhash, e->d_tail_rec, e->d_l3f, e->d_anc_off, e->d_anc_list, e->d_sample_out, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_fb_meta, e->d_acc,
                     e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1], e->d_queue[0], e->d_queue[1], e->d_qcount};
     for (void* p : ptrs) if (p) cudaFree(p);
     pm::kr_free_tables(&e->kr);
