@@ -488,3 +488,13 @@ def test_kr_variant_on_the_16gib_stream(engine_merged, dict_merged):
     print(f"KR vs exact on {n} positions: false_pos={fp} false_neg={fn} partial={partial}")
     assert fn == 0 and partial == 0
     assert fp <= n * 1e-7
+
+@pytest.mark.parametrize("env", [{}, {"PM_DFA_NO_FB": "1"}, {"PM_DFA_FLAT": "1"}], ids=["hot+fallback-words", "hot", "flat"])
+def test_every_variant_of_the_dfa_kernel_is_exact(env, oracle_merged, engine_merged, monkeypatch):
+    """Forward-DFA walker: hot rows + Bloom/failure words of the next level (default), hot rows only, flat."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n = 200_000 + 13
+    for kind in ("planted", "ascii", "almost"):
+        stream = oracle_merged.gen(kind, 777, n)
+        assert np.array_equal(gpu_scan(engine_merged, stream, pm.ALGO_DFA), want_pids(oracle_merged, stream)), kind
