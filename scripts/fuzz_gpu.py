@@ -1,0 +1,92 @@
+"""Differential fuzzing of the GPU kernels against the oracle: random dictionaries (alphabet size, pattern
+lengths, shared suffixes / prefixes, nested patterns) x random streams with planted occurrences x every exact
+kernel (and the randomized one against its restatement).  Usage: python scripts/fuzz_gpu.py [n_cases] [seed]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np, torch
+import patternmatching_b200 as pm
+from oracle_lib import Oracle
+
+
+def make_case(rng):
+    alpha = int(rng.choice([2, 3, 4, 16, 64, 200, 256]))
+    base = int(rng.integers(0, 257 - alpha))
+    sym = np.array([b for b in range(base, base + alpha) if b != 10] or [97], dtype=np.uint8)
+    n_pat = int(rng.choice([1, 5, 50, 500, 5000]))
+    max_len = int(rng.choice([1, 2, 3, 4, 5, 8, 9, 17, 64, 353]))
+    pats = set()
+    stems = [bytes(rng.choice(sym, int(rng.integers(1, max_len + 1)))) for _ in range(8)]
+    tries = 0
+    while len(pats) < n_pat and tries < 20 * n_pat:
+        tries += 1
+        L = int(rng.integers(1, max_len + 1))
+        p = bytes(rng.choice(sym, L))
+        mode = rng.integers(0, 4)
+        if mode == 1:   # shared suffix
+            st = stems[int(rng.integers(0, 8))]; p = (p + st)[-max_len:]
+        elif mode == 2:  # shared prefix
+            st = stems[int(rng.integers(0, 8))]; p = (st + p)[:max_len]
+        elif mode == 3 and pats:  # nested: a suffix of an existing pattern
+            q = list(pats)[int(rng.integers(0, len(pats)))]; p = q[int(rng.integers(0, len(q))):]
+        if p:
+            pats.add(p)
+    pats = sorted(pats)
+    n = int(rng.choice([1, 100, 511, 512, 513, 5000, 70000, 300001]))
+    stream = rng.choice(sym, n).astype(np.uint8)
+    if rng.integers(0, 2):   # some bytes outside the alphabet
+        k = max(1, n // 50)
+        stream[rng.integers(0, n, k)] = rng.integers(0, 256, k).astype(np.uint8)
+    for _ in range(int(rng.integers(0, 1 + n // 20))):   # planted occurrences
+        p = pats[int(rng.integers(0, len(pats)))]
+        c = int(rng.integers(0, n))
+        stream[c:c + len(p)] = np.frombuffer(p, np.uint8)[: n - c]
+    hist = int(rng.choice([0, 0, 1, 3, 4, 15, 16, 17, 351, 352, 353, 1000]))
+    return pats, stream, hist
+
+
+def main():
+    n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    rng = np.random.default_rng(seed)
+    dev = torch.device("cuda:0")
+    bad = 0
+    for case in range(n_cases):
+        pats, stream, hist = make_case(rng)
+        d = pm.Dictionary(); o = Oracle()
+        for i, p in enumerate(pats):
+            d.add_pattern(p, 0, i + 1); o.add_pattern(p, 0, i + 1)
+        d.compile(); o.compile()
+        eng = pm.Engine(d)
+        hist = min(hist, stream.size - 1) if stream.size > 1 else 0
+        body = stream[hist:]
+        o.reset()
+        want_all = (o.scan(stream) + 1).astype(np.uint16)
+        want = want_all[hist:]
+        pad = (-hist) % 16
+        buf = np.concatenate([np.zeros(pad, np.uint8), stream])
+        d_in = torch.from_numpy(buf).to(dev)
+        for algo, name in ((pm.ALGO_SFX, "sfx"), (pm.ALGO_DFA, "dfa"), (pm.ALGO_AUTO, "auto")):
+            d_out = torch.zeros(max(body.size, 8), dtype=torch.int16, device=dev)
+            eng.scan_device(d_in.data_ptr() + pad + hist, body.size, d_out, hist_valid=hist, algo=algo)
+            torch.cuda.synchronize()
+            got = d_out.cpu().numpy().view(np.uint16)[:body.size]
+            if not np.array_equal(got, want):
+                bad += 1
+                w = np.nonzero(got != want)[0]
+                print(f"MISMATCH case {case} algo {name}: {len(pats)} patterns, n={body.size}, hist={hist}, first diff at {w[:5]} got {got[w[:5]]} want {want[w[:5]]}", flush=True)
+        # host path with arbitrary cuts
+        eng.reset()
+        cuts = sorted(set([0, stream.size] + [int(x) for x in rng.integers(0, stream.size + 1, 3)]))
+        outs = [eng.scan_host(stream[a:b], algo=pm.ALGO_SFX) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        got = np.concatenate(outs) if outs else np.zeros(0, np.uint16)
+        if not np.array_equal(got, want_all):
+            bad += 1
+            print(f"MISMATCH case {case} scan_host cuts {cuts}", flush=True)
+        print(f"case {case}: {len(pats)} patterns (max len {max(map(len, pats))}), classes {d.info.n_classes}, n={body.size}, hist={hist}: ok" if not bad else f"case {case} done", flush=True)
+    print("FUZZ RESULT:", "all equal" if bad == 0 else f"{bad} mismatches")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

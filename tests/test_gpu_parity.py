@@ -498,3 +498,18 @@ def test_every_variant_of_the_dfa_kernel_is_exact(env, oracle_merged, engine_mer
     for kind in ("planted", "ascii", "almost"):
         stream = oracle_merged.gen(kind, 777, n)
         assert np.array_equal(gpu_scan(engine_merged, stream, pm.ALGO_DFA), want_pids(oracle_merged, stream)), kind
+
+def test_differential_fuzz_small():
+    """Random dictionaries (2 .. 256 byte classes, lengths 1 .. 353, shared suffixes / prefixes, nested patterns) x
+    random streams with planted occurrences and history: sfx, dfa, auto and the chunked host path against the
+    oracle (scripts/fuzz_gpu.py; 25 seeded cases here, hundreds were run during development)."""
+    import importlib.util, sys
+    spec = importlib.util.spec_from_file_location("fuzz_gpu", os.path.join(os.path.dirname(GOLDEN), "..", "scripts", "fuzz_gpu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    argv = sys.argv
+    try:
+        sys.argv = ["fuzz_gpu.py", "25", "7"]
+        assert mod.main() == 0
+    finally:
+        sys.argv = argv
