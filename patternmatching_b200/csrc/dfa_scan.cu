@@ -27,6 +27,18 @@ namespace {
 constexpr int kThreads = 128;      // flat variant
 constexpr int kHotThreads = 1024;  // hot variant: one CTA per SM, ~200 KB of hot tables
 
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): a lane's 32 stream bytes or its 16 results (32 bytes)
+// move as ONE sector instead of two half-filled ones -- the per-lane segment I/O is a third of this kernel's
+// LSU traffic.  Addresses must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const uint8_t* ptr, uint32_t (&w)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(ptr));
+}
+__device__ __forceinline__ void stg256(uint16_t* ptr, const uint32_t (&r)[8]) {
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads) dfa_flat_kernel(const DfaParams p) {
     const uint64_t seg = uint64_t(blockIdx.x) * kThreads + threadIdx.x;
     const uint64_t s0 = seg * uint64_t(p.seg);
@@ -54,6 +66,24 @@ __global__ void __launch_bounds__(kThreads) dfa_flat_kernel(const DfaParams p) {
     }
     // own segment: 16 bytes in, 16 results (32 bytes) out per step
     uint64_t q = s0;
+    if (p.wide) {
+        for (; q + 32 <= s1; q += 32) {
+            uint32_t ws[8];
+            ldg256(p.stream + q, ws);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[8];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t c = (ws[half * 4 + (k >> 2)] >> (8 * (k & 3))) & 0xFF;
+                    s = __ldg(delta + ((size_t(s) << l2) | __ldg(cls + c)));
+                    const uint32_t o = __ldg(longest + s);
+                    if (k & 1) r[k >> 1] |= o << 16; else r[k >> 1] = o;
+                }
+                stg256(p.out + q + half * 16, r);
+            }
+        }
+    }
     for (; q + 16 <= s1; q += 16) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.stream + q));
         const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
@@ -130,6 +160,23 @@ __global__ void __launch_bounds__(kHotThreads, 1) dfa_hot_kernel(const DfaParams
             for (int k = 0; k < 16; ++k) s = dfa_step<kIdentCls>(s, (ws[k >> 2] >> (8 * (k & 3))) & 0xFF, p, s_hot, s_fb, s_cls);
         }
         uint64_t q = s0;
+        if (p.wide) {   // stream and result base 32-byte aligned (segments start at multiples of 4 KiB)
+            for (; q + 32 <= s1; q += 32) {
+                uint32_t ws[8];
+                ldg256(p.stream + q, ws);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r[8];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        s = dfa_step<kIdentCls>(s, (ws[half * 4 + (k >> 2)] >> (8 * (k & 3))) & 0xFF, p, s_hot, s_fb, s_cls);
+                        const uint32_t o = dfa_longest(s, p, s_long);
+                        if (k & 1) r[k >> 1] |= o << 16; else r[k >> 1] = o;
+                    }
+                    stg256(p.out + q + half * 16, r);
+                }
+            }
+        }
         for (; q + 16 <= s1; q += 16) {
             const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.stream + q));
             const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
@@ -183,6 +230,7 @@ void dfa_plan_hot(uint32_t n_states, uint32_t log2_ncp, const uint32_t* depth_co
 cudaError_t dfa_scan_launch(const DfaParams& p_in, bool ident_cls, bool flat, int n_sms, cudaStream_t st, uint64_t* launches) {
     DfaParams p = p_in;
     if (p.n == 0) return cudaSuccess;
+    p.wide = ((reinterpret_cast<uintptr_t>(p.stream) | reinterpret_cast<uintptr_t>(p.out)) & 31) == 0;
     if (flat || p.hot_rows == 0) {
         p.seg = 4096;
         const uint64_t segs = (p.n + p.seg - 1) / p.seg;

@@ -21,6 +21,7 @@ struct DfaParams {
     uint32_t fb_count;       // states [hot_rows, hot_rows + fb_count) -- the first BFS level below the hot rows -- keep
                              // their fb_meta word in shared memory: no child on c => the step is the failure state's hot row
     uint32_t seg;            // bytes reported per thread (filled by the launcher)
+    uint32_t wide;           // stream and out are 32-byte aligned: 256-bit segment I/O (filled by the launcher)
 };
 
 // how many leading states go to shared memory (whole BFS levels whose targets fit u16)
