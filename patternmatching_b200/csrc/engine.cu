@@ -535,12 +535,15 @@ int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n,
     if (algo == PM_ALGO_KR && ensure_kr(e)) return -1;
     if (algo == PM_ALGO_AUTO && e->auto_choice < 0 && n < 4 * kSampleWin) algo = PM_ALGO_SFX;  // too short to sample
     const bool in_pinned = is_pinned(stream), out_pinned = is_pinned(out);
-    const size_t n_chunks = (n + kHostChunk - 1) / kHostChunk;
+    // pageable buffers go through the pinned staging buffers with memcpy on this thread: smaller pieces, so that the
+    // copies of one piece overlap the transfers and the scan of its neighbours
+    const size_t chunk = (in_pinned && out_pinned) ? kHostChunk : std::min<size_t>(kHostChunk, size_t(2) << 20);
+    const size_t n_chunks = (n + chunk - 1) / chunk;
     auto drain = [&](size_t k) -> int {  // chunk k has fully left the device
         const int b = int(k & 1);
         CU(cudaEventSynchronize(e->done[b]));
         if (!out_pinned) {
-            const size_t o = k * kHostChunk, len = std::min(kHostChunk, n - o);
+            const size_t o = k * chunk, len = std::min(chunk, n - o);
             memcpy(out + o, e->h_out[b], len * sizeof(uint16_t));
         }
         return 0;
@@ -548,7 +551,7 @@ int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n,
     for (size_t k = 0; k < n_chunks; ++k) {
         const int b = int(k & 1);
         if (k >= 2 && drain(k - 2)) return -1;
-        const size_t o = k * kHostChunk, len = std::min(kHostChunk, n - o);
+        const size_t o = k * chunk, len = std::min(chunk, n - o);
         // history in front of the chunk: from this call's own bytes when there are enough, else carried
         const size_t from_call = std::min<size_t>(o, pm::kHalo);
         const size_t hist_total = std::min<size_t>(e->hist_valid + o, pm::kHalo);  // valid history bytes
