@@ -482,11 +482,10 @@ void Dict::build_kr(uint64_t seed) {
             while (k.slot_fp[h] != 0xFFFFFFFFu) h = (h + 1) & mask;
             k.slot_fp[h] = cs[i].fp8;
             k.slot_begin[h] = uint32_t(i);
-            // two Bloom bits per key: the low 19 bits and bits 12..30 of the fingerprint
-            const uint32_t bit = cs[i].fp8 & ((1u << k.bloom_bits) - 1);
-            const uint32_t bit2 = (cs[i].fp8 >> 12) & ((1u << k.bloom_bits) - 1);
-            k.bloom[bit >> 5] |= 1u << (bit & 31);
-            k.bloom[bit2 >> 5] |= 1u << (bit2 & 31);
+            for (int hk = 0; hk < kKrBloomHashes; ++hk) {
+                const uint32_t bit = kr_bloom_bit(cs[i].fp8, hk);
+                k.bloom[bit >> 5] |= 1u << (bit & 31);
+            }
         }
         uint32_t h = uint32_t(splitmix64(cs[i].fp8)) & mask;
         while (k.slot_fp[h] != cs[i].fp8) h = (h + 1) & mask;

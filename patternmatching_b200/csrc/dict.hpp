@@ -136,6 +136,18 @@ class Dict {
 
 // Modular arithmetic in GF(2^31-1) shared by host table construction (and mirrored on the device).
 inline uint64_t kr_mul(uint64_t a, uint64_t b) { return (a * b) % kKrP; }
+
+// Bloom bitmap of the 8-byte-suffix fingerprints (2^19 bits): kKrBloomHashes multiplicative hashes per key.  With
+// ~35 k keys the bitmap is 24% full and a random fingerprint passes all four tests with probability 0.3%; the
+// kernel evaluates them one after the other, so the later ones are almost free.
+constexpr int kKrBloomHashes = 4;
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t kr_bloom_bit(uint32_t fp8, int k) {
+    const uint32_t c = k == 0 ? 0x9E3779B1u : k == 1 ? 0x85EBCA77u : k == 2 ? 0xC2B2AE3Du : 0x27D4EB2Fu;
+    return (fp8 * c) >> 13;   // top 19 bits of the product
+}
 uint64_t kr_pow(uint64_t a, uint64_t e);
 uint64_t kr_inv(uint64_t a);
 uint64_t kr_fp(const uint8_t* s, size_t n, uint64_t r);  // sum s[i] r^i mod p, unsigned bytes

@@ -8,12 +8,12 @@
 // Reference behaviour NOT kept: the O(#patterns) loop per byte (Core/src/mpbg.c:132-145), the
 // unseeded r (bgps.c:469-475) and the bugs that stop it reporting any pattern > 8 bytes.
 //
-// Per tile of 8192 positions (+352-byte halo) a CTA
-//   1. stages the bytes with one bulk async copy,
-//   2. builds the prefix fingerprints PHI(x) = sum_{t<=x} s[t] r^t mod p with a block-wide modular
-//      prefix sum (per-thread serial part, warp-shuffle scan, cross-warp scan),
-//   3. for every position forms the fingerprint of the last 8 bytes, (PHI(x)-PHI(x-8)) r^-(x-7),
-//      tests it against a 64 KiB two-hash Bloom bitmap in shared memory, and only on a hit probes the
+// Per tile of 1024 positions (+352-byte halo) a WARP
+//   1. stages the bytes in its private part of shared memory (coalesced 16-byte loads),
+//   2. builds the prefix fingerprints PHI(x) = sum_{t<x} s[t] r^t mod p with a warp-wide modular prefix sum
+//      (43 serial terms per lane, warp-shuffle scan of the lane totals, offsets added back),
+//   3. for every position forms the fingerprint of the last 8 bytes, (PHI(x+1)-PHI(x-7)) r^-(x-7),
+//      tests it against a 64 KiB four-hash Bloom bitmap in shared memory, and only on a hit probes the
 //      open-addressing table of 8-byte-suffix fingerprints in global memory and verifies the
 //      candidates stage by stage (16, 32, ... bytes, then the full length), longest first.
 // A pattern > 8 bytes is reported iff ALL its stage fingerprints agree; a false positive needs a
@@ -24,19 +24,25 @@
 namespace pm {
 namespace {
 
-constexpr int kThreads = 512;                                  // two CTAs per SM: one computes while the other waits at a barrier
-constexpr int kSpan = kHalo + kKrTile;                        // staged bytes
-constexpr int kElems = (kSpan + kThreads - 1) / kThreads;     // elements per thread in the prefix sum (9)
-constexpr int kPosPer = kKrTile / kThreads;                   // reported positions per thread (8)
+// Every WARP owns a tile: no block-wide barrier anywhere after start-up, so the warps of an SM hide each other's
+// latencies (the first version built the prefix sum per CTA over 8 KiB tiles and spent 63% of its issue slots
+// waiting at the five barriers per tile).
+constexpr int kWarps = 20;
+constexpr int kThreads = kWarps * 32;
+constexpr int kWT = kKrTile;                                   // positions per warp tile (1024)
+constexpr int kSpan = kHalo + kWT;                            // staged bytes per tile (1376)
+constexpr int kPerLane = kSpan / 32;                          // elements per lane in the prefix sum (43: odd => conflict-free)
+static_assert(kSpan % 32 == 0 && (kPerLane & 1) == 1 && kSpan % 16 == 0, "tile geometry");
 constexpr int kBloomWords = (1 << 19) / 32;
 
+constexpr int kPowBytes = ((kSpan + 1) * 4 + 15) / 16 * 16;   // one power table
 constexpr int kOffBloom = 0;                                  // 65536
-constexpr int kOffPhi = kOffBloom + kBloomWords * 4;          // (kSpan + 1) x u32
-constexpr int kOffBytes = ((kOffPhi + (kSpan + 1) * 4 + 15) / 16) * 16;
-constexpr int kOffWarp = kOffBytes + kElems * kThreads;       // padded so every thread may read its 9 bytes
-constexpr int kOffBar = kOffWarp + 32 * 4;
-constexpr int kSmem = kOffBar + 16;
-static_assert(kSmem <= 227 * 1024, "shared memory budget");
+constexpr int kOffRpow = kOffBloom + kBloomWords * 4;
+constexpr int kOffRinv = kOffRpow + kPowBytes;
+constexpr int kOffWarp = kOffRinv + kPowBytes;                // per warp: phi[(kSpan + 1)] u32, then the staged bytes
+constexpr int kWarpBytes = kPowBytes + kSpan;
+constexpr int kSmem = kOffWarp + kWarps * kWarpBytes;
+static_assert(kWarpBytes % 16 == 0 && kSmem <= 227 * 1024, "shared memory budget");
 
 struct KrParams {
     KrDevTables t;
@@ -72,116 +78,114 @@ __device__ __noinline__ uint32_t kr_verify(const KrDevTables& t, const uint32_t*
     return 0;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) kr_scan_kernel(const KrParams p) {
+// s[x] * r^x mod p for a byte s[x] < 256: the product is < 2^39, one fold and one conditional subtract
+__device__ __forceinline__ uint32_t kr_mul_byte(uint32_t byte, uint32_t pw) {
+    const uint64_t x = uint64_t(byte) * pw;
+    const uint32_t v = uint32_t(x & 0x7FFFFFFFu) + uint32_t(x >> 31);
+    return v >= 0x7FFFFFFFu ? v - 0x7FFFFFFFu : v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* s_bloom = reinterpret_cast<uint32_t*>(smem + kOffBloom);
-    uint32_t* s_phi = reinterpret_cast<uint32_t*>(smem + kOffPhi);
-    uint8_t* s_bytes = smem + kOffBytes;
-    uint32_t* s_warp = reinterpret_cast<uint32_t*>(smem + kOffWarp);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
+    uint32_t* s_rpow = reinterpret_cast<uint32_t*>(smem + kOffRpow);
+    uint32_t* s_rinv = reinterpret_cast<uint32_t*>(smem + kOffRinv);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const bool have_halo = p.hist_valid >= uint64_t(kHalo);
+    uint32_t* s_phi = reinterpret_cast<uint32_t*>(smem + kOffWarp + wid * kWarpBytes);
+    uint8_t* s_bytes = reinterpret_cast<uint8_t*>(s_phi) + kPowBytes;
 
-    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     for (int i = tid; i < kBloomWords; i += kThreads) s_bloom[i] = __ldg(p.t.bloom + i);
-    for (int i = tid; i < (kElems * kThreads) / 4; i += kThreads) reinterpret_cast<uint32_t*>(s_bytes)[i] = 0;
-    fence_proxy_async();
-    __syncthreads();
+    for (int i = tid; i <= kSpan; i += kThreads) { s_rpow[i] = __ldg(p.t.rpow + i); s_rinv[i] = __ldg(p.t.rinvpow + i); }
+    __syncthreads();  // the only CTA-wide barrier
 
-    uint32_t it = 0;
-    for (uint64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
-        const uint64_t s0 = t * uint64_t(kKrTile);
-        const uint32_t len = uint32_t(min(uint64_t(kKrTile), p.n - s0));
-        const bool halo = (t > 0) || have_halo;
-        const uint32_t body = len & ~15u;
-        if (tid == 0) {
-            const uint32_t bytes = body + (halo ? kHalo : 0);
-            mbar_arrive_expect_tx(bar, bytes);
-            if (bytes) bulk_g2s(s_bytes + (halo ? 0 : kHalo), p.stream + s0 - (halo ? kHalo : 0), bytes, bar);
-        }
-        // exact results of this tile's positions -> "longest pattern of <= 8 bytes" (two dependent global loads):
-        // issued now, consumed after the prefix sum, so their latency hides behind the tile load and the scan
-        uint32_t short_pid[kPosPer];
+    const uint64_t gw = uint64_t(blockIdx.x) * kWarps + wid, G = uint64_t(gridDim.x) * kWarps;
+    for (uint64_t t = gw; t < p.n_tiles; t += G) {
+        const uint64_t s0 = t * uint64_t(kWT);
+        const uint32_t len = uint32_t(min(uint64_t(kWT), p.n - s0));
+        // ---- stage [s0 - kHalo, s0 + kWT): 16-byte pieces, zeros where the stream has no byte ----
+        const int64_t lo = -int64_t(p.hist_valid), hi = int64_t(p.n);   // readable range, relative to p.stream
 #pragma unroll
-        for (int k = 0; k < kPosPer; ++k) {
-            const uint32_t q = uint32_t(k) * kThreads + tid;
-            short_pid[k] = q < len ? uint32_t(p.out[s0 + q]) : 0u;
+        for (int k = 0; k < (kSpan / 16 + 31) / 32; ++k) {
+            const int j = k * 32 + lane;
+            if (j < kSpan / 16) {
+                const int64_t g = int64_t(s0) - kHalo + 16 * j;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (g >= lo && g + 16 <= hi) {
+                    v = __ldg(reinterpret_cast<const uint4*>(p.stream + g));
+                } else if (g + 16 > lo && g < hi) {
+                    uint32_t w[4] = {0, 0, 0, 0};
+                    for (int b = 0; b < 16; ++b)
+                        if (g + b >= lo && g + b < hi) w[b >> 2] |= uint32_t(p.stream[g + b]) << (8 * (b & 3));
+                    v = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                reinterpret_cast<uint4*>(s_bytes)[j] = v;
+            }
         }
-#pragma unroll
-        for (int k = 0; k < kPosPer; ++k) short_pid[k] = __ldg(p.t.short_of + short_pid[k]);
-        if (!halo) for (int i = tid; i < kHalo; i += kThreads) s_bytes[i] = 0;
-        if (uint32_t(tid) < (len & 15u)) s_bytes[kHalo + body + tid] = p.stream[s0 + body + tid];
-        mbar_wait(bar, it & 1);
-        __syncthreads();
+        __syncwarp();
 
-        // ---- block-wide modular prefix sum of s[x] * r^x ----
-        // pass 1, interleaved mapping (coalesced reads of the power table): the terms go to s_phi[x + 1]
-        for (int x = tid; x < kSpan; x += kThreads) s_phi[x + 1] = kr_mulmod(s_bytes[x], __ldg(p.t.rpow + x));
-        __syncthreads();
-        // pass 2, blocked mapping: every thread sums its kElems consecutive terms (stride-kElems reads, kElems odd:
-        // conflict-free), then the thread totals are scanned across the block
-        uint32_t loc[kElems];
+        // ---- warp-wide modular prefix sum of s[x] * r^x: PHI(x) = sum_{t < x} term(t), phi[0] = 0 ----
+        // blocked mapping: lane l owns x in [43 l, 43 l + 43); the stride (43 words) is odd: conflict-free
+        const int x0 = lane * kPerLane;
         uint32_t acc = 0;
-        const int x0 = tid * kElems;
-#pragma unroll
-        for (int k = 0; k < kElems; ++k) {
-            const int x = x0 + k;
-            const uint32_t term = x < kSpan ? s_phi[x + 1] : 0u;
-            acc = kr_addmod(acc, term);
-            loc[k] = acc;
+#pragma unroll 4
+        for (int k = 0; k < kPerLane; ++k) {
+            acc = kr_addmod(acc, kr_mul_byte(s_bytes[x0 + k], s_rpow[x0 + k]));
+            s_phi[x0 + k + 1] = acc;               // inclusive within the lane
         }
-        uint32_t inc = acc;  // inclusive warp scan of the thread totals
+        uint32_t inc = acc;                         // inclusive warp scan of the lane totals
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
             if (lane >= o) inc = kr_addmod(inc, y);
         }
-        if (lane == 31) s_warp[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            const uint32_t w = s_warp[lane];
-            uint32_t z = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, z, o);
-                if (lane >= o) z = kr_addmod(z, y);
-            }
-            s_warp[lane] = kr_submod(z, w);  // exclusive offset of each warp
-        }
-        __syncthreads();
-        const uint32_t offs = kr_addmod(s_warp[wid], kr_submod(inc, acc));
-#pragma unroll
-        for (int k = 0; k < kElems; ++k) {
-            const int x = x0 + k;
-            if (x < kSpan) s_phi[x + 1] = kr_addmod(offs, loc[k]);
-        }
-        if (tid == 0) s_phi[0] = 0;
-        __syncthreads();
+        const uint32_t offs = kr_submod(inc, acc);  // exclusive offset of this lane
+        if (lane == 0) s_phi[0] = 0;
+#pragma unroll 4
+        for (int k = 0; k < kPerLane; ++k) s_phi[x0 + k + 1] = kr_addmod(s_phi[x0 + k + 1], offs);
+        __syncwarp();
 
         // ---- per position: stage-8 fingerprint, Bloom test, verification ----
-        // position k * kThreads + tid: consecutive lanes take consecutive positions, so the PHI reads are
-        // conflict-free (a blocked mapping would be an 8- or 16-way bank conflict) and the result stores coalesce
+        // position k * 32 + lane: consecutive lanes take consecutive positions (conflict-free PHI reads, coalesced
+        // result traffic).  The exact result of the position is read first: it supplies, through short_of[], the
+        // longest pattern of <= 8 bytes ending there (those are matched exactly).
+#pragma unroll 1
+        for (int kb = 0; kb < kWT / 32; kb += 8) {
+            uint32_t sp[8];
 #pragma unroll
-        for (int k = 0; k < kPosPer; ++k) {
-            const uint32_t q = uint32_t(k) * kThreads + tid;
-            if (q < len) {
-                const uint64_t i = s0 + q;
-                uint32_t r = short_pid[k];
-                const uint64_t avail = i + p.hist_valid + 1;  // bytes of the stream up to and incl. c[i]
-                if (avail >= 9) {
-                    const int x = kHalo + int(q);
-                    const uint32_t f8 = win_fp(s_phi, p.t.rinvpow, x, 8);
-                    const uint32_t bit = f8 & ((1u << 19) - 1);
-                    const uint32_t bit2 = (f8 >> 12) & ((1u << 19) - 1);
-                    if (((s_bloom[bit >> 5] >> (bit & 31)) & 1u) && ((s_bloom[bit2 >> 5] >> (bit2 & 31)) & 1u)) {
-                        const uint32_t hit = kr_verify(p.t, s_phi, x, f8, avail);
-                        if (hit) r = hit;
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t q = uint32_t(kb + k) * 32 + lane;
+                sp[k] = q < len ? uint32_t(p.out[s0 + q]) : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sp[k] = __ldg(p.t.short_of + sp[k]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t q = uint32_t(kb + k) * 32 + lane;
+                if (q < len) {
+                    const uint64_t i = s0 + q;
+                    uint32_t r = sp[k];
+                    const uint64_t avail = i + p.hist_valid + 1;  // bytes of the stream up to and incl. c[i]
+                    if (avail >= 9) {
+                        const int x = kHalo + int(q);
+                        const uint32_t f8 = kr_mulmod(kr_submod(s_phi[x + 1], s_phi[x - 7]), s_rinv[x - 7]);
+                        bool pass = true;
+#pragma unroll
+                        for (int hk = 0; hk < kKrBloomHashes; ++hk) {
+                            if (pass) {
+                                const uint32_t bit = kr_bloom_bit(f8, hk);
+                                pass = ((s_bloom[bit >> 5] >> (bit & 31)) & 1u) != 0;
+                            }
+                        }
+                        if (pass) {
+                            const uint32_t hit = kr_verify(p.t, s_phi, x, f8, avail);
+                            if (hit) r = hit;
+                        }
                     }
+                    p.out[i] = uint16_t(r);
                 }
-                p.out[i] = uint16_t(r);
             }
         }
-        __syncthreads();  // s_bytes / s_phi are rewritten by the next tile
+        __syncwarp();  // s_bytes / s_phi are rewritten by the next tile
     }
 }
 
@@ -234,7 +238,8 @@ cudaError_t kr_scan_launch(const KrDevTables& t, const uint8_t* stream, uint64_t
     p.n_tiles = uint32_t((n + kKrTile - 1) / kKrTile);
     cudaError_t e = cudaFuncSetAttribute(kr_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return e;
-    const uint32_t grid = p.n_tiles < uint32_t(2 * n_sms) ? p.n_tiles : uint32_t(2 * n_sms);
+    const uint32_t ctas = (p.n_tiles + kWarps - 1) / kWarps;
+    const uint32_t grid = ctas < uint32_t(n_sms) ? ctas : uint32_t(n_sms);
     kr_scan_kernel<<<grid, kThreads, kSmem, st>>>(p);
     ++*launches;
     return cudaGetLastError();

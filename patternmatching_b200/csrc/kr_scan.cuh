@@ -8,7 +8,7 @@
 
 namespace pm {
 
-constexpr int kKrTile = 8192;  // positions per CTA iteration
+constexpr int kKrTile = 1024;  // positions per warp tile
 
 struct KrDevTables {
     uint32_t r = 0;
