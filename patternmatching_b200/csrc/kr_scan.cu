@@ -8,14 +8,15 @@
 // Reference behaviour NOT kept: the O(#patterns) loop per byte (Core/src/mpbg.c:132-145), the
 // unseeded r (bgps.c:469-475) and the bugs that stop it reporting any pattern > 8 bytes.
 //
-// Per tile of 1024 positions (+352-byte halo) a WARP
+// Per tile of 512 positions (+32 bytes before it) a WARP
 //   1. stages the bytes in its private part of shared memory (coalesced 16-byte loads),
 //   2. builds the prefix fingerprints PHI(x) = sum_{t<x} s[t] r^t mod p with a warp-wide modular prefix sum
-//      (43 serial terms per lane, warp-shuffle scan of the lane totals, offsets added back),
+//      (17 serial terms per lane, warp-shuffle scan of the lane totals, offsets added back),
 //   3. for every position forms the fingerprint of the last 8 bytes, (PHI(x+1)-PHI(x-7)) r^-(x-7),
 //      tests it against a 64 KiB four-hash Bloom bitmap in shared memory, and only on a hit probes the
 //      open-addressing table of 8-byte-suffix fingerprints in global memory and verifies the
-//      candidates stage by stage (16, 32, ... bytes, then the full length), longest first.
+//      candidates stage by stage (16, 32, ... bytes, then the full length), longest first; the longer window
+//      fingerprints are extended from the 8-byte one, one stream byte and one multiplication at a time.
 // A pattern > 8 bytes is reported iff ALL its stage fingerprints agree; a false positive needs a
 // simultaneous collision in every stage.
 #include "kr_scan.cuh"
@@ -26,13 +27,15 @@ namespace {
 
 // Every WARP owns a tile: no block-wide barrier anywhere after start-up, so the warps of an SM hide each other's
 // latencies (the first version built the prefix sum per CTA over 8 KiB tiles and spent 63% of its issue slots
-// waiting at the five barriers per tile).
-constexpr int kWarps = 20;
+// waiting at the five barriers per tile).  The prefix sum only has to reach 8 bytes back (the stage every
+// position is tested for); the longer stages of the rare candidates are extended byte by byte from the stream.
+constexpr int kWarps = 32;
 constexpr int kThreads = kWarps * 32;
-constexpr int kWT = kKrTile;                                   // positions per warp tile (1024)
-constexpr int kSpan = kHalo + kWT;                            // staged bytes per tile (1376)
-constexpr int kPerLane = kSpan / 32;                          // elements per lane in the prefix sum (43: odd => conflict-free)
-static_assert(kSpan % 32 == 0 && (kPerLane & 1) == 1 && kSpan % 16 == 0, "tile geometry");
+constexpr int kWT = kKrTile;                                   // positions per warp tile (512)
+constexpr int kLead = 32;                                     // staged bytes before the tile (>= 7, multiple of 16)
+constexpr int kSpan = kLead + kWT;                            // staged bytes per tile (544)
+constexpr int kPerLane = kSpan / 32;                          // elements per lane in the prefix sum (17: odd => conflict-free)
+static_assert(kSpan % 32 == 0 && (kPerLane & 1) == 1 && kSpan % 16 == 0 && kLead >= 7, "tile geometry");
 constexpr int kBloomWords = (1 << 19) / 32;
 
 constexpr int kPowBytes = ((kSpan + 1) * 4 + 15) / 16 * 16;   // one power table
@@ -53,12 +56,11 @@ struct KrParams {
     uint32_t n_tiles;
 };
 
-__device__ __forceinline__ uint32_t win_fp(const uint32_t* phi, const uint32_t* __restrict__ rinvpow, int x, int l) {
-    // fingerprint of the l bytes ending at tile-relative index x (Fingerprint.h:66-73, calc_fp_suffix)
-    return kr_mulmod(kr_submod(phi[x + 1], phi[x + 1 - l]), __ldg(rinvpow + (x + 1 - l)));
-}
-
-__device__ __noinline__ uint32_t kr_verify(const KrDevTables& t, const uint32_t* phi, int x, uint32_t f8, uint64_t avail) {
+// A position whose 8-byte fingerprint passed the Bloom test: probe the table of 8-byte-suffix fingerprints and
+// check the candidates, longest first.  The window fingerprint is extended backwards one byte at a time from the
+// stream, fp_{m+1} = s[i-m] + r * fp_m (the sliding identity of Fingerprint.h:75-89 turned around), and compared
+// at every doubling stage and at the full length.  `ci` points at c[i].
+__device__ __noinline__ uint32_t kr_verify(const KrDevTables& t, const uint8_t* __restrict__ ci, uint32_t f8, uint64_t avail) {
     uint32_t h = uint32_t(splitmix64_d(f8)) & t.bucket_mask;
     for (;;) {
         const uint32_t sf = __ldg(t.slot_fp + h);
@@ -71,9 +73,15 @@ __device__ __noinline__ uint32_t kr_verify(const KrDevTables& t, const uint32_t*
         const uint32_t len = __ldg(t.cand_len + k);
         if (uint64_t(len) > avail) continue;
         const uint32_t* sfp = t.stage_fp + __ldg(t.cand_stage_off + k);
+        uint32_t fp = f8, m = 8;
         bool ok = true;
-        for (uint32_t l = 16; l <= len && ok; l <<= 1, ++sfp) ok = win_fp(phi, t.rinvpow, x, int(l)) == __ldg(sfp);
-        if (ok && win_fp(phi, t.rinvpow, x, int(len)) == __ldg(sfp)) return __ldg(t.cand_pid + k);
+        for (uint32_t l = 16; l <= len && ok; l <<= 1, ++sfp) {
+            for (; m < l; ++m) fp = kr_addmod(kr_mulmod(fp, t.r), uint32_t(__ldg(ci - m)));
+            ok = fp == __ldg(sfp);
+        }
+        if (!ok) continue;
+        for (; m < len; ++m) fp = kr_addmod(kr_mulmod(fp, t.r), uint32_t(__ldg(ci - m)));
+        if (fp == __ldg(sfp)) return __ldg(t.cand_pid + k);
     }
     return 0;
 }
@@ -102,13 +110,13 @@ __global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) 
     for (uint64_t t = gw; t < p.n_tiles; t += G) {
         const uint64_t s0 = t * uint64_t(kWT);
         const uint32_t len = uint32_t(min(uint64_t(kWT), p.n - s0));
-        // ---- stage [s0 - kHalo, s0 + kWT): 16-byte pieces, zeros where the stream has no byte ----
+        // ---- stage [s0 - kLead, s0 + kWT): 16-byte pieces, zeros where the stream has no byte ----
         const int64_t lo = -int64_t(p.hist_valid), hi = int64_t(p.n);   // readable range, relative to p.stream
 #pragma unroll
         for (int k = 0; k < (kSpan / 16 + 31) / 32; ++k) {
             const int j = k * 32 + lane;
             if (j < kSpan / 16) {
-                const int64_t g = int64_t(s0) - kHalo + 16 * j;
+                const int64_t g = int64_t(s0) - kLead + 16 * j;
                 uint4 v = make_uint4(0, 0, 0, 0);
                 if (g >= lo && g + 16 <= hi) {
                     v = __ldg(reinterpret_cast<const uint4*>(p.stream + g));
@@ -124,10 +132,10 @@ __global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) 
         __syncwarp();
 
         // ---- warp-wide modular prefix sum of s[x] * r^x: PHI(x) = sum_{t < x} term(t), phi[0] = 0 ----
-        // blocked mapping: lane l owns x in [43 l, 43 l + 43); the stride (43 words) is odd: conflict-free
+        // blocked mapping: lane l owns x in [17 l, 17 l + 17); the stride (17 words) is odd: conflict-free
         const int x0 = lane * kPerLane;
         uint32_t acc = 0;
-#pragma unroll 4
+#pragma unroll
         for (int k = 0; k < kPerLane; ++k) {
             acc = kr_addmod(acc, kr_mul_byte(s_bytes[x0 + k], s_rpow[x0 + k]));
             s_phi[x0 + k + 1] = acc;               // inclusive within the lane
@@ -140,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) 
         }
         const uint32_t offs = kr_submod(inc, acc);  // exclusive offset of this lane
         if (lane == 0) s_phi[0] = 0;
-#pragma unroll 4
+#pragma unroll
         for (int k = 0; k < kPerLane; ++k) s_phi[x0 + k + 1] = kr_addmod(s_phi[x0 + k + 1], offs);
         __syncwarp();
 
@@ -149,24 +157,24 @@ __global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) 
         // result traffic).  The exact result of the position is read first: it supplies, through short_of[], the
         // longest pattern of <= 8 bytes ending there (those are matched exactly).
 #pragma unroll 1
-        for (int kb = 0; kb < kWT / 32; kb += 8) {
-            uint32_t sp[8];
+        for (int kb = 0; kb < kWT / 32; kb += 4) {
+            uint32_t sp[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 4; ++k) {
                 const uint32_t q = uint32_t(kb + k) * 32 + lane;
                 sp[k] = q < len ? uint32_t(p.out[s0 + q]) : 0u;
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) sp[k] = __ldg(p.t.short_of + sp[k]);
+            for (int k = 0; k < 4; ++k) sp[k] = __ldg(p.t.short_of + sp[k]);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 4; ++k) {
                 const uint32_t q = uint32_t(kb + k) * 32 + lane;
                 if (q < len) {
                     const uint64_t i = s0 + q;
                     uint32_t r = sp[k];
                     const uint64_t avail = i + p.hist_valid + 1;  // bytes of the stream up to and incl. c[i]
                     if (avail >= 9) {
-                        const int x = kHalo + int(q);
+                        const int x = kLead + int(q);
                         const uint32_t f8 = kr_mulmod(kr_submod(s_phi[x + 1], s_phi[x - 7]), s_rinv[x - 7]);
                         bool pass = true;
 #pragma unroll
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) 
                             }
                         }
                         if (pass) {
-                            const uint32_t hit = kr_verify(p.t, s_phi, x, f8, avail);
+                            const uint32_t hit = kr_verify(p.t, p.stream + i, f8, avail);
                             if (hit) r = hit;
                         }
                     }

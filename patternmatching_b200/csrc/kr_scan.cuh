@@ -8,7 +8,7 @@
 
 namespace pm {
 
-constexpr int kKrTile = 1024;  // positions per warp tile
+constexpr int kKrTile = 512;   // positions per warp tile
 
 struct KrDevTables {
     uint32_t r = 0;
