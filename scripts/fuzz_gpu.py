@@ -1,6 +1,6 @@
 """Differential fuzzing of the GPU kernels against the oracle: random dictionaries (alphabet size, pattern
 lengths, shared suffixes / prefixes, nested patterns) x random streams with planted occurrences x every exact
-kernel (and the randomized one against its restatement).  Usage: python scripts/fuzz_gpu.py [n_cases] [seed]"""
+kernel, and the randomized one against its restatement.  Usage: python scripts/fuzz_gpu.py [n_cases] [seed]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
@@ -75,6 +75,19 @@ def main():
                 bad += 1
                 w = np.nonzero(got != want)[0]
                 print(f"MISMATCH case {case} algo {name}: {len(pats)} patterns, n={body.size}, hist={hist}, first diff at {w[:5]} got {got[w[:5]]} want {want[w[:5]]}", flush=True)
+        # the randomized variant against the oracle's restatement of it (whole stream, no history)
+        seed = 0xF1A90000 + case
+        eng.set_kr_seed(seed)
+        d_all = torch.from_numpy(stream.copy()).to(dev)
+        d_out = torch.zeros(max(stream.size, 8), dtype=torch.int16, device=dev)
+        eng.scan_device(d_all, stream.size, d_out, hist_valid=0, algo=pm.ALGO_KR)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy().view(np.uint16)[:stream.size]
+        want_kr = (o.kr_scan(stream, seed) + 1).astype(np.uint16)
+        if not np.array_equal(got, want_kr):
+            bad += 1
+            w = np.nonzero(got != want_kr)[0]
+            print(f"MISMATCH case {case} algo kr: {len(pats)} patterns, n={stream.size}, first diff at {w[:5]} got {got[w[:5]]} want {want_kr[w[:5]]}", flush=True)
         # host path with arbitrary cuts
         eng.reset()
         cuts = sorted(set([0, stream.size] + [int(x) for x in rng.integers(0, stream.size + 1, 3)]))
