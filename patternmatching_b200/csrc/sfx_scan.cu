@@ -583,19 +583,24 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
     if (e != cudaSuccess) return e;
     const uint32_t grid = uint32_t(sfx_scan_ctas(p.n, n_sms));
     if (ev) cudaEventRecord(ev[0], st);
-    // shared memory actually needed (the rest of the 256 KB stays L1 / texture cache)
-    const size_t smem = size_t(kOffL3) + (p.l3f ? size_t(p.n_l3) * 4 : 0) + 16;
-    kern<<<grid, kThreads, smem, st>>>(p);
-    if (ev) cudaEventRecord(ev[1], st);
-    ++*launches;
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    {
+    if (p.n_tiles > 0) {
+        // shared memory actually needed (the rest of the 256 KB stays L1 / texture cache)
+        const size_t smem = size_t(kOffL3) + (p.l3f ? size_t(p.n_l3) * 4 : 0) + 16;
+        kern<<<grid, kThreads, smem, st>>>(p);
+        if (ev) cudaEventRecord(ev[1], st);
+        ++*launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
         auto deep = ident_cls ? sfx_deep_kernel<true> : sfx_deep_kernel<false>;
         deep<<<grid, 1024, 0, st>>>(p);  // CTA b drains the strip of scan CTA b
         ++*launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
+    } else {
+        // fewer than one visit (the plugin's read_char / tiny read_block calls): the edge kernel alone
+        e = cudaMemsetAsync(p.qcount, 0, 2 * sizeof(uint32_t), st);
+        if (e != cudaSuccess) return e;
+        if (ev) cudaEventRecord(ev[1], st);
     }
     // Start of a stream: visit 0 reads no bytes before the stream unless 4 bytes of history exist, and a deferred
     // walk is bounded by the bytes that exist; every position that could look back past the start of the readable
