@@ -269,16 +269,20 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
     const bool hist4 = p.hist_valid >= 4;
 
     // the visit's bytes: a = [8l, 8l+8), b = [256+8l, ..), h (lane 0) = the 4 bytes before the visit
-    auto load_visit = [&](uint64_t v, uint2& a, uint2& b, uint32_t& h) {
-        const uint8_t* base = p.stream + v * uint64_t(kTile);
-        a = ldg_stream8(base + 8 * lane);
-        b = ldg_stream8(base + 256 + 8 * lane);
+    // Both pointers are carried from visit to visit (one 64-bit add each) instead of being rebuilt from the visit index.
+    const uint8_t* in_ptr = p.stream + gw * uint64_t(kTile) + 8 * lane;   // this lane's bytes of the NEXT visit to load
+    uint16_t* out_ptr = p.out + gw * uint64_t(kTile) + 8 * lane;          // this lane's results of the current visit
+    const uint64_t step = G * uint64_t(kTile);
+    auto load_visit = [&](bool first, uint2& a, uint2& b, uint32_t& h) {
+        a = ldg_stream8(in_ptr);
+        b = ldg_stream8(in_ptr + 256);
         h = 0;
-        if (lane == 0 && (v != 0 || hist4)) h = ldg_stream4(base - 4);
+        if (lane == 0 && (!first || hist4)) h = ldg_stream4(in_ptr - 4);
+        in_ptr += step;
     };
     uint2 a = make_uint2(0, 0), b = make_uint2(0, 0);
     uint32_t h = 0;
-    if (gw < n_vis) load_visit(gw, a, b, h);
+    if (gw < n_vis) load_visit(gw == 0, a, b, h);
 
     // root2 -> shared memory (once per CTA; coalesced 16-byte loads, L2 hits after the first CTA)
     {
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
         WB[0] = __shfl_up_sync(0xFFFFFFFFu, b.y, 1);
         const uint32_t a31 = __shfl_sync(0xFFFFFFFFu, a.y, 31);
         if (lane == 0) { WA[0] = h; WB[0] = a31; }
-        if (v + G < n_vis) load_visit(v + G, a, b, h);   // next visit's bytes, in flight during this one
+        if (v + G < n_vis) load_visit(false, a, b, h);   // next visit's bytes, in flight during this one
 
         uint32_t ea[8], eb[8];
         bool sample_cont;
@@ -359,8 +363,9 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
                 }
             }
         }
-        store_group(p.out, s0 + ga, ea);
-        store_group(p.out, s0 + gb, eb);
+        store_group(out_ptr, 0, ea);
+        store_group(out_ptr, 256, eb);
+        out_ptr += step;
     }
     __syncthreads();  // every warp of the CTA has finished its visits
     if (tid == 0) { p.qcount[2 * blockIdx.x] = s_qcnt[2]; p.qcount[2 * blockIdx.x + 1] = s_qcnt[1]; }
