@@ -258,9 +258,10 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
     const bool have_l3 = p.l3f != nullptr;
     if (have_l3) for (uint32_t i = tid; i < p.n_l3; i += kThreads) s_l3[i] = __ldg(p.l3f + i);
     // Per-warp choice of the level-3 path, re-made every visit from a 32-position sample of the previous one.
-    // The plain path (predicated L2 lookups) loads the L1 data pipe, the filter path (a shared-memory Bloom word
-    // first) the ALU; on binary bytes (~10% of the positions continue below root2) the threshold sends ~40% of the
-    // visits through the filter, which balances the two pipes; on text (~60% continue) all of them.
+    // The plain path (predicated texture fetches) waits for L2, the filter path (a shared-memory Bloom word first)
+    // costs LSU wavefronts and ALU; on binary bytes (~10% of the positions continue below root2) the threshold
+    // sends ~40% of the visits through the filter, which keeps the LSU pipe busy while the other warps wait for
+    // their fetches; on text (~60% continue) all visits take it.
     bool use_l3a = false, use_l3b = false;
 
     const uint64_t gw = uint64_t(blockIdx.x) * kWarps + warp;   // global warp id
