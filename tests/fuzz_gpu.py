@@ -1,9 +1,10 @@
 """Differential fuzzing of the GPU kernels against the oracle: random dictionaries (alphabet size, pattern
 lengths, shared suffixes / prefixes, nested patterns) x random streams with planted occurrences x every exact
-kernel, and the randomized one against its restatement.  Usage: python scripts/fuzz_gpu.py [n_cases] [seed]"""
+kernel, and the randomized one against its restatement.  Test infrastructure (it drives the oracle).
+Usage: python tests/fuzz_gpu.py [n_cases] [seed]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np, torch
 import patternmatching_b200 as pm
 from oracle_lib import Oracle

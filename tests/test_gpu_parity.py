@@ -502,9 +502,9 @@ def test_every_variant_of_the_dfa_kernel_is_exact(env, oracle_merged, engine_mer
 def test_differential_fuzz_small():
     """Random dictionaries (2 .. 256 byte classes, lengths 1 .. 353, shared suffixes / prefixes, nested patterns) x
     random streams with planted occurrences and history: sfx, dfa, auto and the chunked host path against the
-    oracle (scripts/fuzz_gpu.py; 25 seeded cases here, hundreds were run during development)."""
+    oracle (tests/fuzz_gpu.py; 25 seeded cases here, hundreds were run during development)."""
     import importlib.util, sys
-    spec = importlib.util.spec_from_file_location("fuzz_gpu", os.path.join(os.path.dirname(GOLDEN), "..", "scripts", "fuzz_gpu.py"))
+    spec = importlib.util.spec_from_file_location("fuzz_gpu", os.path.join(os.path.dirname(GOLDEN), "fuzz_gpu.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     argv = sys.argv
