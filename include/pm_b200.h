@@ -52,9 +52,11 @@ int pm_dict_compile(pm_dict* d);
 
 /* Compiled-automaton cache (the reference rebuilds its structures on every run: 6-7 s PatternsTree,
  * PatternsTree.c:186-214, + 4-5 s ac_compile, mpac.c:282-291).  pm_dict_save writes a compiled dictionary to one
- * binary file, pm_dict_load reads it back (NULL + pm_last_error on a foreign / truncated file);
- * pm_dict_compile_files_cached keys the file by a hash of the dictionary files' contents and order
- * (<cache_dir>/pmdict-<hash>.bin): load when present, else ingest + compile + save. */
+ * binary file (temporary name + rename: concurrent processes never see a partial file; versioned magic, trailing
+ * checksum), pm_dict_load reads it back and verifies the checksum and every table size / index bound (NULL +
+ * pm_last_error on a foreign, stale, truncated or damaged file); pm_dict_compile_files_cached keys the file by a
+ * hash of the dictionary files' contents and order (<cache_dir>/pmdict-<hash>.bin): load when present and valid,
+ * else ingest + compile + save. */
 int pm_dict_save(const pm_dict* d, const char* path);
 pm_dict* pm_dict_load(const char* path);
 pm_dict* pm_dict_compile_files_cached(const char* const* paths, int n, const char* cache_dir);
@@ -96,19 +98,31 @@ enum {
     PM_STREAM_ASCII   = 4  /* uniform printable ASCII 0x20..0x7E (text-like traffic) */
 };
 
-/* Thread safety: a pm_dict is read-only once compiled; the pm_engine entry points are serialised per engine by an
- * internal mutex (an engine holds ONE stream state and shared scratch buffers) -- use one engine per concurrent
+/* Thread safety: a pm_dict is read-only once compiled, with one exception that is internally locked: the forward DFA
+ * tables are built on first use (PM_ALGO_DFA / PM_ALGO_AUTO), at most once, under a dictionary-level mutex.  Karp-Rabin
+ * tables are built per engine (per seed) and owned by the engine.  The pm_engine entry points are serialised per engine
+ * by an internal mutex (an engine holds ONE stream state and shared scratch buffers) -- use one engine per concurrent
  * stream; engines of the same dictionary share nothing on the device but cost only 61 MB each.
+ * Diagnostic environment switches are read once, when the engine is created.
  * Upload the compiled tables to CUDA device `device`.  NULL (and pm_last_error) when there is no
  * usable device: there is no CPU fallback. */
 pm_engine* pm_engine_create(const pm_dict* d, int device);
 void pm_engine_free(pm_engine* e);
 /* replaces: MpsElem.total_mem (Core/src/mps.h:77): bytes of all device-resident tables */
 size_t pm_engine_total_mem(const pm_engine* e);
+/* device scratch that is not a table: deferred-walk queues (at most 2 MiB per SM and pipeline slot), the host
+ * pipeline's device buffers, compaction counters.  Grows on demand, never shrinks. */
+size_t pm_engine_scratch_mem(const pm_engine* e);
+/* host threads used to stage pageable buffers and to translate pids (PM_HOST_THREADS; default = cores, at most 16) */
+int pm_engine_host_threads(const pm_engine* e);
 /* KR variant parameters: r is drawn from `seed` (the reference draws it from rand(), bgps.c:469-475) */
 int pm_engine_set_kr_seed(pm_engine* e, uint64_t seed);
 
-/* Scan n bytes that are already in device memory.
+/* Scan n bytes that are already in device memory.  Asynchronous on `cuda_stream`, with these exceptions: the call
+ * synchronises the device when it has to grow the deferred-walk queue (first call, or a larger n than ever before),
+ * when it builds / uploads the DFA or KR tables (first use), and for PM_ALGO_AUTO (it reads back a sample).  An engine
+ * owns ONE set of scan scratch: successive calls are ordered on the device by an internal event, so they may be given
+ * different streams, but they never overlap -- use one engine per concurrent scan.
  *   d_stream   : device pointer, 16-byte aligned, first byte to report on
  *   hist_valid : how many bytes directly BEFORE d_stream belong to the same stream and are readable
  *                (0 = d_stream is the start of the stream / of the allocation).  With
@@ -123,8 +137,18 @@ int pm_engine_scan_device(pm_engine* e, int algo, const uint8_t* d_stream, size_
 
 /* Scan a HOST buffer: pinned double-buffered H2D copy, scan, D2H of the dense uint16 result,
  * synchronous.  State is carried across calls exactly like consecutive read_char calls until
- * pm_engine_reset().  replaces: the chunk loop of measure_single_instance_stats (measure.c:281-304). */
+ * pm_engine_reset().  replaces: the chunk loop of measure_single_instance_stats (measure.c:281-304).
+ * Page-locked buffers (pm_host_alloc) are used in place; pageable ones are staged through the engine's pinned
+ * buffers by its host threads in 4 MiB pieces that overlap the transfers.  Calls of <= 256 KiB (the reference's
+ * 100 KiB chunks, measure.c:77; read_char) take a latency path: one H2D copy, one kernel launch writing into mapped
+ * pinned memory, one synchronise. */
 int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n, uint16_t* out);
+/* Same pipeline; out[i] = id_of_pid[pid of the longest pattern ending at i] -- 8 bytes per position, what the
+ * reference's read_char returns (pattern_id_t is a pointer, Core/src/PatternsTree.h:104; Core/src/mps.h:41-42).
+ * id_of_pid has n_ids >= P + 1 entries, entry 0 = the "no pattern" id.  The translation runs on the engine's host
+ * threads piece by piece while later pieces are still on the GPU.  This is what gpu_read_block calls. */
+int pm_engine_scan_host_ids(pm_engine* e, int algo, const uint8_t* stream, size_t n, const uint64_t* id_of_pid,
+                            size_t n_ids, uint64_t* out);
 /* Same pipeline, sparse result: only the positions whose longest match is a pattern of at least min_len bytes
  * come back, as position-sorted records (pos << 24 | pid), pos counted from the last pm_engine_reset().  The dense
  * result never crosses PCIe (2 B per stream byte down to 8 B per reported match).  At most `cap` records are

@@ -102,6 +102,9 @@ int pmref_build(int n_dicts, const char** dict_paths, int algo_mask) {
     return 0;
 }
 
+/* number of entries of the reference's mps_table (a generic MpsElem host such as pm_driver -p walks the table) */
+int mps_table_count(void) { return MPS_SIZE; }
+
 size_t pmref_n_patterns(void) { return g_npats; }
 size_t pmref_max_pat_len(void) { return g_max_pat_len; }
 size_t pmref_total_mem(int algo) { return g_have[algo] ? mps_table[algo].total_mem(g_obj[algo]) : 0; }

@@ -33,6 +33,7 @@ class Reference:
         L.pmref_success.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
         L.pmref_scan_parallel.restype = C.c_double
         L.pmref_scan_parallel.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int] + [C.POINTER(C.c_uint64)] * 3 + [C.POINTER(C.c_double)]
+        L.pmref_pattern.argtypes = [C.c_size_t] + [C.POINTER(C.c_uint32)] * 5 + [C.POINTER(C.POINTER(C.c_ubyte))]
         self.L = L
         arr = (C.c_char_p * len(dict_paths))(*[os.fsencode(p) for p in dict_paths])
         if L.pmref_build(len(dict_paths), arr, algo_mask) != 0:
@@ -40,6 +41,15 @@ class Reference:
 
     n_patterns = property(lambda s: s.L.pmref_n_patterns())
     max_pat_len = property(lambda s: s.L.pmref_max_pat_len())
+
+    def patterns(self):
+        """Unique patterns in the reference's add_pattern order (post-order of its PatternsTree, PatternsTree.c:390-401):
+        (file, line, parent_file, parent_line, bytes); parent 0xFFFFFFFF = root."""
+        f = C.c_uint32(); l = C.c_uint32(); pf = C.c_uint32(); pl = C.c_uint32(); n = C.c_uint32()
+        b = C.POINTER(C.c_ubyte)()
+        for i in range(self.n_patterns):
+            self.L.pmref_pattern(i, C.byref(f), C.byref(l), C.byref(pf), C.byref(pl), C.byref(n), C.byref(b))
+            yield f.value, l.value, pf.value, pl.value, bytes(bytearray(b[:n.value]))
 
     def total_mem(self, algo=AC):
         return self.L.pmref_total_mem(algo)

@@ -83,6 +83,9 @@ def lib():
         "pm_engine_set_kr_seed": (C.c_int, [vp, u64]),
         "pm_engine_scan_device": (C.c_int, [vp, C.c_int, vp, sz, sz, vp, vp]),
         "pm_engine_scan_host": (C.c_int, [vp, C.c_int, vp, sz, vp]),
+        "pm_engine_scan_host_ids": (C.c_int, [vp, C.c_int, vp, sz, vp, sz, vp]),
+        "pm_engine_scratch_mem": (sz, [vp]),
+        "pm_engine_host_threads": (C.c_int, [vp]),
         "pm_engine_scan_host_records": (C.c_int, [vp, C.c_int, vp, sz, u32, vp, sz, C.POINTER(u64)]),
         "pm_engine_reset": (None, [vp]),
         "pm_engine_summarize": (C.c_int, [vp, vp, sz, u64, C.POINTER(u64), vp]),
@@ -313,6 +316,24 @@ class Engine:
                     "pm_engine_scan_host_records")
         return (out[:min(cnt.value, cap)] if out is not None else None), cnt.value
 
+    def scan_host_ids(self, buf, id_of_pid, algo=ALGO_SFX, out=None):
+        """Dense result translated through a pid -> 64-bit id table (what the plugin's read_block returns)."""
+        a = _u8(buf)
+        t = np.ascontiguousarray(id_of_pid, dtype=np.uint64)
+        if out is None:
+            out = np.empty(a.size, np.uint64)
+        self._check(self.L.pm_engine_scan_host_ids(self.h, algo, a.ctypes.data if a.size else None, a.size, t.ctypes.data,
+                                                    t.size, out.ctypes.data if a.size else None), "pm_engine_scan_host_ids")
+        return out
+
+    @property
+    def scratch_mem(self):
+        return self.L.pm_engine_scratch_mem(self.h)
+
+    @property
+    def host_threads(self):
+        return self.L.pm_engine_host_threads(self.h)
+
     def scan_host_ptr(self, src_ptr, n, dst_ptr, algo=ALGO_SFX):
         self._check(self.L.pm_engine_scan_host(self.h, algo, src_ptr, n, dst_ptr), "pm_engine_scan_host")
 
@@ -403,11 +424,15 @@ class MpsGpu:
         r = self.L.gpu_read_char(self.obj, C.c_char(bytes([c & 0xFF])))
         return r or 0
 
-    def read_block(self, buf):                                      # batched extension
+    def read_block(self, buf, out=None):                            # batched extension
         a = _u8(buf)
-        out = np.zeros(a.size, np.uint64)
+        if out is None:
+            out = np.zeros(a.size, np.uint64)
         self.L.gpu_read_block(self.obj, a.ctypes.data if a.size else None, a.size, out.ctypes.data)
         return out
+
+    def read_block_ptr(self, src_ptr, n, dst_ptr):                  # same call on raw host pointers (bench)
+        self.L.gpu_read_block(self.obj, src_ptr, n, dst_ptr)
 
     def total_mem(self):                                            # MpsElem.total_mem
         return self.L.gpu_total_mem(self.obj)

@@ -6,6 +6,8 @@
 #include <cstring>
 #include <unordered_map>
 
+#include <unistd.h>
+
 namespace pm {
 
 uint64_t splitmix64(uint64_t x) {
@@ -329,13 +331,18 @@ int Dict::compile() {
             }
         }
     }
+    if (!x.fits_u16) {   // not usable by the engine: stays uncompiled
+        error = "dictionary too large for dense uint16 results (needs P + #2-byte-continuations < 65536)";
+        return -1;
+    }
     compiled = true;
     return 0;
 }
 
 // Core/src/mpac.c:147-210 (goto + failure + nearest-output link), completed to a DFA:
 // delta(s,c) = goto(s,c) if present else delta(fail(s),c); longest(s) = id[suffix_link(s)].
-void Dict::build_dfa() {
+void Dict::build_dfa() const {
+    std::lock_guard<std::mutex> lock(lazy_mu_);
     if (dfa.built) return;
     if (fwd_->size() == 1 && !pats.empty()) {  // loaded from a cache file: the forward trie is rebuilt from the patterns
         for (uint32_t i = 0; i < pats.size(); ++i) {
@@ -385,20 +392,35 @@ void Dict::build_dfa() {
 }
 
 // ---- compiled-automaton cache -----------------------------------------------------------------
+// One binary file: magic (carries the layout version), the scalar block, the table vectors, and a trailing FNV-1a
+// checksum over everything before it.  Written to a temporary name in the same directory and renamed into place, so
+// that concurrent ranks (one process per GPU) never see a half-written file; load() trusts nothing: it verifies the
+// checksum and every size / index bound the kernels rely on, and any mismatch means "compile instead".
 namespace {
-constexpr char kMagic[8] = {'P', 'M', 'B', '2', 'D', 'I', 'C', '2'};
-template <class T>
-bool put(FILE* f, const std::vector<T>& v) {
-    const uint64_t n = v.size();
-    return fwrite(&n, 8, 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n);
-}
-template <class T>
-bool get(FILE* f, std::vector<T>& v) {
-    uint64_t n = 0;
-    if (fread(&n, 8, 1, f) != 1 || n > (uint64_t(1) << 32)) return false;
-    v.resize(n);
-    return n == 0 || fread(v.data(), sizeof(T), n, f) == n;
-}
+constexpr char kMagic[8] = {'P', 'M', 'B', '2', 'D', 'I', 'C', '3'};
+struct Hasher {
+    uint64_t h = 1469598103934665603ull;
+    void mix(const void* p, size_t n) {
+        const uint8_t* b = static_cast<const uint8_t*>(p);
+        for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    }
+};
+struct Writer {
+    FILE* f; Hasher hs; bool ok = true;
+    void raw(const void* p, size_t n) { if (n && fwrite(p, 1, n, f) != n) ok = false; hs.mix(p, n); }
+    template <class T> void vec(const std::vector<T>& v) { const uint64_t n = v.size(); raw(&n, 8); raw(v.data(), n * sizeof(T)); }
+};
+struct Reader {
+    FILE* f; Hasher hs; bool ok = true;
+    void raw(void* p, size_t n) { if (n && fread(p, 1, n, f) != n) ok = false; else hs.mix(p, n); }
+    template <class T> void vec(std::vector<T>& v) {
+        uint64_t n = 0;
+        raw(&n, 8);
+        if (!ok || n > (uint64_t(1) << 32)) { ok = false; return; }
+        v.resize(n);
+        raw(v.data(), n * sizeof(T));
+    }
+};
 struct Scalars {
     uint64_t n_lines, n_rejected, n_dups;
     uint32_t n_files, max_len, n_ac_states;
@@ -409,7 +431,8 @@ struct Scalars {
 
 int Dict::save(const char* path) const {
     if (!compiled) return -1;
-    FILE* f = fopen(path, "wb");
+    const std::string tmp = std::string(path) + ".tmp." + std::to_string(uint64_t(getpid()));
+    FILE* f = fopen(tmp.c_str(), "wb");
     if (!f) return -1;
     Scalars sc{};
     sc.n_lines = n_lines; sc.n_rejected = n_rejected; sc.n_dups = n_dups;
@@ -418,10 +441,15 @@ int Dict::save(const char* path) const {
     sc.n2_cont = sfx.n2_cont; sc.cont_base = sfx.cont_base; sc.fits_u16 = sfx.fits_u16; sc.n_classes = sfx.n_classes;
     sc.log2_ncp = sfx.log2_ncp;
     memcpy(sc.cls, sfx.cls, 256);
-    bool ok = fwrite(kMagic, 8, 1, f) == 1 && fwrite(&sc, sizeof(sc), 1, f) == 1 && put(f, pats) && put(f, bytes) &&
-              put(f, anc_off) && put(f, anc_list) && put(f, sfx.root2) && put(f, sfx.l3f) && put(f, sfx.root1) &&
-              put(f, sfx.rows) && put(f, sfx.row_best) && put(f, sfx.tail_rec) && put(f, sfx.depth_hist);
+    Writer w{f};
+    w.raw(kMagic, 8); w.raw(&sc, sizeof(sc));
+    w.vec(pats); w.vec(bytes); w.vec(anc_off); w.vec(anc_list); w.vec(sfx.root2); w.vec(sfx.l3f); w.vec(sfx.root1);
+    w.vec(sfx.rows); w.vec(sfx.row_best); w.vec(sfx.tail_rec); w.vec(sfx.depth_hist);
+    const uint64_t sum = w.hs.h;
+    bool ok = w.ok && fwrite(&sum, 8, 1, f) == 1;
     ok = (fclose(f) == 0) && ok;
+    if (ok && rename(tmp.c_str(), path) != 0) ok = false;
+    if (!ok) remove(tmp.c_str());
     return ok ? 0 : -1;
 }
 
@@ -431,11 +459,48 @@ int Dict::load(const char* path) {
     if (!f) { error = std::string("cannot open ") + path; return -1; }
     char magic[8];
     Scalars sc{};
-    bool ok = fread(magic, 8, 1, f) == 1 && memcmp(magic, kMagic, 8) == 0 && fread(&sc, sizeof(sc), 1, f) == 1 &&
-              get(f, pats) && get(f, bytes) && get(f, anc_off) && get(f, anc_list) && get(f, sfx.root2) && get(f, sfx.l3f) &&
-              get(f, sfx.root1) && get(f, sfx.rows) && get(f, sfx.row_best) && get(f, sfx.tail_rec) && get(f, sfx.depth_hist);
+    Reader r{f};
+    r.raw(magic, 8); r.raw(&sc, sizeof(sc));
+    bool ok = r.ok && memcmp(magic, kMagic, 8) == 0;
+    if (ok) {
+        r.vec(pats); r.vec(bytes); r.vec(anc_off); r.vec(anc_list); r.vec(sfx.root2); r.vec(sfx.l3f); r.vec(sfx.root1);
+        r.vec(sfx.rows); r.vec(sfx.row_best); r.vec(sfx.tail_rec); r.vec(sfx.depth_hist);
+        uint64_t sum = 0;
+        ok = r.ok && fread(&sum, 8, 1, f) == 1 && sum == r.hs.h;
+    }
     fclose(f);
-    if (!ok) { error = std::string("not a compiled dictionary (or truncated): ") + path; return -1; }
+    // structural checks: every size and index the kernels use without looking
+    const uint64_t P = pats.size();
+    if (ok) {
+        ok = sc.fits_u16 == 1 && sc.log2_ncp <= 8 && sc.n_classes >= 1 && sc.n_classes <= (1u << sc.log2_ncp) &&
+             sfx.root2.size() == 65536 && sfx.root1.size() == 256 && sc.n_rows < (1u << 24) &&
+             sfx.rows.size() == (size_t(sc.n_rows) << sc.log2_ncp) && sfx.row_best.size() == sc.n_rows &&
+             sfx.tail_rec.size() == 4 * (P + 1) && sfx.l3f.size() == sc.n2_cont && anc_off.size() == P + 2 &&
+             P + 1 <= sc.cont_base && uint64_t(sc.cont_base) + sc.n2_cont <= 65536 && sc.row2_base == sc.cont_base &&
+             uint64_t(sc.cont_base) + sc.n2_cont <= sc.n_rows && sc.max_len >= (P ? 1u : 0u);
+    }
+    for (uint64_t i = 0; ok && i < P; ++i)
+        ok = pats[i].len >= 1 && pats[i].len <= sc.max_len && pats[i].off + pats[i].len <= bytes.size() && pats[i].parent <= P;
+    for (uint64_t i = 0; ok && i + 1 < anc_off.size(); ++i) ok = anc_off[i] <= anc_off[i + 1] && anc_off[i + 1] <= anc_list.size();
+    for (size_t i = 0; ok && i < anc_list.size(); ++i) ok = anc_list[i] >= 1 && anc_list[i] <= P;
+    auto entry_ok = [&](uint32_t v) {
+        if (v & kContFlag) return (v & 0xFFFFFFu) < sc.n_rows;
+        if (v & kTailFlag) return (v & 0xFFFFu) >= 1 && (v & 0xFFFFu) <= P;
+        return v <= P;
+    };
+    for (size_t i = 0; ok && i < sfx.rows.size(); ++i) ok = entry_ok(sfx.rows[i]);
+    for (size_t i = 0; ok && i < sfx.root1.size(); ++i) ok = entry_ok(sfx.root1[i]);
+    for (size_t i = 0; ok && i < sfx.row_best.size(); ++i) ok = sfx.row_best[i] <= P;
+    for (size_t i = 0; ok && i < sfx.root2.size(); ++i) ok = sfx.root2[i] <= P || (sfx.root2[i] >= sc.cont_base && sfx.root2[i] < sc.cont_base + sc.n2_cont);
+    for (uint64_t q = 1; ok && q <= P; ++q) {
+        const uint32_t* t = sfx.tail_rec.data() + 4 * q;
+        ok = uint64_t(t[0]) + t[1] <= bytes.size() && t[1] <= sc.max_len && t[3] <= P;
+    }
+    if (!ok) {
+        pats.clear(); bytes.clear(); anc_off.clear(); anc_list.clear(); sfx = SfxTables();
+        error = std::string("not a compiled dictionary of this version (or damaged): ") + path;
+        return -1;
+    }
     n_lines = sc.n_lines; n_rejected = sc.n_rejected; n_dups = sc.n_dups;
     n_files = sc.n_files; max_len = sc.max_len; n_ac_states = sc.n_ac_states;
     sfx.n_nodes = sc.n_nodes; sfx.n_rows = sc.n_rows; sfx.n_tail_nodes = sc.n_tail_nodes; sfx.row2_base = sc.row2_base;
@@ -448,9 +513,8 @@ int Dict::load(const char* path) {
     return 0;
 }
 
-void Dict::build_kr(uint64_t seed) {
-    KrTables& k = kr;
-    k = KrTables();
+KrTables Dict::build_kr(uint64_t seed) const {
+    KrTables k;
     k.seed = seed;
     k.r = 1 + splitmix64(seed) % (kKrP - 1);
     struct Cand { uint32_t fp8, pid, len; };
@@ -497,6 +561,7 @@ void Dict::build_kr(uint64_t seed) {
         k.stage_fp.push_back(uint32_t(kr_fp(b, p.len, k.r)));
     }
     k.built = true;
+    return k;
 }
 
 }  // namespace pm

@@ -13,6 +13,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -101,8 +102,13 @@ class Dict {
     int add_mem(const uint8_t* data, size_t n);
     uint32_t add_pattern(const uint8_t* pat, size_t len, uint32_t file, uint32_t line, uint64_t user);
     int compile();
-    void build_dfa();                 // lazily, the table is large (n_states * 256 * 4 bytes)
-    void build_kr(uint64_t seed);
+    // The forward DFA is built lazily (the table is large: n_states * 256 * 4 bytes), at most once and under a
+    // dictionary-level lock: engines on different threads may ask for it at the same time.  After it returns the
+    // tables are read-only like everything else in a compiled dictionary.
+    void build_dfa() const;
+    // Karp-Rabin tables for one seed: returned by value, owned by the caller (an engine) -- the dictionary itself is
+    // not touched, so engines with different seeds share it safely.
+    KrTables build_kr(uint64_t seed) const;
     bool is_pattern_suffix(uint32_t first, uint32_t second) const;
     // compiled-automaton cache: the compiled dictionary as one binary file
     int save(const char* path) const;
@@ -120,14 +126,14 @@ class Dict {
     uint32_t n_ac_states = 1;
     bool compiled = false;
     SfxTables sfx;
-    DfaTables dfa;
-    KrTables kr;
+    mutable DfaTables dfa;            // see build_dfa()
     std::string error;
 
   private:
     // forward trie (also the de-dup structure): hash of (state << 8 | byte) -> child
     struct Trie;
     Trie* fwd_;
+    mutable std::mutex lazy_mu_;      // serialises build_dfa()
   public:
     ~Dict();
     Dict(const Dict&) = delete;

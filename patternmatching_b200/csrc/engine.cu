@@ -7,15 +7,18 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pm_b200.h"
 #include "aux_kernels.cuh"
 #include "dfa_scan.cuh"
 #include "dict.hpp"
+#include "host_pool.hpp"
 #include "kr_scan.cuh"
 #include "pm_dev.cuh"
 #include "sfx_scan.cuh"
@@ -51,20 +54,41 @@ cudaError_t upload(const std::vector<T>& v, T** dptr, size_t* total) {
 }
 constexpr size_t kMaxCtas = 1024;  // upper bound of scan CTAs per launch (one per SM)
 constexpr size_t kPatPad = 16;  // zero bytes in front of the device copy of the pattern text (8-byte windows)
-const size_t kHostChunk = [] {  // bytes per pipeline slot of pm_engine_scan_host (PM_HOST_CHUNK_MIB, default 16)
-    const char* v = getenv("PM_HOST_CHUNK_MIB");
-    const long m = v ? atol(v) : 16;
-    return size_t(m >= 1 && m <= 1024 ? m : 16) << 20;
-}();
+constexpr size_t kSmallCall = size_t(256) << 10;   // host calls up to this many bytes take the single-launch path
+constexpr size_t kPageableChunk = size_t(4) << 20; // pipeline piece when a buffer has to be staged by host threads
+constexpr size_t kQueueMaxPerCta = size_t(256) << 10;  // deferred-walk slots per scan CTA (2 MiB); beyond that walks finish inline
+
+// Diagnostic / A-B switches, read ONCE when an engine is created.
+struct EngineOpts {
+    bool sfx_no_tex = false, sfx_no_l3 = false, dfa_no_fb = false, dfa_flat = false;
+    uint32_t l3_min = 4, l3_min_b = 4;
+    size_t host_chunk = size_t(16) << 20;  // bytes per pipeline slot for pinned buffers (PM_HOST_CHUNK_MIB)
+    int host_threads = 0;                  // staging threads (PM_HOST_THREADS; default: the host's cores, at most 16)
+    static EngineOpts from_env() {
+        EngineOpts o;
+        o.sfx_no_tex = getenv("PM_SFX_NO_TEX") != nullptr;
+        o.sfx_no_l3 = getenv("PM_SFX_NO_L3") != nullptr;
+        o.dfa_no_fb = getenv("PM_DFA_NO_FB") != nullptr;
+        o.dfa_flat = getenv("PM_DFA_FLAT") != nullptr;
+        if (const char* v = getenv("PM_SFX_L3_MIN")) o.l3_min = o.l3_min_b = uint32_t(atoi(v));
+        if (const char* v = getenv("PM_SFX_L3_MIN_B")) o.l3_min_b = uint32_t(atoi(v));
+        if (const char* v = getenv("PM_HOST_CHUNK_MIB")) { const long m = atol(v); if (m >= 1 && m <= 1024) o.host_chunk = size_t(m) << 20; }
+        const unsigned hw = std::thread::hardware_concurrency();
+        o.host_threads = int(std::min<unsigned>(hw ? hw : 1, 16));
+        if (const char* v = getenv("PM_HOST_THREADS")) { const int t = atoi(v); if (t >= 1 && t <= 256) o.host_threads = t; }
+        return o;
+    }
+};
 }  // namespace
 
 struct pm_engine {
     std::mutex mu;  // the entry points below are serialised per engine (one stream state, shared scratch buffers)
     const pm::Dict* dict = nullptr;
-    pm_dict* dict_owner = nullptr;
     int device = 0, n_sms = 0;
-    size_t table_bytes = 0;
+    size_t table_bytes = 0, scratch_bytes = 0;
     uint64_t launches = 0;
+    EngineOpts opts;
+    size_t halo = pm::kHalo;  // bytes of history that make a shard scan equal to the continuous one (>= max_pat_len - 1)
     // sfx tables
     uint16_t* d_root2 = nullptr;
     uint32_t *d_root1 = nullptr, *d_rows = nullptr, *d_row_best = nullptr;
@@ -80,22 +104,30 @@ struct pm_engine {
     uint16_t* d_anc_list = nullptr;
     uint64_t* d_pidhash = nullptr;
     pm::PatTables pt{};
-    // dfa tables (lazy)
+    // dfa tables (device copies made on first use; the host tables belong to the dictionary, see Dict::build_dfa)
     uint32_t* d_delta = nullptr;
     uint16_t* d_longest = nullptr;
     uint8_t* d_dfa_cls = nullptr;
     uint32_t* d_fb_meta = nullptr;
     bool dfa_ready = false;
-    // kr tables (lazy)
+    // kr tables: built for THIS engine's seed and owned by it
     pm::KrDevTables kr{};
     bool kr_ready = false;
-    uint64_t kr_seed = 0xF1A90003ull;
+    uint64_t kr_seed = 0xF1A90003ull, kr_built_seed = 0;
+    size_t kr_bytes = 0;
     // scratch
     unsigned long long* d_acc = nullptr;  // 8 x u64
+    unsigned long long* d_compact_counts = nullptr;  // per-CTA counts of pm_engine_compact, grown on demand
+    size_t compact_cap = 0;
     // deferred-walk queues of the sfx scan, one per pipeline slot (slot 0 also serves pm_engine_scan_device)
     uint64_t* d_queue[2] = {nullptr, nullptr};
-    uint32_t* d_qcount = nullptr;         // 2 counters
+    uint32_t* d_qcount = nullptr;         // 2 x 2 x kMaxCtas counters
     size_t queue_cap[2] = {0, 0};
+    size_t last_ctas[2] = {0, 0};         // scan CTAs of the last sfx launch that used the slot
+    // slot-0 scratch is shared by successive pm_engine_scan_device calls whatever stream they are given: the next
+    // call waits (on the device) for the previous one through this event
+    cudaEvent_t scratch_free = nullptr;
+    bool scratch_used = false;
     // PM_ALGO_AUTO: scratch result buffer for the sampling scans, decision cached per stream (until reset)
     uint16_t* d_sample_out = nullptr;
     int auto_choice = -1;
@@ -112,12 +144,13 @@ struct pm_engine {
     uint16_t* h_out[2] = {nullptr, nullptr};
     cudaStream_t st[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr};
+    std::unique_ptr<pm::HostPool> pool;
     // record path of the host pipeline (lazy)
     uint64_t* d_rec[2] = {nullptr, nullptr};
     unsigned long long* d_rec_counts[2] = {nullptr, nullptr};
     unsigned long long* h_rec_total[2] = {nullptr, nullptr};
-    // stream state carried between pm_engine_scan_host calls (== ac->current_state of the reference)
-    uint8_t h_hist[pm::kHalo];
+    // stream state carried between host calls (== ac->current_state of the reference): the last `halo` bytes, right-aligned
+    std::vector<uint8_t> h_hist;
     size_t hist_valid = 0;
 };
 
@@ -125,42 +158,50 @@ namespace {
 
 int ensure_dfa(pm_engine* e) {
     if (e->dfa_ready) return 0;
-    pm::Dict* d = const_cast<pm::Dict*>(e->dict);
-    d->build_dfa();
-    CU(upload(d->dfa.delta, &e->d_delta, &e->table_bytes));
-    CU(upload(d->dfa.longest, &e->d_longest, &e->table_bytes));
-    CU(upload(d->dfa.fb_meta, &e->d_fb_meta, &e->table_bytes));
-    std::vector<uint8_t> cls(d->dfa.cls, d->dfa.cls + 256);
+    const pm::Dict& d = *e->dict;
+    d.build_dfa();  // at most once per dictionary, under the dictionary's own lock
+    CU(upload(d.dfa.delta, &e->d_delta, &e->table_bytes));
+    CU(upload(d.dfa.longest, &e->d_longest, &e->table_bytes));
+    CU(upload(d.dfa.fb_meta, &e->d_fb_meta, &e->table_bytes));
+    std::vector<uint8_t> cls(d.dfa.cls, d.dfa.cls + 256);
     CU(upload(cls, &e->d_dfa_cls, &e->table_bytes));
     e->dfa_ready = true;
     return 0;
 }
 
 int ensure_kr(pm_engine* e) {
-    if (e->kr_ready && e->dict->kr.seed == e->kr_seed) return 0;
-    pm::Dict* d = const_cast<pm::Dict*>(e->dict);
-    d->build_kr(e->kr_seed);
+    if (e->kr_ready && e->kr_built_seed == e->kr_seed) return 0;
+    const pm::KrTables host = e->dict->build_kr(e->kr_seed);
     pm::kr_free_tables(&e->kr);
-    size_t bytes = 0;
-    cudaError_t ce = pm::kr_upload_tables(*d, &e->kr, &bytes);
+    e->table_bytes -= e->kr_bytes;
+    e->kr_bytes = 0; e->kr_ready = false;
+    cudaError_t ce = pm::kr_upload_tables(*e->dict, host, &e->kr, &e->kr_bytes);
+    e->table_bytes += e->kr_bytes;
     if (ce != cudaSuccess) return cuda_fail(ce, "kr_upload_tables");
-    e->table_bytes += bytes;
-    e->kr_ready = true;
+    e->kr_ready = true; e->kr_built_seed = e->kr_seed;
     return 0;
 }
 
 int ensure_pipe(pm_engine* e) {
     if (e->pipe_ready) return 0;
+    const size_t chunk = e->opts.host_chunk;
     for (int b = 0; b < 2; ++b) {
-        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_in[b]), pm::kHalo + kHostChunk + 16));
-        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_out[b]), kHostChunk * sizeof(uint16_t)));
-        CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_in[b]), pm::kHalo + kHostChunk));
-        CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_out[b]), kHostChunk * sizeof(uint16_t)));
+        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_in[b]), e->halo + chunk + 16));
+        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_out[b]), chunk * sizeof(uint16_t)));
+        CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_in[b]), e->halo + chunk));
+        CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_out[b]), chunk * sizeof(uint16_t)));
         CU(cudaStreamCreateWithFlags(&e->st[b], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&e->done[b], cudaEventDisableTiming));
+        e->scratch_bytes += e->halo + chunk + 16 + chunk * sizeof(uint16_t);
     }
+    e->pool.reset(new pm::HostPool(e->opts.host_threads));
     e->pipe_ready = true;
     return 0;
+}
+
+// both pipeline streams idle: nothing is in flight into a caller's buffer any more (called before an error return)
+void quiesce(pm_engine* e) {
+    for (int b = 0; b < 2; ++b) if (e->st[b]) cudaStreamSynchronize(e->st[b]);
 }
 
 bool is_pinned(const void* p) {
@@ -171,28 +212,31 @@ bool is_pinned(const void* p) {
 
 int fill_sfx_params(pm_engine* e, pm::SfxParams* p, size_t n, int slot) {
     const pm::Dict& d = *e->dict;
-    p->rows_tex = getenv("PM_SFX_NO_TEX") ? 0 : e->rows_tex;
+    p->rows_tex = e->opts.sfx_no_tex ? 0 : e->rows_tex;
     p->root2 = e->d_root2; p->root1 = e->d_root1; p->rows = e->d_rows; p->row_best = e->d_row_best; p->cls = e->d_cls;
     p->cont_base = d.sfx.cont_base; p->row2_base = d.sfx.row2_base; p->log2_ncp = d.sfx.log2_ncp;
-    p->l3f = getenv("PM_SFX_NO_L3") ? nullptr : e->d_l3f; p->n_l3 = uint32_t(d.sfx.l3f.size());
-    p->l3_min = getenv("PM_SFX_L3_MIN") ? uint32_t(atoi(getenv("PM_SFX_L3_MIN"))) : 4u;
-    p->l3_min_b = getenv("PM_SFX_L3_MIN_B") ? uint32_t(atoi(getenv("PM_SFX_L3_MIN_B"))) : p->l3_min;
+    p->l3f = e->opts.sfx_no_l3 ? nullptr : e->d_l3f; p->n_l3 = uint32_t(d.sfx.l3f.size());
+    p->l3_min = e->opts.l3_min; p->l3_min_b = e->opts.l3_min_b;
     p->tail_rec = reinterpret_cast<const uint4*>(e->d_tail_rec); p->pat_bytes = e->d_pat_bytes + kPatPad;
     p->pat_len = e->d_pat_len; p->parent = e->d_parent;
-    // Deferred-walk queue: one strip per scan CTA.  Random bytes defer ~1e-5 of the positions, C3 ~1.3e-3;
-    // strips are sized for 1/64 of the positions (at least 4096 slots) and a CTA that fills its strip
-    // finishes further walks inline.
+    // Deferred-walk queue: one strip per scan CTA.  Random bytes defer ~1e-5 of the positions, C3 ~1.3e-3; strips
+    // are sized for 1/64 of the positions, at least 4096 and at most kQueueMaxPerCta slots (2 MiB per CTA, 296 MiB
+    // for the 16 GiB bench scan; counted in pm_engine_scratch_mem) -- a CTA that fills its strip finishes further
+    // walks inline.  Growing the queue frees and allocates device memory, i.e. synchronises the device.
     const size_t ctas = std::max<size_t>(pm::sfx_scan_ctas(n, e->n_sms), 1);
-    const size_t per_cta = std::max<size_t>(4096, n / 64 / ctas);
+    const size_t per_cta = std::min(kQueueMaxPerCta, std::max<size_t>(4096, n / 64 / ctas));
     const size_t want = ctas * per_cta;
     if (want > e->queue_cap[slot]) {
         if (e->d_queue[slot]) CU(cudaFree(e->d_queue[slot]));
+        e->scratch_bytes -= e->queue_cap[slot] * sizeof(uint64_t);
         e->d_queue[slot] = nullptr; e->queue_cap[slot] = 0;
         CU(cudaMalloc(reinterpret_cast<void**>(&e->d_queue[slot]), want * sizeof(uint64_t)));
         e->queue_cap[slot] = want;
+        e->scratch_bytes += want * sizeof(uint64_t);
     }
     p->queue = e->d_queue[slot]; p->qcount = e->d_qcount + size_t(slot) * 2 * kMaxCtas;
     p->q_per_cta = uint32_t(std::min<size_t>(e->queue_cap[slot] / ctas, 1u << 30));
+    e->last_ctas[slot] = ctas;
     return 0;
 }
 
@@ -206,12 +250,15 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
 constexpr size_t kSampleWin = size_t(256) << 10;
 int choose_algo(pm_engine* e, const uint8_t* d_stream, size_t n, size_t hist_valid, cudaStream_t st, int slot) {
     if (n < 4 * kSampleWin) { e->auto_flat = false; return PM_ALGO_SFX; }
-    if (!e->d_sample_out) CU(cudaMalloc(reinterpret_cast<void**>(&e->d_sample_out), kSampleWin * sizeof(uint16_t)));
+    if (!e->d_sample_out) {
+        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_sample_out), kSampleWin * sizeof(uint16_t)));
+        e->scratch_bytes += kSampleWin * sizeof(uint16_t);
+    }
     uint64_t deferred = 0;
     std::vector<uint32_t> counts(2 * kMaxCtas);
     for (int w = 0; w < 4; ++w) {
         const size_t off = (n / 4 * size_t(w)) & ~size_t(4095);
-        if (scan_device_impl(e, PM_ALGO_SFX, d_stream + off, kSampleWin, std::min<size_t>(off + hist_valid, pm::kHalo),
+        if (scan_device_impl(e, PM_ALGO_SFX, d_stream + off, kSampleWin, std::min<size_t>(off + hist_valid, e->halo),
                              e->d_sample_out, st, slot)) return -1;
         const size_t ctas = pm::sfx_scan_ctas(kSampleWin, e->n_sms);
         CU(cudaMemcpyAsync(counts.data(), e->d_qcount + size_t(slot) * 2 * kMaxCtas, 2 * ctas * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -273,15 +320,17 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
         pm::dfa_plan_hot(d.dfa.n_states, d.dfa.log2_ncp, d.dfa.depth_count.data(), uint32_t(d.dfa.depth_count.size()),
                          &p.hot_rows, &p.hot_long, &p.fb_count);
         p.fb_meta = e->d_fb_meta;
-        if (getenv("PM_DFA_NO_FB")) p.fb_count = 0;
-        cudaError_t ce = pm::dfa_scan_launch(p, d.sfx.cls_identity, force_flat || getenv("PM_DFA_FLAT") != nullptr, e->n_sms, st, &e->launches);
+        if (e->opts.dfa_no_fb) p.fb_count = 0;
+        cudaError_t ce = pm::dfa_scan_launch(p, d.sfx.cls_identity, force_flat || e->opts.dfa_flat, e->n_sms, st, &e->launches);
         if (ce != cudaSuccess) return cuda_fail(ce, "dfa_scan_launch");
         return 0;
     }
     if (algo == PM_ALGO_KR) {
         if (ensure_kr(e)) return -1;
-        // exact part (patterns <= 8 bytes, bgps.c:459-464) comes from the exact scan restricted by length,
-        // the fingerprint part from the KR kernel; see kr_scan.cu
+        // The patterns of <= 8 bytes are matched exactly (bgps.c:459-464 does the same with its KMP): that part is the
+        // exact scan, whose answer kr_scan_kernel reads only through short_of[] (the longest pattern of <= 8 bytes on
+        // its PatternsTree chain); the patterns of > 8 bytes come from the fingerprints alone.  The exact scan's time is
+        // part of every KR number reported.
         pm::SfxParams p{};
         p.stream = d_stream; p.n = n; p.hist_valid = hist_valid; p.out = d_out;
         if (fill_sfx_params(e, &p, n, slot)) return -1;
@@ -294,12 +343,112 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
     return fail("unknown algorithm id");
 }
 
+// ---- host-buffer pipeline -------------------------------------------------------------------------------------
+
+// what a host scan hands back for every position
+struct HostSink {
+    uint16_t* out16 = nullptr;          // dense pids, or
+    uint64_t* out64 = nullptr;          // table[pid] (the plugin's pattern_id_t), 8 bytes per position
+    const uint64_t* table = nullptr;
+};
+
+// remember the last `halo` bytes fed (right-aligned in h_hist): the stream state between calls
+void carry_history(pm_engine* e, const uint8_t* stream, size_t n) {
+    const size_t H = e->halo;
+    if (n >= H) {
+        memcpy(e->h_hist.data(), stream + n - H, H);
+    } else if (n) {
+        memmove(e->h_hist.data(), e->h_hist.data() + n, H - n);
+        memcpy(e->h_hist.data() + H - n, stream, n);
+    }
+    e->hist_valid += n;
+}
+
+// Small calls: stage [history | bytes] in pinned memory, ONE H2D copy, ONE kernel that writes its results straight
+// into mapped pinned memory, one stream synchronise.  Taken for PM_ALGO_SFX / PM_ALGO_AUTO (the walker is the backward
+// scan's own bounded walk); an explicitly requested DFA or KR scan runs its own kernels whatever the size.
+int scan_host_small(pm_engine* e, const uint8_t* stream, size_t n, const HostSink& sink) {
+    const size_t H = e->halo;
+    const size_t hv = std::min(e->hist_valid, H);
+    uint8_t* h = e->h_in[0];
+    memcpy(h + H - hv, e->h_hist.data() + H - hv, hv);
+    memcpy(h + H, stream, n);
+    CU(cudaMemcpyAsync(e->d_in[0] + H - hv, h + H - hv, hv + n, cudaMemcpyHostToDevice, e->st[0]));
+    pm::SfxParams p{};
+    p.stream = e->d_in[0] + H; p.n = n; p.hist_valid = hv; p.out = e->h_out[0];  // pinned host memory is device-addressable (UVA)
+    if (fill_sfx_params(e, &p, n, 0)) return -1;
+    cudaError_t ce = pm::sfx_walk_launch(p, e->st[0], &e->launches);
+    if (ce != cudaSuccess) return cuda_fail(ce, "sfx_walk_launch");
+    CU(cudaStreamSynchronize(e->st[0]));
+    if (sink.out16) memcpy(sink.out16, e->h_out[0], n * sizeof(uint16_t));
+    else pm::HostPool::expand_range(e->h_out[0], 0, n, sink.table, sink.out64);
+    return 0;
+}
+
+int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, const HostSink& sink) {
+    CU(cudaSetDevice(e->device));
+    if (n == 0) return 0;
+    if (ensure_pipe(e)) return -1;
+    if (algo == PM_ALGO_DFA && ensure_dfa(e)) return -1;
+    if (algo == PM_ALGO_KR && ensure_kr(e)) return -1;
+    if (n <= kSmallCall && (algo == PM_ALGO_SFX || algo == PM_ALGO_AUTO)) {
+        if (scan_host_small(e, stream, n, sink)) { quiesce(e); return -1; }
+        carry_history(e, stream, n);
+        return 0;
+    }
+    if (algo == PM_ALGO_AUTO && e->auto_choice < 0 && n < 4 * kSampleWin) algo = PM_ALGO_SFX;  // too short to sample
+    const size_t H = e->halo;
+    const bool in_pinned = is_pinned(stream);
+    const bool direct_out = sink.out16 && is_pinned(sink.out16);   // the D2H copy lands in the caller's buffer
+    // Pageable buffers are staged through the pinned ones by the pool's threads, in smaller pieces so that staging
+    // piece k+1 and unloading piece k-1 overlap the transfers and the scan of piece k.
+    const size_t chunk = (in_pinned && direct_out) ? e->opts.host_chunk : std::min(e->opts.host_chunk, kPageableChunk);
+    const size_t n_chunks = (n + chunk - 1) / chunk;
+    pm::HostPool& pool = *e->pool;
+    auto finish = [&](size_t k) -> int {  // chunk k has fully left the device: hand its results to the caller
+        const int b = int(k & 1);
+        CU(cudaEventSynchronize(e->done[b]));
+        const size_t o = k * chunk, len = std::min(chunk, n - o);
+        if (sink.out64) pool.expand(e->h_out[b], len, sink.table, sink.out64 + o);
+        else if (!direct_out) pool.copy(sink.out16 + o, e->h_out[b], len * sizeof(uint16_t));
+        return 0;
+    };
+    auto submit = [&](size_t k) -> int {
+        const int b = int(k & 1);
+        const size_t o = k * chunk, len = std::min(chunk, n - o);
+        // history in front of the chunk: from this call's own bytes when there are enough, else the carried tail
+        const size_t from_call = std::min(o, H);
+        const size_t hist_total = std::min(e->hist_valid + o, H);
+        uint8_t* din = e->d_in[b];
+        if (from_call < H)
+            CU(cudaMemcpyAsync(din, e->h_hist.data() + from_call, H - from_call, cudaMemcpyHostToDevice, e->st[b]));
+        const uint8_t* src = stream + o - from_call;
+        if (!in_pinned) {
+            pool.copy(e->h_in[b], src, from_call + len);
+            src = e->h_in[b];
+        }
+        CU(cudaMemcpyAsync(din + H - from_call, src, from_call + len, cudaMemcpyHostToDevice, e->st[b]));
+        if (scan_device_impl(e, algo, din + H, len, hist_total, e->d_out[b], e->st[b], b)) return -1;
+        CU(cudaMemcpyAsync(direct_out ? sink.out16 + o : e->h_out[b], e->d_out[b], len * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->st[b]));
+        CU(cudaEventRecord(e->done[b], e->st[b]));
+        return 0;
+    };
+    for (size_t k = 0; k < n_chunks; ++k) {
+        if (k >= 2 && finish(k - 2)) { quiesce(e); return -1; }
+        if (submit(k)) { quiesce(e); return -1; }
+    }
+    for (size_t k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; ++k)
+        if (finish(k)) { quiesce(e); return -1; }
+    carry_history(e, stream, n);
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
 
 const char* pm_last_error(void) { return g_err.c_str(); }
-int pm_version(void) { return 1; }
+int pm_version(void) { return 2; }
 
 pm_dict* pm_dict_create(void) { return new (std::nothrow) pm_dict(); }
 void pm_dict_free(pm_dict* d) { delete d; }
@@ -320,8 +469,7 @@ uint32_t pm_dict_add_pattern(pm_dict* d, const uint8_t* pat, size_t len, uint32_
 }
 int pm_dict_compile(pm_dict* d) {
     if (d->d.max_len > pm::kMaxPatLen) return fail("pattern longer than the supported maximum (353 bytes)");
-    if (d->d.compile()) return fail(d->d.error);
-    if (!d->d.sfx.fits_u16) return fail("dictionary too large for dense uint16 results (needs P + #2-byte-continuations < 65536)");
+    if (d->d.compile()) return fail(d->d.error);   // leaves `compiled` false when the dictionary is not usable
     return 0;
 }
 int pm_dict_save(const pm_dict* d, const char* path) {
@@ -357,11 +505,11 @@ pm_dict* pm_dict_compile_files_cached(const char* const* paths, int n, const cha
     char name[64];
     snprintf(name, sizeof(name), "/pmdict-%016llx.bin", (unsigned long long)key);
     const std::string file = std::string(cache_dir ? cache_dir : ".") + name;
-    if (pm_dict* d = pm_dict_load(file.c_str())) return d;
+    if (pm_dict* d = pm_dict_load(file.c_str())) return d;   // a missing, foreign, stale or damaged file just means "compile"
     pm_dict* d = pm_dict_create();
     for (int i = 0; i < n; ++i) if (pm_dict_add_file(d, paths[i])) { pm_dict_free(d); return nullptr; }
     if (pm_dict_compile(d)) { pm_dict_free(d); return nullptr; }
-    d->d.save(file.c_str());  // best effort: an unwritable cache directory only costs the next compile
+    d->d.save(file.c_str());  // best effort (written to a temporary name, then renamed): an unwritable cache directory only costs the next compile
     g_err.clear();
     return d;
 }
@@ -412,8 +560,11 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
     if (!e) return nullptr;
     e->dict = &dd->d;
     e->device = device;
+    e->opts = EngineOpts::from_env();
     cudaDeviceGetAttribute(&e->n_sms, cudaDevAttrMultiProcessorCount, device);
     const pm::Dict& d = dd->d;
+    e->halo = std::max<size_t>(pm::kHalo, (size_t(d.max_len ? d.max_len - 1 : 0) + 15) / 16 * 16);
+    e->h_hist.assign(e->halo, 0);
     auto up = [&](auto& vec, auto** ptr) -> bool {
         cudaError_t r = upload(vec, ptr, &e->table_bytes);
         if (r != cudaSuccess) { cuda_fail(r, "table upload"); return false; }
@@ -445,25 +596,28 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
     }
     if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_acc), 8 * sizeof(unsigned long long)) != cudaSuccess) ok = false;
     if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_qcount), 4 * kMaxCtas * sizeof(uint32_t)) != cudaSuccess) ok = false;
-    if (!ok) { pm_engine_free(e); return nullptr; }
+    if (ok && cudaEventCreateWithFlags(&e->scratch_free, cudaEventDisableTiming) != cudaSuccess) ok = false;
+    if (!ok) { if (g_err.empty()) cuda_fail(cudaGetLastError(), "pm_engine_create"); pm_engine_free(e); return nullptr; }
     e->pt.n_patterns = uint32_t(P);
     e->pt.off = e->d_pat_off; e->pt.len = e->d_pat_len; e->pt.bytes = e->d_pat_bytes + kPatPad;
     e->pt.parent = e->d_parent; e->pt.chain = e->d_chain; e->pt.pidhash = e->d_pidhash;
     e->pt.anc_off = e->d_anc_off; e->pt.anc_list = e->d_anc_list;
-    memset(e->h_hist, 0, sizeof(e->h_hist));
     return e;
 }
 
 void pm_engine_free(pm_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    e->pool.reset();
     if (e->rows_tex) cudaDestroyTextureObject(e->rows_tex);
     void* ptrs[] = {e->d_root2, e->d_root1, e->d_rows, e->d_row_best, e->d_cls, e->d_pat_off, e->d_pat_len, e->d_pat_bytes,
                     e->d_parent, e->d_chain, e->d_pidhash, e->d_tail_rec, e->d_l3f, e->d_anc_off, e->d_anc_list, e->d_sample_out, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_fb_meta, e->d_acc,
-                    e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1], e->d_queue[0], e->d_queue[1], e->d_qcount};
+                    e->d_compact_counts, e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1], e->d_queue[0], e->d_queue[1], e->d_qcount};
     for (void* p : ptrs) if (p) cudaFree(p);
     pm::kr_free_tables(&e->kr);
     for (cudaEvent_t x : e->prof_events) cudaEventDestroy(x);
+    if (e->scratch_free) cudaEventDestroy(e->scratch_free);
     for (int b = 0; b < 2; ++b) {
         if (e->d_rec[b]) cudaFree(e->d_rec[b]);
         if (e->d_rec_counts[b]) cudaFree(e->d_rec_counts[b]);
@@ -477,22 +631,28 @@ void pm_engine_free(pm_engine* e) {
 }
 
 size_t pm_engine_total_mem(const pm_engine* e) { return e ? e->table_bytes : 0; }
+size_t pm_engine_scratch_mem(const pm_engine* e) { return e ? e->scratch_bytes : 0; }
+int pm_engine_host_threads(const pm_engine* e) { return e ? e->opts.host_threads : 0; }
 uint64_t pm_engine_launch_count(const pm_engine* e) { return e ? e->launches : 0; }
 int pm_engine_auto_choice(const pm_engine* e) { return e->auto_choice < 0 ? -1 : (e->auto_choice == PM_ALGO_DFA && e->auto_flat ? 4 : e->auto_choice); }
 uint64_t pm_engine_last_deferred(pm_engine* e) {
-    std::vector<uint32_t> c(2 * kMaxCtas);
+    std::lock_guard<std::mutex> lock(e->mu);
+    const size_t ctas = std::min(e->last_ctas[0], kMaxCtas);   // only the CTAs of the last launch wrote their counters
+    std::vector<uint32_t> c(2 * ctas + 1);
     cudaSetDevice(e->device);
-    if (cudaMemcpy(c.data(), e->d_qcount, 2 * kMaxCtas * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    if (ctas == 0 || cudaMemcpy(c.data(), e->d_qcount, 2 * ctas * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     uint64_t sum = 0;
-    for (size_t i = 0; i < 2 * size_t(e->n_sms) && i < 2 * kMaxCtas; ++i) sum += c[i];
+    for (size_t i = 0; i < 2 * ctas; ++i) sum += c[i];
     return sum;
 }
 int pm_engine_set_profiling(pm_engine* e, int on) {
+    std::lock_guard<std::mutex> lock(e->mu);
     e->profiling = on != 0;
     e->prof_used = 0;
     return 0;
 }
 int pm_engine_read_profile(pm_engine* e, uint32_t* n_scans, float* main_kernel_ms, float* total_ms) {
+    std::lock_guard<std::mutex> lock(e->mu);
     CU(cudaSetDevice(e->device));
     CU(cudaDeviceSynchronize());
     float a = 0, b = 0;
@@ -508,6 +668,7 @@ int pm_engine_read_profile(pm_engine* e, uint32_t* n_scans, float* main_kernel_m
     return 0;
 }
 int pm_engine_set_kr_seed(pm_engine* e, uint64_t seed) {
+    std::lock_guard<std::mutex> lock(e->mu);
     e->kr_seed = seed;
     return 0;
 }
@@ -516,72 +677,38 @@ int pm_engine_scan_device(pm_engine* e, int algo, const uint8_t* d_stream, size_
                           uint16_t* d_out, void* cuda_stream) {
     std::lock_guard<std::mutex> lock(e->mu);
     CU(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     if (algo == PM_ALGO_AUTO) e->auto_choice = -1;  // device scans are independent calls: decide per call
-    return scan_device_impl(e, algo, d_stream, n, hist_valid, d_out, static_cast<cudaStream_t>(cuda_stream));
+    // successive scans share the deferred-walk queue and its counters: order them on the device even when the
+    // caller alternates streams (no host synchronisation; a no-op when the stream is the same)
+    if (e->scratch_used) CU(cudaStreamWaitEvent(st, e->scratch_free, 0));
+    const int rc = scan_device_impl(e, algo, d_stream, n, hist_valid, d_out, st);
+    CU(cudaEventRecord(e->scratch_free, st));
+    e->scratch_used = true;
+    return rc;
 }
 
 void pm_engine_reset(pm_engine* e) {
     std::lock_guard<std::mutex> lock(e->mu);
     e->auto_choice = -1;  // a new stream: PM_ALGO_AUTO samples again
     e->hist_valid = 0;
-    memset(e->h_hist, 0, sizeof(e->h_hist));
+    std::fill(e->h_hist.begin(), e->h_hist.end(), uint8_t(0));
 }
 
 int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n, uint16_t* out) {
     std::lock_guard<std::mutex> lock(e->mu);
-    CU(cudaSetDevice(e->device));
-    if (ensure_pipe(e)) return -1;
-    if (algo == PM_ALGO_DFA && ensure_dfa(e)) return -1;
-    if (algo == PM_ALGO_KR && ensure_kr(e)) return -1;
-    if (algo == PM_ALGO_AUTO && e->auto_choice < 0 && n < 4 * kSampleWin) algo = PM_ALGO_SFX;  // too short to sample
-    const bool in_pinned = is_pinned(stream), out_pinned = is_pinned(out);
-    // pageable buffers go through the pinned staging buffers with memcpy on this thread: smaller pieces, so that the
-    // copies of one piece overlap the transfers and the scan of its neighbours
-    const size_t chunk = (in_pinned && out_pinned) ? kHostChunk : std::min<size_t>(kHostChunk, size_t(2) << 20);
-    const size_t n_chunks = (n + chunk - 1) / chunk;
-    auto drain = [&](size_t k) -> int {  // chunk k has fully left the device
-        const int b = int(k & 1);
-        CU(cudaEventSynchronize(e->done[b]));
-        if (!out_pinned) {
-            const size_t o = k * chunk, len = std::min(chunk, n - o);
-            memcpy(out + o, e->h_out[b], len * sizeof(uint16_t));
-        }
-        return 0;
-    };
-    for (size_t k = 0; k < n_chunks; ++k) {
-        const int b = int(k & 1);
-        if (k >= 2 && drain(k - 2)) return -1;
-        const size_t o = k * chunk, len = std::min(chunk, n - o);
-        // history in front of the chunk: from this call's own bytes when there are enough, else carried
-        const size_t from_call = std::min<size_t>(o, pm::kHalo);
-        const size_t hist_total = std::min<size_t>(e->hist_valid + o, pm::kHalo);  // valid history bytes
-        uint8_t* din = e->d_in[b];
-        if (from_call < size_t(pm::kHalo)) {
-            // [carried tail][bytes of this call before o]: carried part sits at the front of the halo
-            const size_t carried = pm::kHalo - from_call;
-            CU(cudaMemcpyAsync(din, e->h_hist + from_call, carried, cudaMemcpyHostToDevice, e->st[b]));
-        }
-        if (in_pinned) {
-            CU(cudaMemcpyAsync(din + pm::kHalo - from_call, stream + o - from_call, from_call + len, cudaMemcpyHostToDevice, e->st[b]));
-        } else {
-            memcpy(e->h_in[b], stream + o - from_call, from_call + len);
-            CU(cudaMemcpyAsync(din + pm::kHalo - from_call, e->h_in[b], from_call + len, cudaMemcpyHostToDevice, e->st[b]));
-        }
-        if (scan_device_impl(e, algo, din + pm::kHalo, len, hist_total, e->d_out[b], e->st[b], b)) return -1;
-        CU(cudaMemcpyAsync(out_pinned ? out + o : e->h_out[b], e->d_out[b], len * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->st[b]));
-        CU(cudaEventRecord(e->done[b], e->st[b]));
-    }
-    for (size_t k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; ++k)
-        if (drain(k)) return -1;
-    // carry the last kHalo bytes: h_hist always holds the most recent bytes right-aligned
-    if (n >= size_t(pm::kHalo)) {
-        memcpy(e->h_hist, stream + n - pm::kHalo, pm::kHalo);
-    } else if (n) {
-        memmove(e->h_hist, e->h_hist + n, pm::kHalo - n);
-        memcpy(e->h_hist + pm::kHalo - n, stream, n);
-    }
-    e->hist_valid += n;
-    return 0;
+    HostSink sink;
+    sink.out16 = out;
+    return scan_host_impl(e, algo, stream, n, sink);
+}
+
+int pm_engine_scan_host_ids(pm_engine* e, int algo, const uint8_t* stream, size_t n, const uint64_t* id_of_pid,
+                            size_t n_ids, uint64_t* out) {
+    std::lock_guard<std::mutex> lock(e->mu);
+    if (n_ids < e->dict->pats.size() + 1) return fail("pm_engine_scan_host_ids: id_of_pid needs P + 1 entries (entry 0 = no pattern)");
+    HostSink sink;
+    sink.out64 = out; sink.table = id_of_pid;
+    return scan_host_impl(e, algo, stream, n, sink);
 }
 
 int pm_engine_scan_host_records(pm_engine* e, int algo, const uint8_t* stream, size_t n, uint32_t min_len,
@@ -592,18 +719,17 @@ int pm_engine_scan_host_records(pm_engine* e, int algo, const uint8_t* stream, s
     if (algo == PM_ALGO_DFA && ensure_dfa(e)) return -1;
     if (algo == PM_ALGO_KR && ensure_kr(e)) return -1;
     if (algo == PM_ALGO_AUTO && e->auto_choice < 0 && n < 4 * kSampleWin) algo = PM_ALGO_SFX;
-    const size_t blocks = pm::compact_blocks(kHostChunk) + 1;
-    if (!e->d_rec[0]) {
-        for (int b = 0; b < 2; ++b) {
-            CU(cudaMalloc(reinterpret_cast<void**>(&e->d_rec[b]), kHostChunk * sizeof(uint64_t)));
-            CU(cudaMalloc(reinterpret_cast<void**>(&e->d_rec_counts[b]), (blocks + 1) * sizeof(unsigned long long)));
-            CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_rec_total[b]), sizeof(unsigned long long)));
-        }
+    const size_t chunk = e->opts.host_chunk, H = e->halo;
+    const size_t blocks = pm::compact_blocks(chunk) + 1;
+    for (int b = 0; b < 2; ++b) {   // each piece is checked on its own: a failed allocation leaves the others usable next time
+        if (!e->d_rec[b]) CU(cudaMalloc(reinterpret_cast<void**>(&e->d_rec[b]), chunk * sizeof(uint64_t)));
+        if (!e->d_rec_counts[b]) CU(cudaMalloc(reinterpret_cast<void**>(&e->d_rec_counts[b]), (blocks + 1) * sizeof(unsigned long long)));
+        if (!e->h_rec_total[b]) CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_rec_total[b]), sizeof(unsigned long long)));
     }
     const bool in_pinned = is_pinned(stream);
-    const size_t n_chunks = (n + kHostChunk - 1) / kHostChunk;
+    const size_t n_chunks = (n + chunk - 1) / chunk;
     uint64_t produced = 0;
-    auto drain = [&](size_t k) -> int {  // chunk k: fetch its record count, then exactly that many records
+    auto finish = [&](size_t k) -> int {  // chunk k: fetch its record count, then exactly that many records
         const int b = int(k & 1);
         CU(cudaEventSynchronize(e->done[b]));
         const uint64_t cnt = *e->h_rec_total[b];
@@ -614,38 +740,36 @@ int pm_engine_scan_host_records(pm_engine* e, int algo, const uint8_t* stream, s
         produced += cnt;
         return 0;
     };
-    for (size_t k = 0; k < n_chunks; ++k) {
+    auto submit = [&](size_t k) -> int {
         const int b = int(k & 1);
-        if (k >= 2 && drain(k - 2)) return -1;
-        const size_t o = k * kHostChunk, len = std::min(kHostChunk, n - o);
-        const size_t from_call = std::min<size_t>(o, pm::kHalo);
-        const size_t hist_total = std::min<size_t>(e->hist_valid + o, pm::kHalo);
+        const size_t o = k * chunk, len = std::min(chunk, n - o);
+        const size_t from_call = std::min(o, H);
+        const size_t hist_total = std::min(e->hist_valid + o, H);
         uint8_t* din = e->d_in[b];
-        if (from_call < size_t(pm::kHalo))
-            CU(cudaMemcpyAsync(din, e->h_hist + from_call, pm::kHalo - from_call, cudaMemcpyHostToDevice, e->st[b]));
-        if (in_pinned) {
-            CU(cudaMemcpyAsync(din + pm::kHalo - from_call, stream + o - from_call, from_call + len, cudaMemcpyHostToDevice, e->st[b]));
-        } else {
-            memcpy(e->h_in[b], stream + o - from_call, from_call + len);
-            CU(cudaMemcpyAsync(din + pm::kHalo - from_call, e->h_in[b], from_call + len, cudaMemcpyHostToDevice, e->st[b]));
+        if (from_call < H)
+            CU(cudaMemcpyAsync(din, e->h_hist.data() + from_call, H - from_call, cudaMemcpyHostToDevice, e->st[b]));
+        const uint8_t* src = stream + o - from_call;
+        if (!in_pinned) {
+            e->pool->copy(e->h_in[b], src, from_call + len);
+            src = e->h_in[b];
         }
-        if (scan_device_impl(e, algo, din + pm::kHalo, len, hist_total, e->d_out[b], e->st[b], b)) return -1;
+        CU(cudaMemcpyAsync(din + H - from_call, src, from_call + len, cudaMemcpyHostToDevice, e->st[b]));
+        if (scan_device_impl(e, algo, din + H, len, hist_total, e->d_out[b], e->st[b], b)) return -1;
         cudaError_t ce = pm::compact_launch(e->d_out[b], len, e->hist_valid + o, false, min_len, e->pt, e->d_rec_counts[b],
                                             e->d_rec_counts[b] + blocks, reinterpret_cast<unsigned long long*>(e->d_rec[b]),
-                                            kHostChunk, e->st[b], &e->launches);
+                                            chunk, e->st[b], &e->launches);
         if (ce != cudaSuccess) return cuda_fail(ce, "compact_launch");
         CU(cudaMemcpyAsync(e->h_rec_total[b], e->d_rec_counts[b] + blocks, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->st[b]));
         CU(cudaEventRecord(e->done[b], e->st[b]));
+        return 0;
+    };
+    for (size_t k = 0; k < n_chunks; ++k) {
+        if (k >= 2 && finish(k - 2)) { quiesce(e); return -1; }
+        if (submit(k)) { quiesce(e); return -1; }
     }
     for (size_t k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; ++k)
-        if (drain(k)) return -1;
-    if (n >= size_t(pm::kHalo)) {
-        memcpy(e->h_hist, stream + n - pm::kHalo, pm::kHalo);
-    } else if (n) {
-        memmove(e->h_hist, e->h_hist + n, pm::kHalo - n);
-        memcpy(e->h_hist + pm::kHalo - n, stream, n);
-    }
-    e->hist_valid += n;
+        if (finish(k)) { quiesce(e); return -1; }
+    carry_history(e, stream, n);
     *n_records = produced;
     return 0;
 }
@@ -668,14 +792,20 @@ int pm_engine_compact(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t po
     std::lock_guard<std::mutex> lock(e->mu);
     CU(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    unsigned long long* d_counts = nullptr;
-    CU(cudaMalloc(reinterpret_cast<void**>(&d_counts), (pm::compact_blocks(n) + 1) * sizeof(unsigned long long)));
-    cudaError_t ce = pm::compact_launch(d_out, n, pos_base, expand_ancestors != 0, 1, e->pt, d_counts, e->d_acc + 4,
+    const size_t need = pm::compact_blocks(n) + 1;
+    if (need > e->compact_cap) {   // pooled: grows to the largest n seen and stays
+        if (e->d_compact_counts) CU(cudaFree(e->d_compact_counts));
+        e->scratch_bytes -= e->compact_cap * sizeof(unsigned long long);
+        e->d_compact_counts = nullptr; e->compact_cap = 0;
+        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_compact_counts), need * sizeof(unsigned long long)));
+        e->compact_cap = need;
+        e->scratch_bytes += need * sizeof(unsigned long long);
+    }
+    cudaError_t ce = pm::compact_launch(d_out, n, pos_base, expand_ancestors != 0, 1, e->pt, e->d_compact_counts, e->d_acc + 4,
                                         reinterpret_cast<unsigned long long*>(d_records), cap, st, &e->launches);
     unsigned long long total = 0;
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(&total, e->d_acc + 4, sizeof(total), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-    cudaFree(d_counts);
     if (ce != cudaSuccess) return cuda_fail(ce, "compact");
     *n_records = total;
     return 0;
@@ -695,18 +825,25 @@ int pm_engine_time_scan(pm_engine* e, int algo, const uint8_t* d_stream, size_t 
     std::lock_guard<std::mutex> lock(e->mu);
     CU(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    cudaEvent_t a, b;
-    CU(cudaEventCreate(&a));
-    CU(cudaEventCreate(&b));
-    CU(cudaEventRecord(a, st));
-    for (int i = 0; i < iters; ++i)
-        if (scan_device_impl(e, algo, d_stream, n, hist_valid, d_out, st)) return -1;
-    CU(cudaEventRecord(b, st));
-    CU(cudaEventSynchronize(b));
+    cudaEvent_t a = nullptr, b = nullptr;
+    int rc = -1;
     float ms = 0;
-    CU(cudaEventElapsedTime(&ms, a, b));
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
+    cudaError_t ce = cudaEventCreate(&a);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&b);
+    if (ce == cudaSuccess) ce = cudaEventRecord(a, st);
+    if (ce == cudaSuccess) {
+        rc = 0;
+        for (int i = 0; i < iters && rc == 0; ++i) rc = scan_device_impl(e, algo, d_stream, n, hist_valid, d_out, st);
+        if (rc == 0) {
+            ce = cudaEventRecord(b, st);
+            if (ce == cudaSuccess) ce = cudaEventSynchronize(b);
+            if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, a, b);
+        }
+    }
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    if (ce != cudaSuccess) return cuda_fail(ce, "pm_engine_time_scan");
+    if (rc) return rc;
     *ms_per_scan = ms / float(iters > 0 ? iters : 1);
     return 0;
 }

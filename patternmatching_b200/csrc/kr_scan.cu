@@ -199,8 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) 
 
 }  // namespace
 
-cudaError_t kr_upload_tables(const Dict& d, KrDevTables* t, size_t* bytes) {
-    const KrTables& k = d.kr;
+cudaError_t kr_upload_tables(const Dict& d, const KrTables& k, KrDevTables* t, size_t* bytes) {
     *t = KrDevTables();
     t->r = uint32_t(k.r);
     t->bucket_mask = (1u << k.bucket_bits) - 1;

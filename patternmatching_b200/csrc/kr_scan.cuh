@@ -21,7 +21,7 @@ struct KrDevTables {
     uint16_t* short_of = nullptr;  // pid -> longest ancestor-or-self of <= 8 bytes (0 = none)
 };
 
-cudaError_t kr_upload_tables(const Dict& d, KrDevTables* t, size_t* bytes);
+cudaError_t kr_upload_tables(const Dict& d, const KrTables& k, KrDevTables* t, size_t* bytes);
 void kr_free_tables(KrDevTables* t);
 // d_out holds the exact dense result on entry (used ONLY through short_of[], i.e. for the patterns
 // of <= 8 bytes that the variant matches exactly) and the variant's result on exit.

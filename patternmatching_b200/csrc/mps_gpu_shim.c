@@ -19,10 +19,8 @@ typedef struct {
     pm_engine* eng;
     int algo;
     uint32_t seq;        /* add order: stands in for (file,line), which the plugin API does not pass */
-    void** id_of_pid;    /* pid -> pattern_id_t given to add_pattern */
+    uint64_t* id_of_pid; /* pid -> pattern_id_t given to add_pattern (entry 0 = NULL = null_pattern_id) */
     uint32_t n_pids;
-    uint16_t* tmp;
-    size_t tmp_cap;
 } GpuMps;
 
 static void die(const char* what) {
@@ -58,24 +56,17 @@ void gpu_compile(void* obj) {
     pm_dict_info info;
     pm_dict_get_info(g->dict, &info);
     g->n_pids = info.n_patterns;
-    g->id_of_pid = (void**)calloc((size_t)g->n_pids + 1, sizeof(void*));
-    for (uint32_t pid = 1; pid <= g->n_pids; ++pid) {
-        uint64_t user = 0;
-        pm_dict_pattern(g->dict, pid, NULL, NULL, &user, NULL, NULL, NULL);
-        g->id_of_pid[pid] = (void*)(uintptr_t)user;
-    }
+    g->id_of_pid = (uint64_t*)calloc((size_t)g->n_pids + 1, sizeof(uint64_t));
+    if (!g->id_of_pid) { perror("failed to allocate memory"); exit(EXIT_FAILURE); }
+    for (uint32_t pid = 1; pid <= g->n_pids; ++pid) pm_dict_pattern(g->dict, pid, NULL, NULL, &g->id_of_pid[pid], NULL, NULL, NULL);
 }
 
 size_t gpu_read_block(void* obj, const char* buf, size_t n, void** out) {
     GpuMps* g = (GpuMps*)obj;
-    if (n > g->tmp_cap) {
-        free(g->tmp);
-        g->tmp_cap = n < 4096 ? 4096 : n;
-        g->tmp = (uint16_t*)malloc(g->tmp_cap * sizeof(uint16_t));
-        if (!g->tmp) { perror("failed to allocate memory"); exit(EXIT_FAILURE); }
-    }
-    if (pm_engine_scan_host(g->eng, g->algo, (const uint8_t*)buf, n, g->tmp)) die("pm_engine_scan_host");
-    for (size_t j = 0; j < n; ++j) out[j] = g->id_of_pid[g->tmp[j]]; /* pid 0 -> NULL == null_pattern_id */
+    /* pattern_id_t is a pointer (Core/src/PatternsTree.h:104): 8 bytes per position.  The engine translates pids to
+     * the ids recorded in add_pattern on its staging threads, piece by piece while later pieces are still on the GPU. */
+    if (pm_engine_scan_host_ids(g->eng, g->algo, (const uint8_t*)buf, n, g->id_of_pid, (size_t)g->n_pids + 1, (uint64_t*)out))
+        die("pm_engine_scan_host_ids");
     return n;
 }
 
@@ -101,7 +92,6 @@ void gpu_free(void* obj) {
     pm_engine_free(g->eng);
     pm_dict_free(g->dict);
     free(g->id_of_pid);
-    free(g->tmp);
     free(g);
 }
 

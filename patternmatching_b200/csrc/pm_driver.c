@@ -1,21 +1,33 @@
 /*
- * pm_driver.c -- measurement driver with the reference's command line and CSV schema, running the
- * GPU matchers through the C-ABI (include/pm_b200.h).
+ * pm_driver.c -- measurement driver with the reference's command line and CSV schema.  It hosts matchers through
+ * the reference's own plugin surface, MpsElem (Core/src/mps.h:71-80): the three B200 matchers of libpm_b200.so
+ * (registered with mps_gpu*_register_into, driven through gpu_create / gpu_add_pattern / gpu_compile / gpu_reset /
+ * gpu_read_block) and, with -p, every entry of another library's mps_table[] -- e.g. the reference's CPU
+ * algorithms compiled unchanged -- driven with one read_char call per byte exactly like Core/src/measure.c:292-294.
  *
- *   pm_driver -d FILE [-d FILE ...] -s FILE [-s FILE ...] -o FILE [-v]
+ *   pm_driver -d FILE [-d FILE ...] -s FILE [-s FILE ...] -o FILE [-v] [-p LIB.so] [-b BYTES] [-r gpu|plugin]
+ *
+ *   -p LIB.so   shared library that exports the reference's registry: `void mps_table_setup(void)`, `MpsElem mps_table[]`
+ *               and `int mps_table_count(void)`; each entry becomes a CSV row beside the GPU rows
+ *   -b BYTES    stream chunk per read (the reference: 100 KiB, measure.c:77; default here 16 MiB)
+ *   -r WHICH    the "reliable" instance every row is classified against (mps.c:52-53): `plugin` = a second instance of
+ *               the plugin's first entry (the reference's AC; default when -p is given), `gpu` = the B200 forward DFA
  *
  * What it mirrors (yehonatan145/PatternMatching): the flags of parse_arguments (Core/src/parser.c:104-162,
- * Core/src/util.c:6-13), the flow of main (Core/src/main.c:7-24): build the structures from the merged
- * dictionaries, run every algorithm over every stream with `reset` per stream file, time only the matching
- * (measure.c:290-297), classify every position against a separate "reliable" exact instance
- * (measure.c:174-190, 300-303) and write one CSV row per algorithm with the reference's first six columns
- * (measure.c:352-364, 366-396).  The perf_event columns are replaced by throughput columns.
- * Reference bugs not reproduced: the pointer arrays are sized in pointers, the output file is
- * created with a mode and truncated.
+ * Core/src/util.c:6-13); the flow of main (Core/src/main.c:7-24): build every instance from the merged dictionaries
+ * (init_mps, mps.c:109-113 -- add_pattern once per UNIQUE pattern, then compile), run every instance over every stream
+ * with `reset` per stream file (measure.c:274-275), time only the matching (measure.c:290-297), classify every position
+ * against the reliable instance (measure.c:174-190, 300-303) and write one CSV row per instance with the reference's
+ * first six columns (measure.c:352-396).  The perf_event columns are replaced by throughput columns; time is wall
+ * clock, not clock().  File reads, matching and classification of consecutive chunks overlap (three threads, a ring of
+ * chunk slots).  Reference bugs not reproduced: pointer arrays sized in pointers, output file created with a
+ * mode and truncated.
  */
 #define _GNU_SOURCE
+#include <dlfcn.h>
 #include <errno.h>
 #include <fcntl.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -35,6 +47,9 @@ static void usage(void) {
     fprintf(stderr, "  -s FILE               use FILE as one of the stream files (can be used many times).\n");
     fprintf(stderr, "  -o FILE               set FILE to be the output file.\n");
     fprintf(stderr, "  -v                    set verbose to true (print more information)\n");
+    fprintf(stderr, "  -p LIB.so             also measure every algorithm of LIB.so's mps_table (MpsElem plugins)\n");
+    fprintf(stderr, "  -b BYTES              stream bytes per chunk (default 16777216)\n");
+    fprintf(stderr, "  -r gpu|plugin         which instance is the reliable one\n");
 }
 static void fatal(const char* what) {
     fprintf(stderr, "%s: %s\n", what, pm_last_error());
@@ -46,32 +61,166 @@ static double now_s(void) {
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-typedef struct { const char* name; int algo; } Algo;
-static const Algo ALGOS[] = {
-    {"B200 suffix-trie scan", PM_ALGO_SFX},
-    {"B200 Aho-Corasick DFA", PM_ALGO_DFA},
-    {"B200 Karp-Rabin stages", PM_ALGO_KR},
-};
-enum { N_ALGOS = 3, RELIABLE = PM_ALGO_DFA };
-#define CHUNK ((size_t)64 << 20)
+/* one row of the run: an MpsElem, its instance, and the batched entry when it has one */
+typedef size_t (*read_block_fn)(void*, const char*, size_t, void**);
+typedef struct {
+    pm_mps_elem elem;
+    read_block_fn read_block; /* NULL: loop read_char (measure.c:292-294) */
+    void* obj;
+} Row;
+
+static void feed(const Row* r, const char* buf, size_t n, void** out) {
+    if (r->read_block) { r->read_block(r->obj, buf, n, out); return; }
+    void* (*read_char)(void*, char) = r->elem.read_char;
+    void* obj = r->obj;
+    for (size_t j = 0; j < n; ++j) out[j] = read_char(obj, buf[j]);
+}
+
+/* ---- chunk pipeline: reader -> matcher -> classifier -------------------------------------------------- */
+enum { N_SLOTS = 3 };
+typedef struct {
+    char* buf;
+    void** res;
+    void** real;
+    size_t len;
+    int first_of_file; /* reset both instances before this chunk */
+    int last;          /* no more chunks for this row */
+} Slot;
+typedef struct {
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    int ready[N_SLOTS + 1], head, tail;
+} Chan;
+static void chan_init(Chan* c) { pthread_mutex_init(&c->mu, NULL); pthread_cond_init(&c->cv, NULL); c->head = c->tail = 0; }
+static void chan_put(Chan* c, int v) {
+    pthread_mutex_lock(&c->mu);
+    c->ready[c->tail] = v; c->tail = (c->tail + 1) % (N_SLOTS + 1);
+    pthread_cond_signal(&c->cv);
+    pthread_mutex_unlock(&c->mu);
+}
+static int chan_get(Chan* c) {
+    pthread_mutex_lock(&c->mu);
+    while (c->head == c->tail) pthread_cond_wait(&c->cv, &c->mu);
+    const int v = c->ready[c->head]; c->head = (c->head + 1) % (N_SLOTS + 1);
+    pthread_mutex_unlock(&c->mu);
+    return v;
+}
+
+typedef struct {
+    Slot slot[N_SLOTS];
+    Chan free_q, read_q, scan_q;
+    size_t chunk;
+    char** streams; int n_stream;
+    const Row* row; const Row* reliable;
+    const uint32_t* parent; uint32_t n_pats;
+    double secs; uint64_t bytes; uint64_t cnt[4];
+} Run;
+
+static void* reader_main(void* arg) {
+    Run* R = (Run*)arg;
+    for (int s = 0; s < R->n_stream; ++s) {
+        int fd = open(R->streams[s], O_RDONLY);
+        if (fd == -1) {
+            fprintf(stderr, "can't open stream file %s: %s\n", R->streams[s], strerror(errno));
+            exit(EXIT_FAILURE);
+        }
+        int first = 1;
+        for (;;) {
+            const int k = chan_get(&R->free_q);
+            Slot* sl = &R->slot[k];
+            size_t got = 0;
+            while (got < R->chunk) {
+                ssize_t r = read(fd, sl->buf + got, R->chunk - got);
+                if (r < 0) { fprintf(stderr, "can't read from stream file %s: %s\n", R->streams[s], strerror(errno)); exit(EXIT_FAILURE); }
+                if (r == 0) break;
+                got += (size_t)r;
+            }
+            sl->len = got; sl->first_of_file = first; sl->last = 0;
+            first = 0;
+            chan_put(&R->read_q, k);
+            if (got < R->chunk) break;
+        }
+        close(fd);
+    }
+    const int k = chan_get(&R->free_q);
+    R->slot[k].len = 0; R->slot[k].first_of_file = 0; R->slot[k].last = 1;
+    chan_put(&R->read_q, k);
+    return NULL;
+}
+
+static void* classify_main(void* arg) {
+    Run* R = (Run*)arg;
+    for (;;) {
+        const int k = chan_get(&R->scan_q);
+        Slot* sl = &R->slot[k];
+        const int last = sl->last;
+        for (size_t j = 0; j < sl->len; ++j) { /* measure.c:174-190; ids are pids carried as pointers */
+            const uintptr_t x = (uintptr_t)sl->res[j], y = (uintptr_t)sl->real[j];
+            if (x == y) { R->cnt[0]++; continue; }
+            uintptr_t c = y;
+            while (c && c != x) c = c <= R->n_pats ? R->parent[c] : 0;
+            if (x && c == x) R->cnt[1]++;   /* algo is an ancestor of real: partial success */
+            else if (!x) R->cnt[2]++;       /* false negative */
+            else R->cnt[3]++;               /* false positive */
+        }
+        chan_put(&R->free_q, k);
+        if (last) return NULL;
+    }
+}
+
+static void run_row(Run* R) {
+    chan_init(&R->free_q); chan_init(&R->read_q); chan_init(&R->scan_q);
+    for (int k = 0; k < N_SLOTS; ++k) chan_put(&R->free_q, k);
+    R->secs = 0; R->bytes = 0; memset(R->cnt, 0, sizeof(R->cnt));
+    pthread_t rd, cl;
+    pthread_create(&rd, NULL, reader_main, R);
+    pthread_create(&cl, NULL, classify_main, R);
+    for (;;) {
+        const int k = chan_get(&R->read_q);
+        Slot* sl = &R->slot[k];
+        if (sl->first_of_file) { /* measure.c:274-275: reset both before every stream file */
+            R->reliable->elem.reset(R->reliable->obj);
+            R->row->elem.reset(R->row->obj);
+        }
+        if (sl->len) {
+            const double b = now_s();
+            feed(R->row, sl->buf, sl->len, sl->res);           /* the timed region, measure.c:290-297 */
+            R->secs += now_s() - b;
+            feed(R->reliable, sl->buf, sl->len, sl->real);     /* measure.c:300-302 */
+            R->bytes += sl->len;
+        }
+        const int last = sl->last;
+        chan_put(&R->scan_q, k);
+        if (last) break;
+    }
+    pthread_join(rd, NULL);
+    pthread_join(cl, NULL);
+}
 
 int main(int argc, char* argv[]) {
     program_name = argv[0];
     int opt, n_dict = 0, n_stream = 0, n_out = 0;
+    const char* plugin_path = NULL;
+    const char* reliable_kind = NULL;
+    size_t chunk = (size_t)16 << 20;
     opterr = 0;
-    while ((opt = getopt(argc, argv, "d:s:o:v")) != -1) {
+    while ((opt = getopt(argc, argv, "d:s:o:vp:b:r:")) != -1) {
         if (opt == 'd') ++n_dict;
         else if (opt == 's') ++n_stream;
         else if (opt == 'o') ++n_out;
         else if (opt == 'v') verbose = 1;
+        else if (opt == 'p') plugin_path = optarg;
+        else if (opt == 'b') chunk = (size_t)strtoull(optarg, NULL, 10);
+        else if (opt == 'r') reliable_kind = optarg;
         else {
-            if (optopt == 'd' || optopt == 's' || optopt == 'o') fprintf(stderr, "Option -%c must have argument.\n\n", optopt);
+            if (optopt == 'd' || optopt == 's' || optopt == 'o' || optopt == 'p' || optopt == 'b' || optopt == 'r')
+                fprintf(stderr, "Option -%c must have argument.\n\n", optopt);
             else fprintf(stderr, "Unknown option -%c.\n\n", optopt);
             usage();
             return EXIT_FAILURE;
         }
     }
-    if (n_out != 1 || n_dict == 0 || n_stream == 0) {
+    if (n_out != 1 || n_dict == 0 || n_stream == 0 || chunk == 0) {
         if (n_out > 1) fprintf(stderr, "Error: have more than one output file\n\n");
         usage();
         return EXIT_FAILURE;
@@ -81,13 +230,42 @@ int main(int argc, char* argv[]) {
     char* out_name = NULL;
     int di = 0, si = 0;
     optind = 1;
-    while ((opt = getopt(argc, argv, "d:s:o:v")) != -1) {
+    while ((opt = getopt(argc, argv, "d:s:o:vp:b:r:")) != -1) {
         if (opt == 'd') dicts[di++] = optarg;
         else if (opt == 's') streams[si++] = optarg;
         else if (opt == 'o') out_name = optarg;
     }
 
-    /* init_mps (mps.c:109-113): ingest the merged dictionaries, compile, upload */
+    /* ---- the rows: plugin entries first (the reference's order: its own algorithms), then the GPU matchers ---- */
+    enum { MAX_ROWS = 16 };
+    Row rows[MAX_ROWS];
+    int n_rows = 0, n_plugin = 0;
+    memset(rows, 0, sizeof(rows));
+    if (plugin_path) {
+        void* h = dlopen(plugin_path, RTLD_NOW | RTLD_LOCAL);
+        if (!h) { fprintf(stderr, "can't load plugin %s: %s\n", plugin_path, dlerror()); return EXIT_FAILURE; }
+        void (*setup)(void) = (void (*)(void))dlsym(h, "mps_table_setup");
+        pm_mps_elem* table = (pm_mps_elem*)dlsym(h, "mps_table");
+        int (*count)(void) = (int (*)(void))dlsym(h, "mps_table_count");
+        if (!setup || !table || !count) {
+            fprintf(stderr, "plugin %s must export mps_table_setup, mps_table and mps_table_count\n", plugin_path);
+            return EXIT_FAILURE;
+        }
+        setup();
+        n_plugin = count();
+        for (int i = 0; i < n_plugin && n_rows < MAX_ROWS - 4; ++i) rows[n_rows++].elem = table[i];
+    }
+    mps_gpu_register_into(&rows[n_rows].elem);     rows[n_rows++].read_block = gpu_read_block;
+    mps_gpu_dfa_register_into(&rows[n_rows].elem); rows[n_rows++].read_block = gpu_read_block;
+    mps_gpu_kr_register_into(&rows[n_rows].elem);  rows[n_rows++].read_block = gpu_read_block;
+    Row reliable;
+    memset(&reliable, 0, sizeof(reliable));
+    const int reliable_plugin = reliable_kind ? strcmp(reliable_kind, "plugin") == 0 : n_plugin > 0;
+    if (reliable_plugin && !n_plugin) { fprintf(stderr, "-r plugin needs -p\n\n"); usage(); return EXIT_FAILURE; }
+    if (reliable_plugin) reliable.elem = rows[0].elem;  /* mps.c:52-53: a separate instance of MPS_AC */
+    else { mps_gpu_dfa_register_into(&reliable.elem); reliable.read_block = gpu_read_block; }
+
+    /* ---- init_mps (mps.c:109-113): one create per instance, add_pattern per UNIQUE pattern, compile ---- */
     double t0 = now_s();
     pm_dict* dict = pm_dict_create();
     for (int i = 0; i < n_dict; ++i)
@@ -95,73 +273,48 @@ int main(int argc, char* argv[]) {
             fprintf(stderr, "failed to open dictionary file %s: %s", dicts[i], pm_last_error());
             return EXIT_FAILURE;
         }
-    if (pm_dict_compile(dict)) fatal("pm_dict_compile");
-    const char* dev = getenv("PM_B200_DEVICE");
-    pm_engine* eng = pm_engine_create(dict, dev ? atoi(dev) : 0);
-    if (!eng) fatal("pm_engine_create");
+    if (pm_dict_compile(dict)) fatal("pm_dict_compile");  /* de-dup, (file,line) ids, PatternsTree parents */
     pm_dict_info info;
     pm_dict_get_info(dict, &info);
     if (verbose)
-        printf("dictionaries: %u unique patterns (%llu lines, %llu rejected, %llu duplicates), %u AC states, built in %.2f s\n",
+        printf("dictionaries: %u unique patterns (%llu lines, %llu rejected, %llu duplicates), %u AC states, ingested in %.2f s\n",
                info.n_patterns, (unsigned long long)info.n_lines, (unsigned long long)info.n_rejected,
                (unsigned long long)info.n_duplicates, info.n_ac_states, now_s() - t0);
     uint32_t* parent = (uint32_t*)calloc((size_t)info.n_patterns + 1, sizeof(uint32_t));
     for (uint32_t pid = 1; pid <= info.n_patterns; ++pid) pm_dict_pattern(dict, pid, NULL, NULL, NULL, &parent[pid], NULL, NULL);
-
-    uint8_t* buf = (uint8_t*)pm_host_alloc(CHUNK);
-    uint16_t* res = (uint16_t*)pm_host_alloc(CHUNK * 2);
-    uint16_t* real = (uint16_t*)pm_host_alloc(CHUNK * 2);
-    if (!buf || !res || !real) fatal("pm_host_alloc");
-
-    double secs[N_ALGOS] = {0};
-    uint64_t cnt[N_ALGOS][4];
-    uint64_t bytes_total[N_ALGOS] = {0};
-    size_t mem[N_ALGOS] = {0};
-    memset(cnt, 0, sizeof(cnt));
-    /* reliable pass results are recomputed per chunk: keep a second engine state?  The engine carries ONE
-     * stream state, so each algorithm is run over the whole stream file with the reliable results streamed
-     * from a second engine (== the separate "reliable" instance of mps.c:52-53). */
-    pm_engine* reliable = pm_engine_create(dict, dev ? atoi(dev) : 0);
-    if (!reliable) fatal("pm_engine_create");
-
-    for (int a = 0; a < N_ALGOS; ++a) {
-        if (verbose) { printf("Measuring algorithm %s...", ALGOS[a].name); fflush(stdout); }
-        for (int s = 0; s < n_stream; ++s) {
-            int fd = open(streams[s], O_RDONLY);
-            if (fd == -1) {
-                fprintf(stderr, "can't open stream file %s: %s\n", streams[s], strerror(errno));
-                return EXIT_FAILURE;
-            }
-            pm_engine_reset(eng);        /* measure.c:274-275: reset both before every stream file */
-            pm_engine_reset(reliable);
-            for (;;) {
-                size_t got = 0;
-                while (got < CHUNK) {
-                    ssize_t r = read(fd, buf + got, CHUNK - got);
-                    if (r < 0) { fprintf(stderr, "can't read from stream file %s: %s\n", streams[s], strerror(errno)); return EXIT_FAILURE; }
-                    if (r == 0) break;
-                    got += (size_t)r;
-                }
-                if (!got) break;
-                double b = now_s();
-                if (pm_engine_scan_host(eng, ALGOS[a].algo, buf, got, res)) fatal("pm_engine_scan_host");
-                secs[a] += now_s() - b;
-                if (pm_engine_scan_host(reliable, RELIABLE, buf, got, real)) fatal("pm_engine_scan_host");
-                for (size_t j = 0; j < got; ++j) {          /* measure.c:174-190 */
-                    const uint32_t x = res[j], y = real[j];
-                    if (x == y) { cnt[a][0]++; continue; }
-                    uint32_t c = y;
-                    while (c && c != x) c = parent[c];
-                    if (x && c == x) cnt[a][1]++;             /* algo is an ancestor of real: partial */
-                    else if (!x) cnt[a][2]++;                 /* false negative */
-                    else cnt[a][3]++;                         /* false positive */
-                }
-                bytes_total[a] += got;
-                if (got < CHUNK) break;
-            }
-            close(fd);
+    char* scratch = (char*)malloc((size_t)info.max_pat_len + 1);
+    for (int r = 0; r <= n_rows; ++r) {
+        Row* row = r < n_rows ? &rows[r] : &reliable;
+        t0 = now_s();
+        row->obj = row->elem.create();
+        for (uint32_t pid = 1; pid <= info.n_patterns; ++pid) {
+            uint32_t len = 0; const uint8_t* bytes = NULL;
+            pm_dict_pattern(dict, pid, NULL, NULL, NULL, NULL, &len, &bytes);
+            memcpy(scratch, bytes, len);                      /* the callee must copy: the buffer is scratch */
+            row->elem.add_pattern(row->obj, scratch, len, (void*)(uintptr_t)pid);
         }
-        mem[a] = pm_engine_total_mem(eng);
+        row->elem.compile(row->obj);
+        if (verbose) printf("built %s%s in %.2f s\n", row->elem.name, r == n_rows ? " (reliable instance)" : "", now_s() - t0);
+    }
+    free(scratch);
+
+    /* ---- measure_instances_stats (measure.c:324-333) ---- */
+    Run R;
+    memset(&R, 0, sizeof(R));
+    R.chunk = chunk; R.streams = streams; R.n_stream = n_stream; R.reliable = &reliable; R.parent = parent; R.n_pats = info.n_patterns;
+    for (int k = 0; k < N_SLOTS; ++k) {
+        R.slot[k].buf = (char*)pm_host_alloc(chunk);
+        R.slot[k].res = (void**)pm_host_alloc(chunk * sizeof(void*));
+        R.slot[k].real = (void**)pm_host_alloc(chunk * sizeof(void*));
+        if (!R.slot[k].buf || !R.slot[k].res || !R.slot[k].real) fatal("pm_host_alloc");
+    }
+    double secs[MAX_ROWS]; uint64_t cnt[MAX_ROWS][4], bytes_total[MAX_ROWS]; size_t mem[MAX_ROWS];
+    for (int a = 0; a < n_rows; ++a) {
+        if (verbose) { printf("Measuring algorithm %s...", rows[a].elem.name); fflush(stdout); }
+        R.row = &rows[a];
+        run_row(&R);
+        secs[a] = R.secs; bytes_total[a] = R.bytes; memcpy(cnt[a], R.cnt, sizeof(R.cnt));
+        mem[a] = rows[a].elem.total_mem(rows[a].obj);    /* measure.c:310 */
         if (verbose) printf("Done\n");
     }
 
@@ -172,15 +325,17 @@ int main(int argc, char* argv[]) {
         return EXIT_FAILURE;
     }
     fprintf(f, "Algorithm,Time (in secs),Total Memory Used,False Positive Rate,False Negative Rate,Partial Success Rate,Stream Bytes,GB/s (host buffers)");
-    for (int a = 0; a < N_ALGOS; ++a) {
+    for (int a = 0; a < n_rows; ++a) {
         const long double sum = (long double)(cnt[a][0] + cnt[a][1] + cnt[a][2] + cnt[a][3]);
-        fprintf(f, "\n%s,%.6f,%zu,%.6Lf,%.6Lf,%.6Lf,%llu,%.3f", ALGOS[a].name, secs[a], mem[a],
+        fprintf(f, "\n%s,%.6f,%zu,%.6Lf,%.6Lf,%.6Lf,%llu,%.3f", rows[a].elem.name, secs[a], mem[a],
                 sum ? cnt[a][3] / sum : 0.0L, sum ? cnt[a][2] / sum : 0.0L, sum ? cnt[a][1] / sum : 0.0L,
                 (unsigned long long)bytes_total[a], secs[a] > 0 ? bytes_total[a] / secs[a] / 1e9 : 0.0);
     }
     fclose(f);
-    pm_host_free(buf); pm_host_free(res); pm_host_free(real);
-    pm_engine_free(eng); pm_engine_free(reliable); pm_dict_free(dict);
+    for (int k = 0; k < N_SLOTS; ++k) { pm_host_free(R.slot[k].buf); pm_host_free(R.slot[k].res); pm_host_free(R.slot[k].real); }
+    for (int a = n_plugin; a < n_rows; ++a) rows[a].elem.free(rows[a].obj);  /* the reference never frees its own (and ac_free is not re-entrant) */
+    if (!reliable_plugin) reliable.elem.free(reliable.obj);
+    pm_dict_free(dict);
     free(parent); free(dicts); free(streams);
     return 0;
 }

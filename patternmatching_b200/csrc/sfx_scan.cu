@@ -627,4 +627,14 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
     return e;
 }
 
+// Small calls (the plugin's read_char and the reference's 100 KiB chunks, measure.c:77): ONE launch of the bounded
+// walker over every position instead of scan + deep + edge -- at these sizes the call is launch-latency bound.
+cudaError_t sfx_walk_launch(const SfxParams& p, cudaStream_t st, uint64_t* launches) {
+    if (p.n == 0) return cudaSuccess;
+    if (p.n > (uint64_t(1) << 30)) return cudaErrorInvalidValue;
+    sfx_edge_kernel<<<uint32_t((p.n + 127) / 128), 128, 0, st>>>(p, uint32_t(p.n), 0);
+    ++*launches;
+    return cudaGetLastError();
+}
+
 }  // namespace pm

@@ -44,4 +44,7 @@ constexpr uint32_t kSfxMaxL3 = 16384;  // filter words that fit beside root2 in 
 cudaError_t sfx_scan_launch(const SfxParams& p, bool ident_cls, int n_sms, uint32_t max_pat_len, cudaStream_t st,
                             uint64_t* launches, cudaEvent_t* ev = nullptr);
 
+// every position by the bounded walker straight from global memory: one launch, for small calls
+cudaError_t sfx_walk_launch(const SfxParams& p, cudaStream_t st, uint64_t* launches);
+
 }  // namespace pm

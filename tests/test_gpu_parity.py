@@ -421,12 +421,13 @@ SFX_VARIANTS = [
 
 
 @pytest.mark.parametrize("env", SFX_VARIANTS, ids=lambda e: "+".join(f"{k[7:]}={v}" for k, v in e.items()) or "default")
-def test_every_variant_of_the_scan_kernel_is_exact(env, oracle_merged, engine_merged, monkeypatch):
+def test_every_variant_of_the_scan_kernel_is_exact(env, oracle_merged, dict_merged, monkeypatch):
     """The scan kernel has two level-3 paths (texture fetch / shared-memory filter), chosen per warp, and a
     plain-load fallback: each combination, forced through the environment, equals the oracle -- on the merged
     dictionary (256 byte classes) and on a dictionary with few byte classes (the class-mapped code paths)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
+    engine_merged = pm.Engine(dict_merged)     # the switches are read once, when an engine is created
     n = 300_000 + 77     # ~586 visits + a ragged end
     for kind in ("planted", "ascii", "almost"):
         stream = oracle_merged.gen(kind, 12345, n)
@@ -490,10 +491,11 @@ def test_kr_variant_on_the_16gib_stream(engine_merged, dict_merged):
     assert fp <= n * 1e-7
 
 @pytest.mark.parametrize("env", [{}, {"PM_DFA_NO_FB": "1"}, {"PM_DFA_FLAT": "1"}], ids=["hot+fallback-words", "hot", "flat"])
-def test_every_variant_of_the_dfa_kernel_is_exact(env, oracle_merged, engine_merged, monkeypatch):
+def test_every_variant_of_the_dfa_kernel_is_exact(env, oracle_merged, dict_merged, monkeypatch):
     """Forward-DFA walker: hot rows + Bloom/failure words of the next level (default), hot rows only, flat."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
+    engine_merged = pm.Engine(dict_merged)     # the switches are read once, when an engine is created
     n = 200_000 + 13
     for kind in ("planted", "ascii", "almost"):
         stream = oracle_merged.gen(kind, 777, n)
