@@ -78,6 +78,10 @@ int pm_dict_get_info(const pm_dict* d, pm_dict_info* info);
  * i.e. PatternsTreeNode.parent (Core/src/PatternsTree.h:90-94). */
 int pm_dict_pattern(const pm_dict* d, uint32_t pid, uint32_t* file, uint32_t* line, uint64_t* user_id,
                     uint32_t* parent_pid, uint32_t* len, const uint8_t** bytes);
+/* Read-only view of one compiled table, for inspection and for the tests' host-side emulation of the kernels' table
+ * walks: "sfx.root2", "sfx.rows", "deep.recs", "deep.hot_rows", "deep.hot_longest", "deep.dense_rows" (layouts in
+ * patternmatching_b200/csrc/dict.hpp).  The pointer stays valid until pm_dict_free. */
+int pm_dict_table(const pm_dict* d, const char* name, const void** data, size_t* bytes);
 /* replaces: is_pattern_suffix (Core/src/PatternsTree.c:485-494) on pids */
 int pm_dict_is_pattern_suffix(const pm_dict* d, uint32_t first_pid, uint32_t second_pid);
 
@@ -140,8 +144,8 @@ int pm_engine_scan_device(pm_engine* e, int algo, const uint8_t* d_stream, size_
  * pm_engine_reset().  replaces: the chunk loop of measure_single_instance_stats (measure.c:281-304).
  * Page-locked buffers (pm_host_alloc) are used in place; pageable ones are staged through the engine's pinned
  * buffers by its host threads in 4 MiB pieces that overlap the transfers.  Calls of <= 256 KiB (the reference's
- * 100 KiB chunks, measure.c:77; read_char) take a latency path: one H2D copy, one kernel launch writing into mapped
- * pinned memory, one synchronise. */
+ * 100 KiB chunks, measure.c:77; read_char) take a latency path: one H2D copy, one kernel launch, one D2H copy, one
+ * synchronise. */
 int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n, uint16_t* out);
 /* Same pipeline; out[i] = id_of_pid[pid of the longest pattern ending at i] -- 8 bytes per position, what the
  * reference's read_char returns (pattern_id_t is a pointer, Core/src/PatternsTree.h:104; Core/src/mps.h:41-42).

@@ -76,6 +76,7 @@ def lib():
         "pm_dict_compile_files_cached": (vp, [C.POINTER(C.c_char_p), C.c_int, C.c_char_p]),
         "pm_dict_pattern": (C.c_int, [vp, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64), C.POINTER(u32),
                                       C.POINTER(u32), C.POINTER(C.POINTER(C.c_ubyte))]),
+        "pm_dict_table": (C.c_int, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(sz)]),
         "pm_dict_is_pattern_suffix": (C.c_int, [vp, u32, u32]),
         "pm_engine_create": (vp, [vp, C.c_int]),
         "pm_engine_free": (None, [vp]),
@@ -237,6 +238,17 @@ class Dictionary:
             files[pid] = f.value
             lines[pid] = l.value
         return files, lines
+
+    def table(self, name, dtype):
+        """Read-only numpy view of a compiled table (see pm_dict_table in include/pm_b200.h)."""
+        ptr = C.c_void_p(); n = C.c_size_t()
+        if self.L.pm_dict_table(self.h, name.encode(), C.byref(ptr), C.byref(n)) != 0:
+            raise _err(self.L, "pm_dict_table")
+        if n.value == 0:
+            return np.zeros(0, dtype)
+        a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_ubyte)), shape=(n.value,)).view(dtype)
+        a.flags.writeable = False
+        return a
 
     def is_pattern_suffix(self, first_pid, second_pid):
         return bool(self.L.pm_dict_is_pattern_suffix(self.h, first_pid, second_pid))

@@ -198,6 +198,65 @@ __global__ void __launch_bounds__(kHotThreads, 1) dfa_hot_kernel(const DfaParams
     }
 }
 
+// The WHOLE automaton in shared memory with the transition and the longest-pattern id of its target fused into one
+// u32 entry: one gather per byte instead of two (small-alphabet / small dictionaries, config C5a).
+template <bool kIdentCls>
+__global__ void __launch_bounds__(kHotThreads, 1) dfa_small_kernel(const DfaParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem);
+    uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_tab + (size_t(p.n_states) << p.log2_ncp));
+    for (uint32_t i = threadIdx.x; i < (p.n_states << p.log2_ncp); i += kHotThreads) {
+        const uint32_t nx = __ldg(p.delta + i);
+        s_tab[i] = nx | (uint32_t(__ldg(p.longest + nx)) << 16);
+    }
+    if (threadIdx.x < 256) s_cls[threadIdx.x] = p.cls[threadIdx.x];
+    __syncthreads();
+    const uint32_t l2 = p.log2_ncp;
+    auto step = [&](uint32_t e, uint32_t c) -> uint32_t {
+        if constexpr (!kIdentCls) c = s_cls[c];
+        return s_tab[((e & 0xFFFFu) << l2) | c];
+    };
+    const uint64_t n_seg = (p.n + p.seg - 1) / p.seg;
+    for (uint64_t seg = uint64_t(blockIdx.x) * kHotThreads + threadIdx.x; seg < n_seg; seg += uint64_t(gridDim.x) * kHotThreads) {
+        const uint64_t s0 = seg * uint64_t(p.seg);
+        const uint64_t s1 = min(p.n, s0 + uint64_t(p.seg));
+        int64_t w = int64_t(s0) - int64_t(p.warm);
+        if (w < -int64_t(p.hist_valid)) w = -int64_t(p.hist_valid);
+        uint32_t e = 0;   // state in the low half, its longest pid in the high half
+        int64_t q0 = w;
+        for (; q0 < int64_t(s0) && (q0 & 15); ++q0) e = step(e, *(p.stream + q0));
+        for (; q0 < int64_t(s0); q0 += 16) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.stream + q0));
+            const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) e = step(e, (ws[k >> 2] >> (8 * (k & 3))) & 0xFF);
+        }
+        uint64_t q = s0;
+        if (p.wide) {
+            for (; q + 32 <= s1; q += 32) {
+                uint32_t ws[8];
+                ldg256(p.stream + q, ws);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r[8];
+#pragma unroll
+                    for (int k = 0; k < 16; k += 2) {
+                        e = step(e, (ws[half * 4 + (k >> 2)] >> (8 * (k & 3))) & 0xFF);
+                        const uint32_t e2 = step(e, (ws[half * 4 + (k >> 2)] >> (8 * ((k + 1) & 3))) & 0xFF);
+                        r[k >> 1] = __byte_perm(e, e2, 0x7632);   // {longest(e), longest(e2)}
+                        e = e2;
+                    }
+                    stg256(p.out + q + half * 16, r);
+                }
+            }
+        }
+        for (; q < s1; ++q) {
+            e = step(e, p.stream[q]);
+            p.out[q] = uint16_t(e >> 16);
+        }
+    }
+}
+
 }  // namespace
 
 void dfa_plan_hot(uint32_t n_states, uint32_t log2_ncp, const uint32_t* depth_count, uint32_t n_depths,
@@ -243,6 +302,18 @@ cudaError_t dfa_scan_launch(const DfaParams& p_in, bool ident_cls, bool flat, in
     uint32_t seg = 4096;
     while (seg < 16384 && p.n / (uint64_t(seg) * 2) >= uint64_t(n_sms) * kHotThreads * 2) seg *= 2;
     p.seg = seg;
+    // the whole automaton is hot and its fused u32 table fits: one gather per byte
+    const size_t small_smem = (size_t(p.n_states) << p.log2_ncp) * 4 + 256;
+    if (p.hot_rows == p.n_states && p.n_states <= 65535 && small_smem <= 200 * 1024 && !p.no_fused) {
+        auto kern = ident_cls ? dfa_small_kernel<true> : dfa_small_kernel<false>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_smem));
+        if (e != cudaSuccess) return e;
+        const uint64_t n_seg = (p.n + seg - 1) / seg;
+        const uint64_t ctas = (n_seg + kHotThreads - 1) / kHotThreads;
+        kern<<<uint32_t(ctas < uint64_t(n_sms) ? ctas : uint64_t(n_sms)), kHotThreads, small_smem, st>>>(p);
+        ++*launches;
+        return cudaGetLastError();
+    }
     const size_t smem = (size_t(p.hot_rows) << p.log2_ncp) * 2 + size_t(p.fb_count) * 4 + size_t(p.hot_long) * 2 + 256;
     auto kern = ident_cls ? dfa_hot_kernel<true> : dfa_hot_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));

@@ -20,6 +20,8 @@ struct DfaParams {
     const uint32_t* fb_meta; // [state] Bloom of the goto children | failure state << 16 (see dict.hpp)
     uint32_t fb_count;       // states [hot_rows, hot_rows + fb_count) -- the first BFS level below the hot rows -- keep
                              // their fb_meta word in shared memory: no child on c => the step is the failure state's hot row
+    uint32_t n_states;       // states of the automaton
+    uint32_t no_fused;       // do not use the fused-entry kernel for automata that fit shared memory entirely (A/B switch)
     uint32_t seg;            // bytes reported per thread (filled by the launcher)
     uint32_t wide;           // stream and out are 32-byte aligned: 256-bit segment I/O (filled by the launcher)
 };

@@ -391,6 +391,129 @@ void Dict::build_dfa() const {
     d.built = true;
 }
 
+// Core/src/mpac.c:147-210 again, this time kept as goto + failure + nearest-output link and packed for the deep-match
+// kernel (see DeepTables in dict.hpp).
+void Dict::build_deep() const {
+    std::lock_guard<std::mutex> lock(lazy_mu_);
+    if (deep.built) return;
+    if (fwd_->size() == 1 && !pats.empty()) {  // loaded from a cache file: rebuild the forward trie from the patterns
+        for (uint32_t i = 0; i < pats.size(); ++i) {
+            uint32_t st = 0;
+            for (uint32_t k = 0; k < pats[i].len; ++k) st = fwd_->child_or_add(st, bytes[pats[i].off + k]);
+            fwd_->term[st] = i + 1;
+        }
+    }
+    Bfs t(fwd_->edge, fwd_->term);
+    DeepTables& x = deep;
+    x = DeepTables();
+    x.built = true;
+    x.n_states = t.n;
+    {
+        uint32_t maxd = 0;
+        for (uint32_t v = 0; v < t.n; ++v) maxd = std::max(maxd, t.depth[v]);
+        x.depth_count.assign(maxd + 1, 0);
+        for (uint32_t v = 0; v < t.n; ++v) x.depth_count[t.depth[v]]++;
+    }
+    auto go = [&](uint32_t v, uint8_t b) -> uint32_t {  // goto(v, b) or 0xFFFFFFFF; children are sorted by byte
+        uint32_t lo = t.off[v], hi = t.off[v + 1];
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) / 2;
+            if (t.byte[mid] < b) lo = mid + 1; else hi = mid;
+        }
+        return (lo < t.off[v + 1] && t.byte[lo] == b) ? t.child[lo] : 0xFFFFFFFFu;
+    };
+    // failure links and longest pids in breadth-first order (ids ARE breadth-first)
+    std::vector<uint32_t> fail(t.n, 0), longest(t.n, 0);
+    for (uint32_t s = 0; s < t.n; ++s) {
+        if (s) longest[s] = t.term[s] ? t.term[s] : longest[fail[s]];
+        for (uint32_t k = t.off[s]; k < t.off[s + 1]; ++k) {
+            const uint32_t c = t.child[k];
+            const uint8_t b = t.byte[k];
+            uint32_t f = 0;
+            if (s) {
+                uint32_t v = fail[s];
+                for (;;) {
+                    const uint32_t g = go(v, b);
+                    if (g != 0xFFFFFFFFu) { f = g; break; }
+                    if (!v) break;
+                    v = fail[v];
+                }
+            }
+            fail[c] = f;
+        }
+    }
+    auto delta = [&](uint32_t s, uint8_t b) -> uint32_t {  // complete DFA transition
+        for (;;) {
+            const uint32_t g = go(s, b);
+            if (g != 0xFFFFFFFFu) return g;
+            if (!s) return 0;
+            s = fail[s];
+        }
+    };
+    // numbering: depth <= 1, then depth 2 (both breadth-first = their current order), then depth >= 3 depth-first
+    uint32_t n_le1 = 0, n_le2 = 0;
+    for (uint32_t v = 0; v < t.n; ++v) { n_le1 += t.depth[v] <= 1; n_le2 += t.depth[v] <= 2; }
+    std::vector<uint32_t> nid(t.n, 0);
+    for (uint32_t v = 0; v < n_le2; ++v) nid[v] = v;   // breadth-first ids of depth <= 2 are already 0 .. n_le2-1
+    {
+        uint32_t next = n_le2;
+        std::vector<uint32_t> stack;
+        for (uint32_t v = n_le1; v < n_le2; ++v) {      // subtrees of the depth-2 states, in order
+            for (uint32_t k = t.off[v + 1]; k-- > t.off[v];) stack.push_back(t.child[k]);
+            while (!stack.empty()) {
+                const uint32_t u = stack.back();
+                stack.pop_back();
+                nid[u] = next++;
+                for (uint32_t k = t.off[u + 1]; k-- > t.off[u];) stack.push_back(t.child[k]);   // reversed: smallest byte on top
+            }
+        }
+    }
+    std::vector<uint32_t> old_of(t.n, 0);
+    for (uint32_t v = 0; v < t.n; ++v) old_of[nid[v]] = v;
+    x.n_hot = n_le1; x.n_hot_targets = n_le2;
+    if (n_le2 > 65535 || t.n >= (1u << 24) || pats.size() > 65535) return;   // usable stays false
+    x.hot_rows.assign(size_t(n_le1) << 8, 0);
+    x.hot_longest.assign(n_le1, 0);
+    for (uint32_t s = 0; s < n_le1; ++s) {
+        x.hot_longest[s] = uint16_t(longest[s]);
+        for (uint32_t b = 0; b < 256; ++b) x.hot_rows[(size_t(s) << 8) | b] = uint16_t(nid[delta(s, uint8_t(b))]);
+    }
+    x.recs.assign(size_t(t.n) * 8, 0);
+    for (uint32_t id = n_le1; id < t.n; ++id) {
+        const uint32_t v = old_of[id];
+        uint32_t* r = x.recs.data() + size_t(id) * 8;
+        const uint32_t nc = t.off[v + 1] - t.off[v];
+        r[1] = longest[v];
+        uint32_t kind = 0, count = 0;
+        if (nc == 1 && t.depth[v] >= 3) {           // CHAIN: follow single children while they are id + 1
+            kind = 1;
+            uint32_t u = v;
+            uint64_t labels = 0;
+            while (count < 8 && t.off[u + 1] - t.off[u] == 1) {
+                const uint32_t c = t.child[t.off[u]];
+                // depth-first numbering makes the only child the next id
+                labels |= uint64_t(t.byte[t.off[u]]) << (8 * count);
+                r[4 + count / 2] |= (longest[c] & 0xFFFFu) << (16 * (count & 1));
+                ++count;
+                u = c;
+            }
+            r[2] = uint32_t(labels); r[3] = uint32_t(labels >> 32);
+            ++x.n_chain;
+        } else if (nc <= 6) {                        // BRANCH (also leaves and depth-2 states with one child)
+            for (uint32_t k = t.off[v]; k < t.off[v + 1]; ++k) r[2 + count++] = (nid[t.child[k]] << 8) | t.byte[k];
+            ++x.n_branch;
+        } else {                                     // DENSE
+            kind = 2;
+            r[2] = x.n_dense++;
+            const size_t base = x.dense_rows.size();
+            x.dense_rows.resize(base + 256);
+            for (uint32_t b = 0; b < 256; ++b) x.dense_rows[base + b] = nid[delta(v, uint8_t(b))];
+        }
+        r[0] = nid[fail[v]] | (kind << 24) | (count << 26);
+    }
+    x.usable = true;
+}
+
 // ---- compiled-automaton cache -----------------------------------------------------------------
 // One binary file: magic (carries the layout version), the scalar block, the table vectors, and a trailing FNV-1a
 // checksum over everything before it.  Written to a temporary name in the same directory and renamed into place, so

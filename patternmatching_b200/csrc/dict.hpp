@@ -76,6 +76,29 @@ struct DfaTables {
     bool built = false;
 };
 
+// Compact forward automaton for deep-match traffic (deep_scan.cu): the reference's goto + failure machine
+// (Core/src/mpac.c:147-210) kept as goto + failure -- NOT completed to a dense DFA -- in one 32-byte record per
+// state, 23 MB for snort+et instead of the dense table's 734 MB, so that it is L2-resident.
+//   state numbering: the root and the depth-1 states first ("hot": their complete DFA rows live in shared memory as
+//   u16), then the depth-2 states in breadth-first order, then every deeper state in depth-first pre-order with
+//   children in byte order -- the first child of a state of depth >= 3 is always state + 1, so a run of single-child
+//   states ("chain") is a run of consecutive ids and one record describes up to eight steps of it.
+//   record of state s (8 x u32):  w0 = failure state | kind << 24 | count << 26,  w1 = longest pid at s,
+//     kind 0 BRANCH: count <= 6 goto edges, w2.. = child << 8 | byte (sorted by byte); a miss follows the failure link
+//     kind 1 CHAIN : count <= 8 steps: bytes of states s+1 .. s+count in w2,w3, their longest pids (u16) in w4..w7
+//     kind 2 DENSE : more than 6 children: w2 = index of a complete 256-entry DFA row in dense_rows
+struct DeepTables {
+    uint32_t n_states = 0, n_hot = 0, n_hot_targets = 0;   // hot rows point at states < n_hot_targets (fit u16)
+    std::vector<uint16_t> hot_rows;      // [hot state << 8 | byte] -> next state (complete DFA transition)
+    std::vector<uint16_t> hot_longest;   // [hot state] -> longest pid
+    std::vector<uint32_t> recs;          // 8 words per state (records of the hot states are unused)
+    std::vector<uint32_t> dense_rows;    // 256 entries per DENSE state
+    uint32_t n_dense = 0, n_chain = 0, n_branch = 0;
+    std::vector<uint32_t> depth_count;   // states per depth (forward trie)
+    bool usable = false;                 // false: the automaton does not fit this layout (ids >= 2^24, > 65535 pids, ...)
+    bool built = false;
+};
+
 // Karp-Rabin suffix-stage tables (randomized variant).
 struct KrTables {
     uint64_t seed = 0, r = 0;
@@ -106,6 +129,7 @@ class Dict {
     // dictionary-level lock: engines on different threads may ask for it at the same time.  After it returns the
     // tables are read-only like everything else in a compiled dictionary.
     void build_dfa() const;
+    void build_deep() const;          // same contract as build_dfa(): lazily, once, under the dictionary's lock
     // Karp-Rabin tables for one seed: returned by value, owned by the caller (an engine) -- the dictionary itself is
     // not touched, so engines with different seeds share it safely.
     KrTables build_kr(uint64_t seed) const;
@@ -127,6 +151,7 @@ class Dict {
     bool compiled = false;
     SfxTables sfx;
     mutable DfaTables dfa;            // see build_dfa()
+    mutable DeepTables deep;          // see build_deep()
     std::string error;
 
   private:

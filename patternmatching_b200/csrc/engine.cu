@@ -16,6 +16,7 @@
 
 #include "../../include/pm_b200.h"
 #include "aux_kernels.cuh"
+#include "deep_scan.cuh"
 #include "dfa_scan.cuh"
 #include "dict.hpp"
 #include "host_pool.hpp"
@@ -60,7 +61,7 @@ constexpr size_t kQueueMaxPerCta = size_t(256) << 10;  // deferred-walk slots pe
 
 // Diagnostic / A-B switches, read ONCE when an engine is created.
 struct EngineOpts {
-    bool sfx_no_tex = false, sfx_no_l3 = false, dfa_no_fb = false, dfa_flat = false;
+    bool sfx_no_tex = false, sfx_no_l3 = false, dfa_no_fb = false, dfa_flat = false, dfa_deep = false, dfa_no_fused = false;
     uint32_t l3_min = 4, l3_min_b = 4;
     size_t host_chunk = size_t(16) << 20;  // bytes per pipeline slot for pinned buffers (PM_HOST_CHUNK_MIB)
     int host_threads = 0;                  // staging threads (PM_HOST_THREADS; default: the host's cores, at most 16)
@@ -70,6 +71,8 @@ struct EngineOpts {
         o.sfx_no_l3 = getenv("PM_SFX_NO_L3") != nullptr;
         o.dfa_no_fb = getenv("PM_DFA_NO_FB") != nullptr;
         o.dfa_flat = getenv("PM_DFA_FLAT") != nullptr;
+        o.dfa_deep = getenv("PM_DFA_DEEP") != nullptr;
+        o.dfa_no_fused = getenv("PM_DFA_NO_FUSED") != nullptr;
         if (const char* v = getenv("PM_SFX_L3_MIN")) o.l3_min = o.l3_min_b = uint32_t(atoi(v));
         if (const char* v = getenv("PM_SFX_L3_MIN_B")) o.l3_min_b = uint32_t(atoi(v));
         if (const char* v = getenv("PM_HOST_CHUNK_MIB")) { const long m = atol(v); if (m >= 1 && m <= 1024) o.host_chunk = size_t(m) << 20; }
@@ -110,6 +113,10 @@ struct pm_engine {
     uint8_t* d_dfa_cls = nullptr;
     uint32_t* d_fb_meta = nullptr;
     bool dfa_ready = false;
+    // compact goto + failure automaton of the deep-match walker (device copies made on first use)
+    uint16_t *d_deep_hot = nullptr, *d_deep_long = nullptr;
+    uint32_t *d_deep_recs = nullptr, *d_deep_dense = nullptr;
+    bool deep_ready = false;
     // kr tables: built for THIS engine's seed and owned by it
     pm::KrDevTables kr{};
     bool kr_ready = false;
@@ -166,6 +173,19 @@ int ensure_dfa(pm_engine* e) {
     std::vector<uint8_t> cls(d.dfa.cls, d.dfa.cls + 256);
     CU(upload(cls, &e->d_dfa_cls, &e->table_bytes));
     e->dfa_ready = true;
+    return 0;
+}
+
+int ensure_deep(pm_engine* e) {
+    if (e->deep_ready) return 0;
+    const pm::Dict& d = *e->dict;
+    d.build_deep();
+    if (!d.deep.usable) return fail("the automaton does not fit the deep-match layout");
+    CU(upload(d.deep.hot_rows, &e->d_deep_hot, &e->table_bytes));
+    CU(upload(d.deep.hot_longest, &e->d_deep_long, &e->table_bytes));
+    CU(upload(d.deep.recs, &e->d_deep_recs, &e->table_bytes));
+    CU(upload(d.deep.dense_rows, &e->d_deep_dense, &e->table_bytes));
+    e->deep_ready = true;
     return 0;
 }
 
@@ -267,11 +287,12 @@ int choose_algo(pm_engine* e, const uint8_t* d_stream, size_t n, size_t hist_val
     }
     const bool deep = deferred * 32 > 4 * kSampleWin;     // more than 1/32 of the positions walk past level 4
     if (!deep) { e->auto_flat = false; return PM_ALGO_SFX; }
-    if (ensure_dfa(e)) return -1;
-    uint32_t hot_rows = 0, hot_long = 0, fb_count = 0;
     const pm::Dict& d = *e->dict;
-    pm::dfa_plan_hot(d.dfa.n_states, d.dfa.log2_ncp, d.dfa.depth_count.data(), uint32_t(d.dfa.depth_count.size()), &hot_rows, &hot_long, &fb_count);
-    e->auto_flat = hot_rows < d.dfa.n_states;              // deep walks and an automaton that does not fit: occupancy + L1 win
+    d.build_deep();   // cheap (no dense table): gives the forward trie's states per depth
+    uint32_t hot_rows = 0, hot_long = 0, fb_count = 0;
+    pm::dfa_plan_hot(d.deep.n_states, d.sfx.log2_ncp, d.deep.depth_count.data(), uint32_t(d.deep.depth_count.size()), &hot_rows, &hot_long, &fb_count);
+    // deep walks and an automaton that does not fit shared memory: the compact-record walker (the dense DFA is never built)
+    e->auto_flat = hot_rows < d.deep.n_states;
     return PM_ALGO_DFA;
 }
 
@@ -311,12 +332,28 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
         if (ce != cudaSuccess) return cuda_fail(ce, "sfx_scan_launch");
         return 0;
     }
+    if (algo == PM_ALGO_DFA && (force_flat || e->opts.dfa_deep) && !e->opts.dfa_flat) {
+        // deep-match traffic on an automaton that does not fit shared memory: the compact goto + failure records
+        e->dict->build_deep();
+        if (e->dict->deep.usable) {
+            if (ensure_deep(e)) return -1;
+            pm::DeepParams p{};
+            p.stream = d_stream; p.n = n; p.hist_valid = hist_valid; p.out = d_out;
+            p.hot_rows = e->d_deep_hot; p.hot_longest = e->d_deep_long; p.n_hot = d.deep.n_hot;
+            p.recs = e->d_deep_recs; p.dense_rows = e->d_deep_dense;
+            p.warm = d.max_len ? d.max_len - 1 : 0;
+            cudaError_t ce = pm::deep_scan_launch(p, e->n_sms, st, &e->launches);
+            if (ce != cudaSuccess) return cuda_fail(ce, "deep_scan_launch");
+            return 0;
+        }
+    }
     if (algo == PM_ALGO_DFA) {
         if (ensure_dfa(e)) return -1;
         pm::DfaParams p{};
         p.stream = d_stream; p.n = n; p.hist_valid = hist_valid; p.out = d_out;
         p.delta = e->d_delta; p.longest = e->d_longest; p.cls = e->d_dfa_cls; p.log2_ncp = d.dfa.log2_ncp;
         p.warm = d.max_len ? d.max_len - 1 : 0;
+        p.n_states = d.dfa.n_states; p.no_fused = e->opts.dfa_no_fused ? 1u : 0u;
         pm::dfa_plan_hot(d.dfa.n_states, d.dfa.log2_ncp, d.dfa.depth_count.data(), uint32_t(d.dfa.depth_count.size()),
                          &p.hot_rows, &p.hot_long, &p.fb_count);
         p.fb_meta = e->d_fb_meta;
@@ -364,8 +401,8 @@ void carry_history(pm_engine* e, const uint8_t* stream, size_t n) {
     e->hist_valid += n;
 }
 
-// Small calls: stage [history | bytes] in pinned memory, ONE H2D copy, ONE kernel that writes its results straight
-// into mapped pinned memory, one stream synchronise.  Taken for PM_ALGO_SFX / PM_ALGO_AUTO (the walker is the backward
+// Small calls: stage [history | bytes] in pinned memory, ONE H2D copy, ONE kernel, one D2H copy, one stream synchronise
+// (results written by the kernel straight into mapped pinned memory were slower: 2-byte posted writes over PCIe).  Taken for PM_ALGO_SFX / PM_ALGO_AUTO (the walker is the backward
 // scan's own bounded walk); an explicitly requested DFA or KR scan runs its own kernels whatever the size.
 int scan_host_small(pm_engine* e, const uint8_t* stream, size_t n, const HostSink& sink) {
     const size_t H = e->halo;
@@ -375,10 +412,11 @@ int scan_host_small(pm_engine* e, const uint8_t* stream, size_t n, const HostSin
     memcpy(h + H, stream, n);
     CU(cudaMemcpyAsync(e->d_in[0] + H - hv, h + H - hv, hv + n, cudaMemcpyHostToDevice, e->st[0]));
     pm::SfxParams p{};
-    p.stream = e->d_in[0] + H; p.n = n; p.hist_valid = hv; p.out = e->h_out[0];  // pinned host memory is device-addressable (UVA)
+    p.stream = e->d_in[0] + H; p.n = n; p.hist_valid = hv; p.out = e->d_out[0];
     if (fill_sfx_params(e, &p, n, 0)) return -1;
     cudaError_t ce = pm::sfx_walk_launch(p, e->st[0], &e->launches);
     if (ce != cudaSuccess) return cuda_fail(ce, "sfx_walk_launch");
+    CU(cudaMemcpyAsync(e->h_out[0], e->d_out[0], n * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->st[0]));
     CU(cudaStreamSynchronize(e->st[0]));
     if (sink.out16) memcpy(sink.out16, e->h_out[0], n * sizeof(uint16_t));
     else pm::HostPool::expand_range(e->h_out[0], 0, n, sink.table, sink.out64);
@@ -402,18 +440,44 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
     const bool direct_out = sink.out16 && is_pinned(sink.out16);   // the D2H copy lands in the caller's buffer
     // Pageable buffers are staged through the pinned ones by the pool's threads, in smaller pieces so that staging
     // piece k+1 and unloading piece k-1 overlap the transfers and the scan of piece k.
-    const size_t chunk = (in_pinned && direct_out) ? e->opts.host_chunk : std::min(e->opts.host_chunk, kPageableChunk);
+    // When host threads have work to do, a call is cut into at least ~8 pieces (512 KiB .. 4 MiB) so that the exposed
+    // first stage-in and last unload stay a small part of it.
+    size_t chunk = e->opts.host_chunk;
+    if (!(in_pinned && direct_out)) {
+        chunk = std::min(chunk, kPageableChunk);
+        while (chunk > (size_t(512) << 10) && n / chunk < 8) chunk >>= 1;
+    }
     const size_t n_chunks = (n + chunk - 1) / chunk;
     pm::HostPool& pool = *e->pool;
-    auto finish = [&](size_t k) -> int {  // chunk k has fully left the device: hand its results to the caller
-        const int b = int(k & 1);
-        CU(cudaEventSynchronize(e->done[b]));
-        const size_t o = k * chunk, len = std::min(chunk, n - o);
-        if (sink.out64) pool.expand(e->h_out[b], len, sink.table, sink.out64 + o);
-        else if (!direct_out) pool.copy(sink.out16 + o, e->h_out[b], len * sizeof(uint16_t));
-        return 0;
+    // One pool run per pipeline step does BOTH host copies that are due: unloading piece k-2 (translate / copy its
+    // results out of the pinned buffer) and staging piece k (copy its bytes into the pinned buffer) -- every wake-up of
+    // the workers costs tens of microseconds, comparable to the copies themselves for small pieces.
+    auto host_step = [&](bool unload, size_t ku, bool stage, size_t ks) {
+        const size_t ou = ku * chunk, lenu = unload ? std::min(chunk, n - ou) : 0;
+        const size_t os = ks * chunk, lens = stage ? std::min(chunk, n - os) : 0;
+        const size_t from_call = stage ? std::min(os, H) : 0;
+        const uint16_t* res = e->h_out[ku & 1];
+        const bool do_unload = unload && (sink.out64 || !direct_out);
+        const bool do_stage = stage && !in_pinned;
+        if (!do_unload && !do_stage) return;
+        auto work = [&](int part, int parts) {
+            size_t lo, hi;
+            if (do_unload) {
+                pm::HostPool::slice(lenu, part, parts, 512, &lo, &hi);
+                if (hi > lo) {
+                    if (sink.out64) pm::HostPool::expand_range(res, lo, hi, sink.table, sink.out64 + ou);
+                    else memcpy(sink.out16 + ou + lo, res + lo, (hi - lo) * sizeof(uint16_t));
+                }
+            }
+            if (do_stage) {
+                pm::HostPool::slice(from_call + lens, part, parts, 4096, &lo, &hi);
+                if (hi > lo) memcpy(e->h_in[ks & 1] + lo, stream + os - from_call + lo, hi - lo);
+            }
+        };
+        if (lenu + lens < (size_t(128) << 10)) work(0, 1);   // not worth waking anybody
+        else pool.run(work);
     };
-    auto submit = [&](size_t k) -> int {
+    auto submit = [&](size_t k) -> int {   // piece k is staged (or pinned in place): enqueue copy in, scan, copy out
         const int b = int(k & 1);
         const size_t o = k * chunk, len = std::min(chunk, n - o);
         // history in front of the chunk: from this call's own bytes when there are enough, else the carried tail
@@ -422,23 +486,22 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
         uint8_t* din = e->d_in[b];
         if (from_call < H)
             CU(cudaMemcpyAsync(din, e->h_hist.data() + from_call, H - from_call, cudaMemcpyHostToDevice, e->st[b]));
-        const uint8_t* src = stream + o - from_call;
-        if (!in_pinned) {
-            pool.copy(e->h_in[b], src, from_call + len);
-            src = e->h_in[b];
-        }
+        const uint8_t* src = in_pinned ? stream + o - from_call : e->h_in[b];
         CU(cudaMemcpyAsync(din + H - from_call, src, from_call + len, cudaMemcpyHostToDevice, e->st[b]));
         if (scan_device_impl(e, algo, din + H, len, hist_total, e->d_out[b], e->st[b], b)) return -1;
         CU(cudaMemcpyAsync(direct_out ? sink.out16 + o : e->h_out[b], e->d_out[b], len * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->st[b]));
         CU(cudaEventRecord(e->done[b], e->st[b]));
         return 0;
     };
-    for (size_t k = 0; k < n_chunks; ++k) {
-        if (k >= 2 && finish(k - 2)) { quiesce(e); return -1; }
-        if (submit(k)) { quiesce(e); return -1; }
+    for (size_t k = 0; k < n_chunks + 2; ++k) {
+        const bool unload = k >= 2, stage = k < n_chunks;
+        if (unload) {   // piece k-2 has left the device (its slot's buffers are reused by piece k)
+            cudaError_t ce = cudaEventSynchronize(e->done[k & 1]);
+            if (ce != cudaSuccess) { quiesce(e); return cuda_fail(ce, "cudaEventSynchronize"); }
+        }
+        host_step(unload, k - 2, stage, k);
+        if (stage && submit(k)) { quiesce(e); return -1; }
     }
-    for (size_t k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; ++k)
-        if (finish(k)) { quiesce(e); return -1; }
     carry_history(e, stream, n);
     return 0;
 }
@@ -535,6 +598,23 @@ int pm_dict_pattern(const pm_dict* d, uint32_t pid, uint32_t* file, uint32_t* li
     if (bytes) *bytes = d->d.bytes.data() + p.off;
     return 0;
 }
+int pm_dict_table(const pm_dict* d, const char* name, const void** data, size_t* bytes) {
+    const pm::Dict& x = d->d;
+    if (!x.compiled) return fail("pm_dict_table: dictionary is not compiled");
+    const std::string n = name ? name : "";
+    auto give = [&](const auto& v) { *data = v.data(); *bytes = v.size() * sizeof(v[0]); return 0; };
+    if (n == "sfx.root2") return give(x.sfx.root2);
+    if (n == "sfx.rows") return give(x.sfx.rows);
+    if (n.rfind("deep.", 0) == 0) {
+        x.build_deep();
+        if (!x.deep.usable) return fail("pm_dict_table: the automaton does not fit the deep-match layout");
+        if (n == "deep.recs") return give(x.deep.recs);
+        if (n == "deep.hot_rows") return give(x.deep.hot_rows);
+        if (n == "deep.hot_longest") return give(x.deep.hot_longest);
+        if (n == "deep.dense_rows") return give(x.deep.dense_rows);
+    }
+    return fail("pm_dict_table: unknown table " + n);
+}
 int pm_dict_is_pattern_suffix(const pm_dict* d, uint32_t first_pid, uint32_t second_pid) {
     return d->d.is_pattern_suffix(first_pid, second_pid) ? 1 : 0;
 }
@@ -612,7 +692,7 @@ void pm_engine_free(pm_engine* e) {
     e->pool.reset();
     if (e->rows_tex) cudaDestroyTextureObject(e->rows_tex);
     void* ptrs[] = {e->d_root2, e->d_root1, e->d_rows, e->d_row_best, e->d_cls, e->d_pat_off, e->d_pat_len, e->d_pat_bytes,
-                    e->d_parent, e->d_chain, e->d_pidhash, e->d_tail_rec, e->d_l3f, e->d_anc_off, e->d_anc_list, e->d_sample_out, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_fb_meta, e->d_acc,
+                    e->d_parent, e->d_chain, e->d_pidhash, e->d_tail_rec, e->d_l3f, e->d_anc_off, e->d_anc_list, e->d_sample_out, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_fb_meta, e->d_deep_hot, e->d_deep_long, e->d_deep_recs, e->d_deep_dense, e->d_acc,
                     e->d_compact_counts, e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1], e->d_queue[0], e->d_queue[1], e->d_qcount};
     for (void* p : ptrs) if (p) cudaFree(p);
     pm::kr_free_tables(&e->kr);

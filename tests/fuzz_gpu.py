@@ -59,6 +59,9 @@ def main():
             d.add_pattern(p, 0, i + 1); o.add_pattern(p, 0, i + 1)
         d.compile(); o.compile()
         eng = pm.Engine(d)
+        os.environ["PM_DFA_DEEP"] = "1"      # a second engine whose DFA scans take the compact-record walker (deep_scan.cu)
+        eng_deep = pm.Engine(d)
+        del os.environ["PM_DFA_DEEP"]
         hist = min(hist, stream.size - 1) if stream.size > 1 else 0
         body = stream[hist:]
         o.reset()
@@ -67,9 +70,9 @@ def main():
         pad = (-hist) % 16
         buf = np.concatenate([np.zeros(pad, np.uint8), stream])
         d_in = torch.from_numpy(buf).to(dev)
-        for algo, name in ((pm.ALGO_SFX, "sfx"), (pm.ALGO_DFA, "dfa"), (pm.ALGO_AUTO, "auto")):
+        for algo, name in ((pm.ALGO_SFX, "sfx"), (pm.ALGO_DFA, "dfa"), (pm.ALGO_AUTO, "auto"), (pm.ALGO_DFA, "deep")):
             d_out = torch.zeros(max(body.size, 8), dtype=torch.int16, device=dev)
-            eng.scan_device(d_in.data_ptr() + pad + hist, body.size, d_out, hist_valid=hist, algo=algo)
+            (eng_deep if name == "deep" else eng).scan_device(d_in.data_ptr() + pad + hist, body.size, d_out, hist_valid=hist, algo=algo)
             torch.cuda.synchronize()
             got = d_out.cpu().numpy().view(np.uint16)[:body.size]
             if not np.array_equal(got, want):

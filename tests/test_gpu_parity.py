@@ -490,9 +490,11 @@ def test_kr_variant_on_the_16gib_stream(engine_merged, dict_merged):
     assert fn == 0 and partial == 0
     assert fp <= n * 1e-7
 
-@pytest.mark.parametrize("env", [{}, {"PM_DFA_NO_FB": "1"}, {"PM_DFA_FLAT": "1"}], ids=["hot+fallback-words", "hot", "flat"])
+@pytest.mark.parametrize("env", [{}, {"PM_DFA_NO_FB": "1"}, {"PM_DFA_FLAT": "1"}, {"PM_DFA_DEEP": "1"}],
+                         ids=["hot+fallback-words", "hot", "flat", "deep-records"])
 def test_every_variant_of_the_dfa_kernel_is_exact(env, oracle_merged, dict_merged, monkeypatch):
-    """Forward-DFA walker: hot rows + Bloom/failure words of the next level (default), hot rows only, flat."""
+    """Forward-DFA walker: hot rows + Bloom/failure words of the next level (default), hot rows only, flat (dense table
+    in global memory), and the compact goto + failure records of deep_scan.cu."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     engine_merged = pm.Engine(dict_merged)     # the switches are read once, when an engine is created
@@ -500,6 +502,32 @@ def test_every_variant_of_the_dfa_kernel_is_exact(env, oracle_merged, dict_merge
     for kind in ("planted", "ascii", "almost"):
         stream = oracle_merged.gen(kind, 777, n)
         assert np.array_equal(gpu_scan(engine_merged, stream, pm.ALGO_DFA), want_pids(oracle_merged, stream)), kind
+    # history shorter / longer than the warm-up, ragged sizes
+    total = oracle_merged.gen("almost", 0, 70_000)
+    want = want_pids(oracle_merged, total)
+    for cut, n2 in ((352, 1), (1000, 15), (4096, 4097), (20_000, 50_000 - 3)):
+        got = gpu_scan(engine_merged, total[cut:cut + n2], pm.ALGO_DFA, hist=total[cut - 352:cut])
+        assert np.array_equal(got, want[cut:cut + n2]), (cut, n2)
+
+
+def test_small_automaton_kernel_variants(monkeypatch):
+    """An automaton that fits shared memory entirely: fused {next state, longest pid} entries (default) and the two-gather
+    hot kernel (PM_DFA_NO_FUSED), on a small-alphabet dictionary with class compression."""
+    pats = [b"a" * k for k in range(1, 65)]
+    for L in range(1, 9):
+        for v in range(1 << L):
+            pats.append(bytes(ord("a") + ((v >> i) & 1) for i in range(L)))
+    lines = b"\n".join(pats) + b"\n"
+    o = Oracle(); o.add_dict_bytes(lines); o.compile()
+    stream = o.gen("ab", 4096, (1 << 20) + 77)
+    stream[::5000] = 0x7A                      # bytes outside the alphabet
+    want = want_pids(o, stream)
+    for env in ({}, {"PM_DFA_NO_FUSED": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = pm.Engine(pm.Dictionary().add_bytes(lines).compile())
+        assert np.array_equal(gpu_scan(eng, stream, pm.ALGO_DFA), want), env
+        assert np.array_equal(gpu_scan(eng, stream[5:70000], pm.ALGO_DFA, hist=stream[:5]), want_pids(o, stream[:70000])[5:]), env
 
 def test_differential_fuzz_small():
     """Random dictionaries (2 .. 256 byte classes, lengths 1 .. 353, shared suffixes / prefixes, nested patterns) x

@@ -149,3 +149,63 @@ def test_plugin_registration_fills_an_mpselem():
     e.add_pattern(obj, b"a\x00b", 3, 0x1234)
     assert e.total_mem(obj) == 0
     e.free(obj)
+
+
+def emulate_deep_walk(d, stream):
+    """Host emulation of deep_scan.cu's per-lane state machine over the compact goto + failure records
+    (dict.hpp: DeepTables): the table builder is host logic and is checked here without a GPU."""
+    recs = d.table("deep.recs", np.uint32).reshape(-1, 8)
+    hot = d.table("deep.hot_rows", np.uint16).reshape(-1, 256)
+    hot_long = d.table("deep.hot_longest", np.uint16)
+    dense = d.table("deep.dense_rows", np.uint32).reshape(-1, 256)
+    n_hot = hot.shape[0]
+    out = np.zeros(stream.size, np.uint16)
+    s, q, n, fetches = 0, 0, stream.size, 0
+    while q < n:
+        c = int(stream[q])
+        if s < n_hot:
+            s = int(hot[s, c])
+            out[q] = hot_long[s] if s < n_hot else recs[s, 1]
+            q += 1
+            continue
+        w = recs[s]
+        fetches += 1
+        kind, cnt, fail = (int(w[0]) >> 24) & 3, int(w[0]) >> 26, int(w[0]) & 0xFFFFFF
+        if kind == 1:
+            labels = int(w[2]) | (int(w[3]) << 32)
+            longs = int(w[4]) | (int(w[5]) << 32) | (int(w[6]) << 64) | (int(w[7]) << 96)
+            j = 0
+            while j < cnt and q < n and int(stream[q]) == (labels >> (8 * j)) & 0xFF:
+                out[q] = (longs >> (16 * j)) & 0xFFFF
+                q += 1; j += 1
+            s = fail if (j == 0 and q < n) else s + j
+        elif kind == 0:
+            nxt = [int(x) >> 8 for x in w[2:2 + cnt] if (int(x) & 0xFF) == c]
+            if nxt:
+                s = nxt[0]; out[q] = recs[s, 1]; q += 1
+            else:
+                s = fail
+        else:
+            s = int(dense[int(w[2]), c])
+            out[q] = hot_long[s] if s < n_hot else recs[s, 1]
+            q += 1
+    return out, fetches
+
+
+def test_deep_automaton_records_walk_like_the_oracle(dict_merged, oracle_merged):
+    for kind, n in (("almost", 60000), ("planted", 30000), ("ascii", 20000)):
+        stream = oracle_merged.gen(kind, 4096 * 3, n)
+        got, fetches = emulate_deep_walk(dict_merged, stream)
+        want = (oracle_merged.scan(stream) + 1).astype(np.uint16)
+        assert np.array_equal(got, want), kind
+        print(f"deep records on {kind}: {fetches / n:.3f} record fetches per byte")
+    # a small-alphabet dictionary: long chains, heavy failure traffic
+    pats = [b"a" * k for k in range(1, 41)] + [b"ab" * k + b"c" for k in range(1, 20)] + [b"bca", b"cab", b"abcabcabd"]
+    d = pm.Dictionary(); o = Oracle()
+    for i, p in enumerate(pats):
+        d.add_pattern(p, 0, i + 1); o.add_pattern(p, 0, i + 1)
+    d.compile(); o.compile()
+    rng = np.random.default_rng(2)
+    stream = rng.choice(np.frombuffer(b"aaabbc", np.uint8), 50000)
+    got, _ = emulate_deep_walk(d, stream)
+    assert np.array_equal(got, (o.scan(stream) + 1).astype(np.uint16))
