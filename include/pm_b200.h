@@ -117,7 +117,7 @@ size_t pm_engine_total_mem(const pm_engine* e);
 /* device scratch that is not a table: deferred-walk queues (at most 2 MiB per SM and pipeline slot), the host
  * pipeline's device buffers, compaction counters.  Grows on demand, never shrinks. */
 size_t pm_engine_scratch_mem(const pm_engine* e);
-/* host threads used to stage pageable buffers and to translate pids (PM_HOST_THREADS; default = cores, at most 16) */
+/* host threads used to stage pageable buffers and to translate pids (PM_HOST_THREADS; default = half the cores, at most 16) */
 int pm_engine_host_threads(const pm_engine* e);
 /* KR variant parameters: r is drawn from `seed` (the reference draws it from rand(), bgps.c:469-475) */
 int pm_engine_set_kr_seed(pm_engine* e, uint64_t seed);
@@ -144,8 +144,8 @@ int pm_engine_scan_device(pm_engine* e, int algo, const uint8_t* d_stream, size_
  * pm_engine_reset().  replaces: the chunk loop of measure_single_instance_stats (measure.c:281-304).
  * Page-locked buffers (pm_host_alloc) are used in place; pageable ones are staged through the engine's pinned
  * buffers by its host threads in 4 MiB pieces that overlap the transfers.  Calls of <= 256 KiB (the reference's
- * 100 KiB chunks, measure.c:77; read_char) take a latency path: one H2D copy, one kernel launch, one D2H copy, one
- * synchronise. */
+ * 100 KiB chunks, measure.c:77; read_char) take a latency path: one H2D copy, one kernel launch writing into mapped
+ * pinned memory, one synchronise. */
 int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n, uint16_t* out);
 /* Same pipeline; out[i] = id_of_pid[pid of the longest pattern ending at i] -- 8 bytes per position, what the
  * reference's read_char returns (pattern_id_t is a pointer, Core/src/PatternsTree.h:104; Core/src/mps.h:41-42).
@@ -176,6 +176,17 @@ int pm_engine_summarize(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t 
  * Synchronous. */
 int pm_engine_compact(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t pos_base, int expand_ancestors,
                       uint64_t* d_records, size_t cap, uint64_t* n_records, void* cuda_stream);
+
+/* Sparse mode on device-resident data: scan and return only the positions whose longest match is a pattern of at least
+ * min_len bytes, as position-sorted records (pos_base + i) << 24 | pid in d_records (capacity `cap`; *n_records = number
+ * found, may exceed cap: nothing is written past cap).  The dense result is written to d_out as by pm_engine_scan_device.
+ * PM_ALGO_SFX with min_len >= 3: the scan kernel itself marks the qualifying positions in a 1-bit-per-position bitmap
+ * (row entries carry the pattern length, so the test is one compare per position) and the compaction reads that bitmap and
+ * the flagged entries only -- the dense result is not read again.  Other algorithms / min_len < 3: dense scan followed by
+ * the dense compaction.  Synchronous (returns the count). */
+int pm_engine_scan_device_records(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid,
+                                  uint64_t pos_base, uint32_t min_len, uint16_t* d_out, uint64_t* d_records, size_t cap,
+                                  uint64_t* n_records, void* cuda_stream);
 
 /* Seeded synthetic streams generated directly in HBM (definitions: SURVEY.md 8d, oracle/pm_oracle.c):
  * writes bytes [off, off+n) of stream `kind` to d_dst.  off and n multiples of 4096. */

@@ -84,6 +84,7 @@ def lib():
         "pm_engine_set_kr_seed": (C.c_int, [vp, u64]),
         "pm_engine_scan_device": (C.c_int, [vp, C.c_int, vp, sz, sz, vp, vp]),
         "pm_engine_scan_host": (C.c_int, [vp, C.c_int, vp, sz, vp]),
+        "pm_engine_scan_device_records": (C.c_int, [vp, C.c_int, vp, sz, sz, u64, u32, vp, vp, sz, C.POINTER(u64), vp]),
         "pm_engine_scan_host_ids": (C.c_int, [vp, C.c_int, vp, sz, vp, sz, vp]),
         "pm_engine_scratch_mem": (sz, [vp]),
         "pm_engine_host_threads": (C.c_int, [vp]),
@@ -303,6 +304,16 @@ class Engine:
     def scan_device(self, d_stream, n, d_out, hist_valid=0, algo=ALGO_SFX, cuda_stream=0):
         self._check(self.L.pm_engine_scan_device(self.h, algo, _ptr(d_stream), n, hist_valid, _ptr(d_out), cuda_stream),
                     "pm_engine_scan_device")
+
+    def scan_device_records(self, d_stream, n, d_out, d_records, cap, min_len=4, hist_valid=0, pos_base=0, algo=ALGO_SFX,
+                            cuda_stream=0):
+        """Sparse mode: dense result in d_out, position-sorted (pos << 24 | pid) records of the matches with >= min_len
+        pattern bytes in d_records; returns the number of such matches."""
+        cnt = C.c_uint64()
+        self._check(self.L.pm_engine_scan_device_records(self.h, algo, _ptr(d_stream), n, hist_valid, pos_base, min_len,
+                                                          _ptr(d_out), _ptr(d_records), cap, C.byref(cnt), cuda_stream),
+                    "pm_engine_scan_device_records")
+        return cnt.value
 
     def scan_host(self, buf, algo=ALGO_SFX, out=None):
         a = _u8(buf)

@@ -225,11 +225,89 @@ __global__ void __launch_bounds__(kCompactThreads) compact_write_kernel(const ui
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Compaction of the scan kernel's sparse-mode bitmap (sfx_scan.cu, kFlags): bit i set = position i holds a match that
+// qualifies.  Reads the bitmap (1 bit per position) and only the flagged entries of the dense result; deterministic and
+// position-sorted like the dense compaction above (count, single-CTA scan, scatter).
+// ------------------------------------------------------------------------------------------------
+constexpr int kBmThreads = 256;
+constexpr int kBmWords = 8;                                // words (of 32 positions) per thread
+constexpr int kBmChunkWords = kBmThreads * kBmWords;       // per CTA: 65,536 positions
+
+__global__ void __launch_bounds__(kBmThreads) bitmap_count_kernel(const uint32_t* __restrict__ flags, uint64_t n_words,
+                                                                   unsigned long long* __restrict__ block_counts) {
+    const uint64_t w0 = uint64_t(blockIdx.x) * kBmChunkWords + uint64_t(threadIdx.x) * kBmWords;
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < kBmWords; ++k) if (w0 + k < n_words) c += __popc(__ldg(flags + w0 + k));
+    __shared__ uint32_t sh[kBmThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int w = 0; w < kBmThreads / 32; ++w) s += sh[w];
+        block_counts[blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kBmThreads) bitmap_write_kernel(const uint32_t* __restrict__ flags, uint64_t n_words,
+                                                                   const uint16_t* __restrict__ out, uint64_t pos_base,
+                                                                   const unsigned long long* __restrict__ block_offs,
+                                                                   unsigned long long* __restrict__ recs, uint64_t cap) {
+    const uint64_t w0 = uint64_t(blockIdx.x) * kBmChunkWords + uint64_t(threadIdx.x) * kBmWords;
+    uint32_t word[kBmWords], c = 0;
+#pragma unroll
+    for (int k = 0; k < kBmWords; ++k) {
+        word[k] = (w0 + k < n_words) ? __ldg(flags + w0 + k) : 0u;
+        c += __popc(word[k]);
+    }
+    __shared__ uint32_t sh[kBmThreads / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) sh[wid] = x;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < wid; ++w) woff += sh[w];
+    uint64_t dst = block_offs[blockIdx.x] + woff + x - c;
+#pragma unroll
+    for (int k = 0; k < kBmWords; ++k) {
+        uint32_t m = word[k];
+        while (m) {
+            const uint32_t b = __ffs(m) - 1;
+            m &= m - 1;
+            const uint64_t i = (w0 + k) * 32 + b;
+            if (dst < cap) recs[dst] = ((pos_base + i) << 24) | out[i];
+            ++dst;
+        }
+    }
+}
+
 }  // namespace
+
+size_t bitmap_blocks(uint64_t n) { return size_t(((n + 31) / 32 + kBmChunkWords - 1) / kBmChunkWords); }
+
+cudaError_t compact_bitmap_launch(const uint32_t* flags, const uint16_t* out, uint64_t n, uint64_t pos_base,
+                                  unsigned long long* d_block_counts, unsigned long long* d_total, unsigned long long* recs,
+                                  uint64_t cap, cudaStream_t st, uint64_t* launches) {
+    const uint64_t n_words = (n + 31) / 32, nb = bitmap_blocks(n);
+    if (nb == 0) return cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st);
+    bitmap_count_kernel<<<uint32_t(nb), kBmThreads, 0, st>>>(flags, n_words, d_block_counts);
+    compact_scan_kernel<<<1, 1024, 0, st>>>(d_block_counts, nb, d_total);
+    bitmap_write_kernel<<<uint32_t(nb), kBmThreads, 0, st>>>(flags, n_words, out, pos_base, d_block_counts, recs, cap);
+    *launches += 3;
+    return cudaGetLastError();
+}
 
 cudaError_t generate_launch(int kind, uint64_t off, uint64_t n, uint8_t* dst, const PatTables& t, cudaStream_t st,
                             uint64_t* launches) {
     if (n == 0) return cudaSuccess;
+    if (n > (uint64_t(1) << 34)) return cudaErrorInvalidValue;   // 16 GiB per call: the grids below are sized in 32 bits
     const uint32_t words = uint32_t((n + 7) / 8), blocks4k = uint32_t((n + 4095) / 4096);
     switch (kind) {
         case 0:

@@ -29,4 +29,11 @@ cudaError_t compact_launch(const uint16_t* out, uint64_t n, uint64_t pos_base, b
                            unsigned long long* d_block_counts, unsigned long long* d_total, unsigned long long* recs,
                            uint64_t cap, cudaStream_t st, uint64_t* launches);
 
+// sparse mode: compact the scan kernel's flag bitmap (bit i = position i qualifies) into position-sorted records
+// (pos_base + i) << 24 | out[i]; d_block_counts needs bitmap_blocks(n) + 1 entries
+size_t bitmap_blocks(uint64_t n);
+cudaError_t compact_bitmap_launch(const uint32_t* flags, const uint16_t* out, uint64_t n, uint64_t pos_base,
+                                  unsigned long long* d_block_counts, unsigned long long* d_total, unsigned long long* recs,
+                                  uint64_t cap, cudaStream_t st, uint64_t* launches);
+
 }  // namespace pm

@@ -279,8 +279,12 @@ int Dict::compile() {
     x.cont_base = cont_base;
     x.fits_u16 = (n2c < 65536) && (uint64_t(P) + 1 <= x.cont_base) && n_rows < (1u << 24);
 
+    // a FINAL entry of rows / root1 carries, above the 16-bit pid, the pattern's length (capped at 255) in bits 16-23:
+    // the scan kernel's sparse mode tests "length >= min_len" with one compare and no lookup; everything that stores a
+    // result keeps the low 16 bits only.  (root2 entries are u16: their patterns have at most 2 bytes.)
+    auto fin = [&](uint32_t pid) -> uint32_t { return pid ? pid | (std::min<uint32_t>(pats[pid - 1].len, 255u) << 16) : 0u; };
     auto entry_for_child = [&](uint32_t c) -> uint32_t {  // walk arrives at existing child c
-        if (!t.internal(c)) return best[c];
+        if (!t.internal(c)) return fin(best[c]);
         if (in_tail(c)) return kTailFlag | leaf_pid[c];
         return kContFlag | row_of[c];
     };
@@ -290,7 +294,7 @@ int Dict::compile() {
     for (uint32_t v = 1; v < t.n; ++v) {
         if (!t.internal(v) || in_tail(v)) continue;
         uint32_t* row = x.rows.data() + size_t(row_of[v]) * ncp;
-        for (uint32_t c = 0; c < ncp; ++c) row[c] = best[v];  // path dies here: answer is best(v)
+        for (uint32_t c = 0; c < ncp; ++c) row[c] = fin(best[v]);  // path dies here: answer is best(v)
         for (uint32_t k = t.off[v]; k < t.off[v + 1]; ++k) row[x.cls[t.byte[k]]] = entry_for_child(t.child[k]);
         x.row_best[row_of[v]] = best[v];
     }
@@ -520,7 +524,7 @@ void Dict::build_deep() const {
 // that concurrent ranks (one process per GPU) never see a half-written file; load() trusts nothing: it verifies the
 // checksum and every size / index bound the kernels rely on, and any mismatch means "compile instead".
 namespace {
-constexpr char kMagic[8] = {'P', 'M', 'B', '2', 'D', 'I', 'C', '3'};
+constexpr char kMagic[8] = {'P', 'M', 'B', '2', 'D', 'I', 'C', '4'};
 struct Hasher {
     uint64_t h = 1469598103934665603ull;
     void mix(const void* p, size_t n) {
@@ -609,7 +613,7 @@ int Dict::load(const char* path) {
     auto entry_ok = [&](uint32_t v) {
         if (v & kContFlag) return (v & 0xFFFFFFu) < sc.n_rows;
         if (v & kTailFlag) return (v & 0xFFFFu) >= 1 && (v & 0xFFFFu) <= P;
-        return v <= P;
+        return (v & 0xFFFFu) <= P && (v >> 24) == 0 && ((v >> 16) == 0) == ((v & 0xFFFFu) == 0);
     };
     for (size_t i = 0; ok && i < sfx.rows.size(); ++i) ok = entry_ok(sfx.rows[i]);
     for (size_t i = 0; ok && i < sfx.root1.size(); ++i) ok = entry_ok(sfx.root1[i]);

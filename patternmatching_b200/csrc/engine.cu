@@ -64,7 +64,7 @@ struct EngineOpts {
     bool sfx_no_tex = false, sfx_no_l3 = false, dfa_no_fb = false, dfa_flat = false, dfa_deep = false, dfa_no_fused = false;
     uint32_t l3_min = 4, l3_min_b = 4;
     size_t host_chunk = size_t(16) << 20;  // bytes per pipeline slot for pinned buffers (PM_HOST_CHUNK_MIB)
-    int host_threads = 0;                  // staging threads (PM_HOST_THREADS; default: the host's cores, at most 16)
+    int host_threads = 0;                  // staging threads (PM_HOST_THREADS; default: half the host's cores, at most 16)
     static EngineOpts from_env() {
         EngineOpts o;
         o.sfx_no_tex = getenv("PM_SFX_NO_TEX") != nullptr;
@@ -76,8 +76,10 @@ struct EngineOpts {
         if (const char* v = getenv("PM_SFX_L3_MIN")) o.l3_min = o.l3_min_b = uint32_t(atoi(v));
         if (const char* v = getenv("PM_SFX_L3_MIN_B")) o.l3_min_b = uint32_t(atoi(v));
         if (const char* v = getenv("PM_HOST_CHUNK_MIB")) { const long m = atol(v); if (m >= 1 && m <= 1024) o.host_chunk = size_t(m) << 20; }
+        // half of the host's cores (at most 16): on the 16-vCPU B200 box 8 staging threads gave the best host-path
+        // numbers, 16 (one per core, competing with the CUDA driver's own threads and the caller) were slower
         const unsigned hw = std::thread::hardware_concurrency();
-        o.host_threads = int(std::min<unsigned>(hw ? hw : 1, 16));
+        o.host_threads = int(std::max(1u, std::min<unsigned>((hw ? hw : 2) / 2, 16)));
         if (const char* v = getenv("PM_HOST_THREADS")) { const int t = atoi(v); if (t >= 1 && t <= 256) o.host_threads = t; }
         return o;
     }
@@ -126,6 +128,8 @@ struct pm_engine {
     unsigned long long* d_acc = nullptr;  // 8 x u64
     unsigned long long* d_compact_counts = nullptr;  // per-CTA counts of pm_engine_compact, grown on demand
     size_t compact_cap = 0;
+    uint32_t* d_flags = nullptr;          // sparse mode: one bit per position (pm_engine_scan_device_records), grown on demand
+    size_t flags_words = 0;
     // deferred-walk queues of the sfx scan, one per pipeline slot (slot 0 also serves pm_engine_scan_device)
     uint64_t* d_queue[2] = {nullptr, nullptr};
     uint32_t* d_qcount = nullptr;         // 2 x 2 x kMaxCtas counters
@@ -156,6 +160,7 @@ struct pm_engine {
     uint64_t* d_rec[2] = {nullptr, nullptr};
     unsigned long long* d_rec_counts[2] = {nullptr, nullptr};
     unsigned long long* h_rec_total[2] = {nullptr, nullptr};
+    uint32_t* d_rec_flags[2] = {nullptr, nullptr};   // sparse-mode bitmaps of the two pipeline slots
     // stream state carried between host calls (== ac->current_state of the reference): the last `halo` bytes, right-aligned
     std::vector<uint8_t> h_hist;
     size_t hist_valid = 0;
@@ -269,23 +274,26 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
 // whose work per byte is constant.  Synchronises `st` (one small D2H copy).
 constexpr size_t kSampleWin = size_t(256) << 10;
 int choose_algo(pm_engine* e, const uint8_t* d_stream, size_t n, size_t hist_valid, cudaStream_t st, int slot) {
-    if (n < 4 * kSampleWin) { e->auto_flat = false; return PM_ALGO_SFX; }
+    // four windows of 256 KiB; a shorter input (the host pipeline's pieces) is sampled whole, below 64 KiB not at all
+    const size_t win = std::min(kSampleWin, n & ~size_t(4095));
+    const int n_win = n >= 4 * kSampleWin ? 4 : 1;
+    if (win < (size_t(64) << 10)) { e->auto_flat = false; return PM_ALGO_SFX; }
     if (!e->d_sample_out) {
         CU(cudaMalloc(reinterpret_cast<void**>(&e->d_sample_out), kSampleWin * sizeof(uint16_t)));
         e->scratch_bytes += kSampleWin * sizeof(uint16_t);
     }
     uint64_t deferred = 0;
     std::vector<uint32_t> counts(2 * kMaxCtas);
-    for (int w = 0; w < 4; ++w) {
+    for (int w = 0; w < n_win; ++w) {
         const size_t off = (n / 4 * size_t(w)) & ~size_t(4095);
-        if (scan_device_impl(e, PM_ALGO_SFX, d_stream + off, kSampleWin, std::min<size_t>(off + hist_valid, e->halo),
+        if (scan_device_impl(e, PM_ALGO_SFX, d_stream + off, win, std::min<size_t>(off + hist_valid, e->halo),
                              e->d_sample_out, st, slot)) return -1;
-        const size_t ctas = pm::sfx_scan_ctas(kSampleWin, e->n_sms);
+        const size_t ctas = pm::sfx_scan_ctas(win, e->n_sms);
         CU(cudaMemcpyAsync(counts.data(), e->d_qcount + size_t(slot) * 2 * kMaxCtas, 2 * ctas * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         for (size_t i = 0; i < 2 * ctas; ++i) deferred += counts[i];
     }
-    const bool deep = deferred * 32 > 4 * kSampleWin;     // more than 1/32 of the positions walk past level 4
+    const bool deep = deferred * 32 > size_t(n_win) * win;     // more than 1/32 of the positions walk past level 4
     if (!deep) { e->auto_flat = false; return PM_ALGO_SFX; }
     const pm::Dict& d = *e->dict;
     d.build_deep();   // cheap (no dense table): gives the forward trie's states per depth
@@ -380,6 +388,17 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
     return fail("unknown algorithm id");
 }
 
+int ensure_compact_counts(pm_engine* e, size_t need) {
+    if (need <= e->compact_cap) return 0;   // pooled: grows to the largest request seen and stays
+    if (e->d_compact_counts) CU(cudaFree(e->d_compact_counts));
+    e->scratch_bytes -= e->compact_cap * sizeof(unsigned long long);
+    e->d_compact_counts = nullptr; e->compact_cap = 0;
+    CU(cudaMalloc(reinterpret_cast<void**>(&e->d_compact_counts), need * sizeof(unsigned long long)));
+    e->compact_cap = need;
+    e->scratch_bytes += need * sizeof(unsigned long long);
+    return 0;
+}
+
 // ---- host-buffer pipeline -------------------------------------------------------------------------------------
 
 // what a host scan hands back for every position
@@ -401,8 +420,9 @@ void carry_history(pm_engine* e, const uint8_t* stream, size_t n) {
     e->hist_valid += n;
 }
 
-// Small calls: stage [history | bytes] in pinned memory, ONE H2D copy, ONE kernel, one D2H copy, one stream synchronise
-// (results written by the kernel straight into mapped pinned memory were slower: 2-byte posted writes over PCIe).  Taken for PM_ALGO_SFX / PM_ALGO_AUTO (the walker is the backward
+// Small calls: stage [history | bytes] in pinned memory, ONE H2D copy, ONE kernel that writes its results straight
+// into mapped pinned memory, one stream synchronise (measured on the B200 box: 63 us per 100 KiB call, 14 us per
+// read_char; with a D2H copy of the results instead of mapped stores: 77 us / 18 us).  Taken for PM_ALGO_SFX / PM_ALGO_AUTO (the walker is the backward
 // scan's own bounded walk); an explicitly requested DFA or KR scan runs its own kernels whatever the size.
 int scan_host_small(pm_engine* e, const uint8_t* stream, size_t n, const HostSink& sink) {
     const size_t H = e->halo;
@@ -412,11 +432,10 @@ int scan_host_small(pm_engine* e, const uint8_t* stream, size_t n, const HostSin
     memcpy(h + H, stream, n);
     CU(cudaMemcpyAsync(e->d_in[0] + H - hv, h + H - hv, hv + n, cudaMemcpyHostToDevice, e->st[0]));
     pm::SfxParams p{};
-    p.stream = e->d_in[0] + H; p.n = n; p.hist_valid = hv; p.out = e->d_out[0];
+    p.stream = e->d_in[0] + H; p.n = n; p.hist_valid = hv; p.out = e->h_out[0];  // pinned host memory is device-addressable (UVA)
     if (fill_sfx_params(e, &p, n, 0)) return -1;
     cudaError_t ce = pm::sfx_walk_launch(p, e->st[0], &e->launches);
     if (ce != cudaSuccess) return cuda_fail(ce, "sfx_walk_launch");
-    CU(cudaMemcpyAsync(e->h_out[0], e->d_out[0], n * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->st[0]));
     CU(cudaStreamSynchronize(e->st[0]));
     if (sink.out16) memcpy(sink.out16, e->h_out[0], n * sizeof(uint16_t));
     else pm::HostPool::expand_range(e->h_out[0], 0, n, sink.table, sink.out64);
@@ -434,7 +453,6 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
         carry_history(e, stream, n);
         return 0;
     }
-    if (algo == PM_ALGO_AUTO && e->auto_choice < 0 && n < 4 * kSampleWin) algo = PM_ALGO_SFX;  // too short to sample
     const size_t H = e->halo;
     const bool in_pinned = is_pinned(stream);
     const bool direct_out = sink.out16 && is_pinned(sink.out16);   // the D2H copy lands in the caller's buffer
@@ -693,7 +711,7 @@ void pm_engine_free(pm_engine* e) {
     if (e->rows_tex) cudaDestroyTextureObject(e->rows_tex);
     void* ptrs[] = {e->d_root2, e->d_root1, e->d_rows, e->d_row_best, e->d_cls, e->d_pat_off, e->d_pat_len, e->d_pat_bytes,
                     e->d_parent, e->d_chain, e->d_pidhash, e->d_tail_rec, e->d_l3f, e->d_anc_off, e->d_anc_list, e->d_sample_out, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_fb_meta, e->d_deep_hot, e->d_deep_long, e->d_deep_recs, e->d_deep_dense, e->d_acc,
-                    e->d_compact_counts, e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1], e->d_queue[0], e->d_queue[1], e->d_qcount};
+                    e->d_compact_counts, e->d_flags, e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1], e->d_queue[0], e->d_queue[1], e->d_qcount};
     for (void* p : ptrs) if (p) cudaFree(p);
     pm::kr_free_tables(&e->kr);
     for (cudaEvent_t x : e->prof_events) cudaEventDestroy(x);
@@ -701,6 +719,7 @@ void pm_engine_free(pm_engine* e) {
     for (int b = 0; b < 2; ++b) {
         if (e->d_rec[b]) cudaFree(e->d_rec[b]);
         if (e->d_rec_counts[b]) cudaFree(e->d_rec_counts[b]);
+        if (e->d_rec_flags[b]) cudaFree(e->d_rec_flags[b]);
         if (e->h_rec_total[b]) cudaFreeHost(e->h_rec_total[b]);
         if (e->h_in[b]) cudaFreeHost(e->h_in[b]);
         if (e->h_out[b]) cudaFreeHost(e->h_out[b]);
@@ -798,14 +817,15 @@ int pm_engine_scan_host_records(pm_engine* e, int algo, const uint8_t* stream, s
     if (ensure_pipe(e)) return -1;
     if (algo == PM_ALGO_DFA && ensure_dfa(e)) return -1;
     if (algo == PM_ALGO_KR && ensure_kr(e)) return -1;
-    if (algo == PM_ALGO_AUTO && e->auto_choice < 0 && n < 4 * kSampleWin) algo = PM_ALGO_SFX;
     const size_t chunk = e->opts.host_chunk, H = e->halo;
     const size_t blocks = pm::compact_blocks(chunk) + 1;
     for (int b = 0; b < 2; ++b) {   // each piece is checked on its own: a failed allocation leaves the others usable next time
         if (!e->d_rec[b]) CU(cudaMalloc(reinterpret_cast<void**>(&e->d_rec[b]), chunk * sizeof(uint64_t)));
         if (!e->d_rec_counts[b]) CU(cudaMalloc(reinterpret_cast<void**>(&e->d_rec_counts[b]), (blocks + 1) * sizeof(unsigned long long)));
         if (!e->h_rec_total[b]) CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_rec_total[b]), sizeof(unsigned long long)));
+        if (!e->d_rec_flags[b]) CU(cudaMalloc(reinterpret_cast<void**>(&e->d_rec_flags[b]), (chunk / 32 + 16) * 4));
     }
+    const bool fused = algo == PM_ALGO_SFX && min_len >= 3;   // the scan kernel marks the qualifying positions itself
     const bool in_pinned = is_pinned(stream);
     const size_t n_chunks = (n + chunk - 1) / chunk;
     uint64_t produced = 0;
@@ -834,10 +854,23 @@ int pm_engine_scan_host_records(pm_engine* e, int algo, const uint8_t* stream, s
             src = e->h_in[b];
         }
         CU(cudaMemcpyAsync(din + H - from_call, src, from_call + len, cudaMemcpyHostToDevice, e->st[b]));
-        if (scan_device_impl(e, algo, din + H, len, hist_total, e->d_out[b], e->st[b], b)) return -1;
-        cudaError_t ce = pm::compact_launch(e->d_out[b], len, e->hist_valid + o, false, min_len, e->pt, e->d_rec_counts[b],
-                                            e->d_rec_counts[b] + blocks, reinterpret_cast<unsigned long long*>(e->d_rec[b]),
-                                            chunk, e->st[b], &e->launches);
+        cudaError_t ce;
+        if (fused) {
+            pm::SfxParams p{};
+            p.stream = din + H; p.n = len; p.hist_valid = hist_total; p.out = e->d_out[b];
+            if (fill_sfx_params(e, &p, len, b)) return -1;
+            p.flags = reinterpret_cast<uint8_t*>(e->d_rec_flags[b]); p.min_len = min_len;
+            ce = pm::sfx_scan_launch(p, e->dict->sfx.cls_identity, e->n_sms, e->dict->max_len, e->st[b], &e->launches);
+            if (ce == cudaSuccess)
+                ce = pm::compact_bitmap_launch(e->d_rec_flags[b], e->d_out[b], len, e->hist_valid + o, e->d_rec_counts[b],
+                                               e->d_rec_counts[b] + blocks, reinterpret_cast<unsigned long long*>(e->d_rec[b]),
+                                               chunk, e->st[b], &e->launches);
+        } else {
+            if (scan_device_impl(e, algo, din + H, len, hist_total, e->d_out[b], e->st[b], b)) return -1;
+            ce = pm::compact_launch(e->d_out[b], len, e->hist_valid + o, false, min_len, e->pt, e->d_rec_counts[b],
+                                    e->d_rec_counts[b] + blocks, reinterpret_cast<unsigned long long*>(e->d_rec[b]),
+                                    chunk, e->st[b], &e->launches);
+        }
         if (ce != cudaSuccess) return cuda_fail(ce, "compact_launch");
         CU(cudaMemcpyAsync(e->h_rec_total[b], e->d_rec_counts[b] + blocks, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->st[b]));
         CU(cudaEventRecord(e->done[b], e->st[b]));
@@ -872,21 +905,65 @@ int pm_engine_compact(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t po
     std::lock_guard<std::mutex> lock(e->mu);
     CU(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    const size_t need = pm::compact_blocks(n) + 1;
-    if (need > e->compact_cap) {   // pooled: grows to the largest n seen and stays
-        if (e->d_compact_counts) CU(cudaFree(e->d_compact_counts));
-        e->scratch_bytes -= e->compact_cap * sizeof(unsigned long long);
-        e->d_compact_counts = nullptr; e->compact_cap = 0;
-        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_compact_counts), need * sizeof(unsigned long long)));
-        e->compact_cap = need;
-        e->scratch_bytes += need * sizeof(unsigned long long);
-    }
+    if (ensure_compact_counts(e, pm::compact_blocks(n) + 1)) return -1;
     cudaError_t ce = pm::compact_launch(d_out, n, pos_base, expand_ancestors != 0, 1, e->pt, e->d_compact_counts, e->d_acc + 4,
                                         reinterpret_cast<unsigned long long*>(d_records), cap, st, &e->launches);
     unsigned long long total = 0;
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(&total, e->d_acc + 4, sizeof(total), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
     if (ce != cudaSuccess) return cuda_fail(ce, "compact");
+    *n_records = total;
+    return 0;
+}
+
+int pm_engine_scan_device_records(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid,
+                                  uint64_t pos_base, uint32_t min_len, uint16_t* d_out, uint64_t* d_records, size_t cap,
+                                  uint64_t* n_records, void* cuda_stream) {
+    std::lock_guard<std::mutex> lock(e->mu);
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if (n == 0) { *n_records = 0; return 0; }
+    if ((reinterpret_cast<uintptr_t>(d_stream) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
+        return fail("pm_engine_scan_device_records: d_stream and d_out must be 16-byte aligned");
+    if (e->scratch_used) CU(cudaStreamWaitEvent(st, e->scratch_free, 0));
+    const bool fused = algo == PM_ALGO_SFX && min_len >= 3;
+    int rc = 0;
+    unsigned long long total = 0;
+    cudaError_t ce = cudaSuccess;
+    if (fused) {
+        // the scan kernel itself marks the qualifying positions (one bit each); the compaction reads that bitmap and
+        // only the flagged entries of the dense result
+        const size_t words = (n + 31) / 32 + 16;
+        if (words > e->flags_words) {
+            if (e->d_flags) CU(cudaFree(e->d_flags));
+            e->scratch_bytes -= e->flags_words * 4;
+            e->d_flags = nullptr; e->flags_words = 0;
+            CU(cudaMalloc(reinterpret_cast<void**>(&e->d_flags), words * 4));
+            e->flags_words = words;
+            e->scratch_bytes += words * 4;
+        }
+        if (ensure_compact_counts(e, pm::bitmap_blocks(n) + 1)) return -1;
+        pm::SfxParams p{};
+        p.stream = d_stream; p.n = n; p.hist_valid = hist_valid; p.out = d_out;
+        if (fill_sfx_params(e, &p, n, 0)) return -1;
+        p.flags = reinterpret_cast<uint8_t*>(e->d_flags); p.min_len = min_len;
+        ce = pm::sfx_scan_launch(p, e->dict->sfx.cls_identity, e->n_sms, e->dict->max_len, st, &e->launches);
+        if (ce == cudaSuccess)
+            ce = pm::compact_bitmap_launch(e->d_flags, d_out, n, pos_base, e->d_compact_counts, e->d_acc + 4,
+                                           reinterpret_cast<unsigned long long*>(d_records), cap, st, &e->launches);
+    } else {
+        if (ensure_compact_counts(e, pm::compact_blocks(n) + 1)) return -1;
+        rc = scan_device_impl(e, algo, d_stream, n, hist_valid, d_out, st);
+        if (rc == 0)
+            ce = pm::compact_launch(d_out, n, pos_base, false, min_len ? min_len : 1, e->pt, e->d_compact_counts, e->d_acc + 4,
+                                    reinterpret_cast<unsigned long long*>(d_records), cap, st, &e->launches);
+    }
+    if (rc == 0 && ce == cudaSuccess) ce = cudaMemcpyAsync(&total, e->d_acc + 4, sizeof(total), cudaMemcpyDeviceToHost, st);
+    if (rc == 0 && ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaEventRecord(e->scratch_free, st);
+    e->scratch_used = true;
+    if (rc) return rc;
+    if (ce != cudaSuccess) return cuda_fail(ce, "pm_engine_scan_device_records");
     *n_records = total;
     return 0;
 }

@@ -19,6 +19,8 @@
 // positions per visit, arranged so that the 16-byte result stores of a warp are fully coalesced, and
 // gets its stream bytes with two 8-byte loads issued one visit ahead.  Kernels: sfx_scan_kernel (levels
 // 1-4, every position), sfx_deep_kernel (the parked walks), sfx_edge_kernel (the ragged ends).
+#include <type_traits>
+
 #include "pm_dev.cuh"
 #include "sfx_scan.cuh"
 
@@ -108,6 +110,23 @@ __device__ __noinline__ uint32_t sfx_finish(const SfxParams& p, uint32_t v, uint
         return cand;
     }
     return v;
+}
+
+// sparse mode: is the longest match `pid` a pattern of at least min_len bytes?  (rare paths only: deferred walks, edges)
+__device__ __forceinline__ bool is_long(const SfxParams& p, uint32_t pid) {
+    pid &= 0xFFFFu;
+    return pid != 0 && __ldg(p.pat_len + pid - 1) >= p.min_len;
+}
+__device__ __forceinline__ void flag_set(const SfxParams& p, uint64_t pos, bool on) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(p.flags) + (pos >> 5);
+    const uint32_t bit = 1u << (pos & 31);
+    if (on) atomicOr(w, bit); else atomicAnd(w, ~bit);
+}
+
+// a deferred walk's result: dense slot, and in sparse mode its flag bit (the scan kernel left it clear)
+__device__ __forceinline__ void put_result(const SfxParams& p, uint64_t pos, uint32_t pid) {
+    p.out[pos] = uint16_t(pid);
+    if (p.flags != nullptr && is_long(p, pid)) flag_set(p, pos, true);
 }
 
 // Where the main kernel finds its tables.  The 2-byte root table sits in shared memory (LSU pipe); the rows of
@@ -238,7 +257,11 @@ __device__ __forceinline__ uint32_t ldg_stream4(const uint8_t* ptr) {
 // stream bytes go from global memory straight into registers, one visit ahead of their use: staging them in shared
 // memory (bulk async copies into a per-warp double buffer, the first design of round 1) made every byte cross the
 // LSU data pipe this kernel is bound by a second time, and cost ~56 warp instructions of bookkeeping per tile.
-template <bool kIdentCls, bool kTex>
+// kFlags: sparse mode -- besides the dense result, one bit per position: "the longest match has >= min_len bytes".
+// A final entry of levels 3/4 carries the pattern length above the pid (dict.cpp), so the test is one compare; entries
+// that ended in the 2-byte root table are patterns of <= 2 bytes and never qualify (min_len >= 3); deferred walks set
+// their bit when they are finished.  A lane packs its 8 bits into one byte: 32 coalesced bytes per group and warp.
+template <bool kIdentCls, bool kTex, bool kFlags>
 __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint16_t* s_root2 = reinterpret_cast<uint16_t*>(smem + kOffRoot2);
@@ -344,7 +367,8 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
                             q_strip[slot] = (pos << 25) | (tail ? (4u << 16) | (ea[j] & 0xFFFFu) : (ea[j] & 0xFFFFFFu));
                             ea[j] = 0;  // placeholder; sfx_deep_kernel writes the result
                         } else {
-                            ea[j] = sfx_finish(p, ea[j], 4, p.stream + pos, pos + p.hist_valid + 1);
+                            ea[j] = sfx_finish(p, ea[j], 4, p.stream + pos, pos + p.hist_valid + 1) & 0xFFFFu;
+                            if constexpr (kFlags) { if (is_long(p, ea[j])) ea[j] |= 255u << 16; }
                         }
                     }
                 }
@@ -358,7 +382,8 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
                             q_strip[slot] = (pos << 25) | (tail ? (4u << 16) | (eb[j] & 0xFFFFu) : (eb[j] & 0xFFFFFFu));
                             eb[j] = 0;
                         } else {
-                            eb[j] = sfx_finish(p, eb[j], 4, p.stream + pos, pos + p.hist_valid + 1);
+                            eb[j] = sfx_finish(p, eb[j], 4, p.stream + pos, pos + p.hist_valid + 1) & 0xFFFFu;
+                            if constexpr (kFlags) { if (is_long(p, eb[j])) eb[j] |= 255u << 16; }
                         }
                     }
                 }
@@ -366,6 +391,18 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
         }
         store_group(out_ptr, 0, ea);
         store_group(out_ptr, 256, eb);
+        if constexpr (kFlags) {
+            const uint32_t thr = p.min_len << 16;   // entry = length << 16 | pid for finals of levels 3/4, 0 for parked walks
+            uint32_t fa = 0, fb = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (ea[j] >= thr) fa |= 1u << j;
+                if (eb[j] >= thr) fb |= 1u << j;
+            }
+            uint8_t* fp = p.flags + (s0 >> 3) + lane;
+            fp[0] = uint8_t(fa);
+            fp[32] = uint8_t(fb);
+        }
         out_ptr += step;
     }
     __syncthreads();  // every warp of the CTA has finished its visits
@@ -456,10 +493,10 @@ __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
                     if (v[s] & kTail) {  // hand over to phase B
                         const uint32_t t = atomicAdd(&s_tails, 1u);
                         if (t < cap_tails) q_strip[p.q_per_cta - 1 - t] = (pos[s] << 25) | (uint32_t(k[s]) << 16) | (v[s] & 0xFFFFu);
-                        else p.out[pos[s]] = uint16_t(sfx_finish(p, v[s], k[s], p.stream + pos[s], avail));  // strip full
+                        else put_result(p, pos[s], sfx_finish(p, v[s], k[s], p.stream + pos[s], avail));  // strip full
                         st[s] = kIdle;
                     } else if (!(v[s] & kCont)) {
-                        p.out[pos[s]] = uint16_t(v[s]);
+                        put_result(p, pos[s], v[s]);
                         st[s] = kIdle;
                     } else if (hist_left[s] == 0) {
                         st[s] = kHist;
@@ -467,7 +504,7 @@ __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
                 }
                 // the walk needs a byte that does not exist (start of the stream): the row's own best pattern
                 if ((st[s] == kHist || st[s] == kRow) && k[s] >= avail) {
-                    p.out[pos[s]] = uint16_t(__ldg(p.row_best + (v[s] & 0xFFFFFFu)));
+                    put_result(p, pos[s], __ldg(p.row_best + (v[s] & 0xFFFFFFu)));
                     st[s] = kIdle;
                 }
             }
@@ -531,23 +568,23 @@ __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
                     const uint32_t left = lim[s] - k[s];
                     k[s] += same < left ? same : left;
                     if (same < 8 || k[s] >= lim[s]) {
-                        if (k[s] < next_term[s]) { p.out[pos[s]] = uint16_t(best_start[s]); st[s] = kIdle; }       // no further terminal reached
-                        else if (k[s] >= len[s]) { p.out[pos[s]] = uint16_t(pid[s]); st[s] = kIdle; }              // the whole pattern
+                        if (k[s] < next_term[s]) { put_result(p, pos[s], best_start[s]); st[s] = kIdle; }       // no further terminal reached
+                        else if (k[s] >= len[s]) { put_result(p, pos[s], pid[s]); st[s] = kIdle; }              // the whole pattern
                         else st[s] = kChain;   // the longest pattern of the chain with length <= k
                     }
                 } else if (st[s] == kChain) {
                     if (ld_len[s] > k[s]) {
                         pid[s] = ld_par[s];
-                        if (pid[s] == 0) { p.out[pos[s]] = 0; st[s] = kIdle; }
+                        if (pid[s] == 0) { put_result(p, pos[s], 0); st[s] = kIdle; }
                     } else {
-                        p.out[pos[s]] = uint16_t(pid[s]);
+                        put_result(p, pos[s], pid[s]);
                         st[s] = kIdle;
                     }
                 }
                 // a tail item that cannot advance at all (k already at its limit) is resolved by the same rules
                 if (st[s] == kCmp && k[s] >= lim[s]) {
-                    if (k[s] < next_term[s]) { p.out[pos[s]] = uint16_t(best_start[s]); st[s] = kIdle; }
-                    else if (k[s] >= len[s]) { p.out[pos[s]] = uint16_t(pid[s]); st[s] = kIdle; }
+                    if (k[s] < next_term[s]) { put_result(p, pos[s], best_start[s]); st[s] = kIdle; }
+                    else if (k[s] >= len[s]) { put_result(p, pos[s], pid[s]); st[s] = kIdle; }
                     else st[s] = kChain;
                 }
             }
@@ -563,7 +600,9 @@ __global__ void sfx_edge_kernel(const SfxParams p, uint32_t head, uint32_t tail)
     if (t >= head + tail) return;
     const uint64_t i = t < head ? uint64_t(t) : p.n - tail + (t - head);
     const uint64_t avail = i + p.hist_valid + 1;
-    p.out[i] = uint16_t(sfx_finish(p, p.root1[p.stream[i]], 1, p.stream + i, avail));
+    const uint32_t pid = sfx_finish(p, p.root1[p.stream[i]], 1, p.stream + i, avail) & 0xFFFFu;
+    p.out[i] = uint16_t(pid);
+    if (p.flags != nullptr) flag_set(p, i, is_long(p, pid));   // these positions are redone (head) or not covered (tail) by the scan kernel
 }
 
 }  // namespace
@@ -583,12 +622,24 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
     p.n_tiles = p.n / kTile;
     if (p.n_l3 > kSfxMaxL3) p.l3f = nullptr;  // the filter does not fit beside root2: plain L2 lookups only
     const bool tex = p.rows_tex != 0;
-    auto kern = ident_cls ? (tex ? sfx_scan_kernel<true, true> : sfx_scan_kernel<true, false>)
-                          : (tex ? sfx_scan_kernel<false, true> : sfx_scan_kernel<false, false>);
+    if (p.flags != nullptr && p.min_len < 3) return cudaErrorInvalidValue;   // sparse mode: patterns of >= 3 bytes only
+    auto pick = [&](auto flags_tag) {
+        constexpr bool F = decltype(flags_tag)::value;
+        return ident_cls ? (tex ? sfx_scan_kernel<true, true, F> : sfx_scan_kernel<true, false, F>)
+                         : (tex ? sfx_scan_kernel<false, true, F> : sfx_scan_kernel<false, false, F>);
+    };
+    auto kern = p.flags != nullptr ? pick(std::true_type{}) : pick(std::false_type{});
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
     const uint32_t grid = uint32_t(sfx_scan_ctas(p.n, n_sms));
     if (ev) cudaEventRecord(ev[0], st);
+    if (p.flags != nullptr) {   // the flag words the scan kernel does not write: those of the ragged end (or all, without a full visit)
+        const uint64_t first = (p.n / kTile) * (kTile / 32), last = (p.n + 31) / 32;
+        if (last > first) {
+            e = cudaMemsetAsync(reinterpret_cast<uint32_t*>(p.flags) + first, 0, (last - first) * 4, st);
+            if (e != cudaSuccess) return e;
+        }
+    }
     if (p.n_tiles > 0) {
         // shared memory actually needed (the rest of the 256 KB stays L1 / texture cache)
         const size_t smem = size_t(kOffL3) + (p.l3f ? size_t(p.n_l3) * 4 : 0) + 16;

@@ -33,6 +33,10 @@ struct SfxParams {
     uint32_t* qcount;         // [2 * grid] per CTA: "continue at row" items (front of the strip), "tail" items (back)
     uint32_t q_per_cta;       // strip length; a CTA that fills its strip finishes further walks inline
     uint64_t n_tiles;         // full visits (n / kSfxTile); filled by the launcher
+    // sparse mode (nullptr = off): bit i of this bitmap (bit i & 7 of byte i >> 3) is set iff the longest match at position i
+    // is a pattern of at least min_len (>= 3) bytes; ceil(n / 32) words, 4-byte aligned.  Compacted by compact_bitmap_launch.
+    uint8_t* flags;
+    uint32_t min_len;
 };
 
 size_t sfx_smem_bytes();

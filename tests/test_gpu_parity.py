@@ -543,3 +543,30 @@ def test_differential_fuzz_small():
         assert mod.main() == 0
     finally:
         sys.argv = argv
+
+
+@pytest.mark.parametrize("kind,n", [("planted", (3 << 20) + 100), ("almost", 300_001), ("ascii", 1 << 20), ("planted", 511), ("almost", 5000)])
+def test_sparse_mode_marks_matches_in_the_scan_kernel(kind, n, oracle_merged, engine_merged):
+    """pm_engine_scan_device_records: with PM_ALGO_SFX and min_len >= 3 the scan kernel writes one flag bit per position
+    (final row entries carry the pattern length; deferred walks and the ragged ends set their bits when they finish) and
+    the compaction reads only the bitmap and the flagged results; other settings take the dense compaction.  Both must
+    equal the oracle's longest matches filtered by pattern length, position-sorted, and leave the dense result intact."""
+    torch, dev = torch_dev()
+    stream = oracle_merged.gen(kind, 4096 * 9, ((n + 4095) // 4096) * 4096)[:n]
+    longest = oracle_merged.scan(stream)
+    lens = oracle_merged.lengths()
+    d_in = torch.from_numpy(stream).to(dev)
+    base = 7_000_000_000
+    for algo, min_len in ((pm.ALGO_SFX, 3), (pm.ALGO_SFX, 4), (pm.ALGO_SFX, 9), (pm.ALGO_SFX, 300), (pm.ALGO_SFX, 2), (pm.ALGO_DFA, 4)):
+        keep = np.nonzero((longest >= 0) & (lens[np.maximum(longest, 0)] >= min_len))[0]
+        want = ((keep.astype(np.uint64) + np.uint64(base)) << np.uint64(24)) | (longest[keep].astype(np.uint64) + np.uint64(1))
+        d_out = torch.zeros(max(n, 8), dtype=torch.int16, device=dev)
+        rec = torch.zeros(max(want.size, 1) + 5, dtype=torch.int64, device=dev)
+        cnt = engine_merged.scan_device_records(d_in, n, d_out, rec, rec.numel(), min_len=min_len, pos_base=base, algo=algo)
+        assert cnt == want.size, (algo, min_len, cnt, want.size)
+        assert np.array_equal(rec.cpu().numpy().view(np.uint64)[:cnt], want), (algo, min_len)
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint16)[:n], (longest + 1).astype(np.uint16))
+    # capacity smaller than the result: the count is still exact, nothing is written past cap
+    rec = torch.full((16,), -1, dtype=torch.int64, device=dev)
+    cnt = engine_merged.scan_device_records(d_in, n, d_out, rec, 8, min_len=3)
+    assert cnt >= 0 and bool((rec[8:] == -1).all().item())
