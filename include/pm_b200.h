@@ -169,6 +169,12 @@ void pm_engine_reset(pm_engine* e);
 int pm_engine_summarize(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t pos_base, uint64_t out4[4],
                         void* cuda_stream);
 
+/* replaces: measure_success_rate (Core/src/measure.c:174-190) on two dense results in device memory (both 16-byte
+ * aligned): d_algo is what a matcher reported, d_real what the reliable one reported.  counts4 = {success, partial success
+ * (the reported pattern is a PatternsTree ancestor of the real one), false negatives (nothing reported), false positives}.
+ * Synchronous. */
+int pm_engine_classify(pm_engine* e, const uint16_t* d_algo, const uint16_t* d_real, size_t n, uint64_t counts4[4], void* cuda_stream);
+
 /* Compact a dense result into position-sorted (pos, pid) records (pos = pos_base + i, 40 bits;
  * pid 24 bits; record = pos << 24 | pid), longest match per position; with expand_ancestors != 0
  * one record per match incl. PatternsTree ancestors (longest first).  d_records has capacity `cap`
@@ -211,6 +217,27 @@ void* pm_host_alloc(size_t bytes);
 void pm_host_free(void* p);
 /* number of kernel launches issued by this engine since creation (bench.py's gpu_launches) */
 uint64_t pm_engine_launch_count(const pm_engine* e);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU, the stream cut into contiguous shards that each read max_pat_len-1 bytes of history
+ * (hist_valid) -- no exchange step in the scan (Core/src/measure.c:262-306 keeps state across chunks, a
+ * warmed-up shard reports the same matches).  The only communication is the gather of the per-rank, position-sorted
+ * record lists to one rank, over NCCL (NVLink): all-gather of the counts, then grouped ncclSend / ncclRecv of the
+ * variable-length lists; rank order is position order, so the concatenation is sorted.  NCCL is dlopen'ed at first use
+ * (libnccl.so.2 of the process), the library has no link-time dependency on it.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pm_comm pm_comm;
+const char* pm_comm_last_error(void);
+/* rank 0 creates the 128-byte NCCL unique id and hands it to the other ranks by any means (bench.py: torch.distributed) */
+int pm_comm_unique_id(uint8_t id[128]);
+pm_comm* pm_comm_create(const uint8_t id[128], int rank, int world, int device);
+void pm_comm_free(pm_comm* c);
+/* Every rank passes its n_local sorted records (device memory).  On return counts[0..world) (host, may be NULL) holds every
+ * rank's count and *n_all their sum; on `root`, d_all (device, capacity `cap` records) receives the concatenation in rank
+ * order -- enqueued on cuda_stream: synchronise it (or record an event) before reading.  The call itself synchronises
+ * the stream once, after the all-gather of the counts (they size the receives). */
+int pm_comm_gather_records(pm_comm* c, const uint64_t* d_local, uint64_t n_local, uint64_t* d_all, uint64_t cap,
+                           uint64_t* counts, uint64_t* n_all, int root, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------------------------
  * The reference plugin surface (Core/src/mps.h:71-80) -- implemented in mps_gpu_shim.c on top of

@@ -91,6 +91,7 @@ def lib():
         "pm_engine_scan_host_records": (C.c_int, [vp, C.c_int, vp, sz, u32, vp, sz, C.POINTER(u64)]),
         "pm_engine_reset": (None, [vp]),
         "pm_engine_summarize": (C.c_int, [vp, vp, sz, u64, C.POINTER(u64), vp]),
+        "pm_engine_classify": (C.c_int, [vp, vp, vp, sz, C.POINTER(u64), vp]),
         "pm_engine_compact": (C.c_int, [vp, vp, sz, u64, C.c_int, vp, sz, C.POINTER(u64), vp]),
         "pm_engine_generate": (C.c_int, [vp, C.c_int, u64, sz, vp, vp]),
         "pm_engine_time_scan": (C.c_int, [vp, C.c_int, vp, sz, sz, vp, C.c_int, C.POINTER(C.c_float), vp]),
@@ -99,6 +100,11 @@ def lib():
         "pm_engine_read_profile": (C.c_int, [vp, C.POINTER(u32), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "pm_engine_last_deferred": (u64, [vp]),
         "pm_engine_auto_choice": (C.c_int, [vp]),
+        "pm_comm_last_error": (C.c_char_p, []),
+        "pm_comm_unique_id": (C.c_int, [vp]),
+        "pm_comm_create": (vp, [vp, C.c_int, C.c_int, C.c_int]),
+        "pm_comm_free": (None, [vp]),
+        "pm_comm_gather_records": (C.c_int, [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64), C.c_int, vp]),
         "pm_host_alloc": (vp, [sz]),
         "pm_host_free": (None, [vp]),
         "gpu_create": (vp, []), "gpu_dfa_create": (vp, []), "gpu_kr_create": (vp, []),
@@ -365,6 +371,12 @@ class Engine:
         self._check(self.L.pm_engine_summarize(self.h, _ptr(d_out), n, pos_base, o, cuda_stream), "pm_engine_summarize")
         return dict(positions=o[0], matches=o[1], hsum_longest=o[2], hsum_all=o[3])
 
+    def classify(self, d_algo, d_real, n, cuda_stream=0):
+        """measure_success_rate (measure.c:174-190) on the device: counts of success / partial / false_neg / false_pos."""
+        o = (C.c_uint64 * 4)()
+        self._check(self.L.pm_engine_classify(self.h, _ptr(d_algo), _ptr(d_real), n, o, cuda_stream), "pm_engine_classify")
+        return dict(success=o[0], partial=o[1], false_neg=o[2], false_pos=o[3])
+
     def compact(self, d_out, n, d_records, cap, pos_base=0, expand_ancestors=False, cuda_stream=0):
         cnt = C.c_uint64()
         self._check(self.L.pm_engine_compact(self.h, _ptr(d_out), n, pos_base, int(expand_ancestors), _ptr(d_records), cap,
@@ -397,6 +409,52 @@ class Engine:
         self._check(self.L.pm_engine_time_scan(self.h, algo, _ptr(d_stream), n, hist_valid, _ptr(d_out), iters,
                                                C.byref(ms), cuda_stream), "pm_engine_time_scan")
         return ms.value
+
+
+class Comm:
+    """The library's NCCL communicator for the record gather (include/pm_b200.h: pm_comm_*).  One per rank."""
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int):
+        self.L = lib()
+        self.rank, self.world = rank, world
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        self.h = self.L.pm_comm_create(buf, rank, world, device)
+        if not self.h:
+            raise PmError("pm_comm_create: " + self.L.pm_comm_last_error().decode(errors="replace"))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        L = lib()
+        buf = (C.c_ubyte * 128)()
+        if L.pm_comm_unique_id(buf) != 0:
+            raise PmError("pm_comm_unique_id: " + L.pm_comm_last_error().decode(errors="replace"))
+        return bytes(buf)
+
+    @classmethod
+    def from_torch(cls, dist, device_index):
+        """Create the communicator inside a torch.distributed job: rank 0's unique id is broadcast with torch."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+        t = torch.zeros(128, dtype=torch.uint8, device=torch.device("cuda", device_index))
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return cls(bytes(t.cpu().numpy().tobytes()), rank, world, device_index)
+
+    def gather_records(self, d_local, n_local, d_all, cap, root=0, cuda_stream=0):
+        """-> (per-rank counts, total); on `root` d_all holds the concatenation once cuda_stream has been synchronised."""
+        counts = (C.c_uint64 * self.world)()
+        total = C.c_uint64()
+        rc = self.L.pm_comm_gather_records(self.h, _ptr(d_local) if d_local is not None else None, n_local,
+                                           _ptr(d_all) if d_all is not None else None, cap, counts, C.byref(total), root, cuda_stream)
+        if rc != 0:
+            raise PmError("pm_comm_gather_records: " + self.L.pm_comm_last_error().decode(errors="replace"))
+        return list(counts), total.value
+
+    def free(self):
+        if self.h:
+            self.L.pm_comm_free(self.h)
+            self.h = None
 
 
 class PinnedBuffer:

@@ -114,6 +114,41 @@ __global__ void __launch_bounds__(256) summarize_kernel(const uint16_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// Success classification of one dense result against another (Core/src/measure.c:174-190 on pids): per position
+// equal -> success; the algorithm's answer is a PatternsTree ancestor of the real one -> partial success; the algorithm
+// reported nothing -> false negative; anything else -> false positive.  acc[0..3] = success, partial, false_neg, false_pos.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) classify_kernel(const uint16_t* __restrict__ algo, const uint16_t* __restrict__ real,
+                                                      uint64_t n, PatTables t, unsigned long long* __restrict__ acc) {
+    uint32_t cnt[4] = {0, 0, 0, 0};
+    auto one = [&](uint32_t a, uint32_t r) {
+        if (a == r) { ++cnt[0]; return; }
+        uint32_t c = r;
+        while (c && c != a) c = __ldg(t.parent + c);   // is_pattern_suffix(algo, real), PatternsTree.c:485-494
+        if (a && c == a) ++cnt[1];
+        else if (!a) ++cnt[2];
+        else ++cnt[3];
+    };
+    const uint64_t n8 = n / 8;
+    const uint4* a8 = reinterpret_cast<const uint4*>(algo);
+    const uint4* r8 = reinterpret_cast<const uint4*>(real);
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint4 a = __ldcs(a8 + i), r = __ldcs(r8 + i);
+        if (a.x == r.x && a.y == r.y && a.z == r.z && a.w == r.w) { cnt[0] += 8; continue; }
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) one((aw[k >> 1] >> (16 * (k & 1))) & 0xFFFF, (rw[k >> 1] >> (16 * (k & 1))) & 0xFFFF);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) one(algo[n8 * 8 + threadIdx.x], real[n8 * 8 + threadIdx.x]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t v = cnt[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&acc[k], (unsigned long long)v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Compaction: dense -> position-sorted records, deterministic (count, scan, scatter)
 // ------------------------------------------------------------------------------------------------
 constexpr int kCompactChunk = 2048;  // positions per CTA
@@ -344,6 +379,16 @@ cudaError_t summarize_launch(const uint16_t* out, uint64_t n, uint64_t pos_base,
     uint64_t want = (n / 8 + 255) / 256 + 1;
     const uint32_t grid = uint32_t(want < uint64_t(n_sms) * 8 ? want : uint64_t(n_sms) * 8);
     summarize_kernel<<<grid, 256, 0, st>>>(out, n, pos_base, t, d_acc4);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t classify_launch(const uint16_t* algo, const uint16_t* real, uint64_t n, const PatTables& t,
+                            unsigned long long* d_acc4, int n_sms, cudaStream_t st, uint64_t* launches) {
+    cudaError_t e = cudaMemsetAsync(d_acc4, 0, 4 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess || n == 0) return e;
+    const uint64_t want = (n / 8 + 255) / 256 + 1;
+    classify_kernel<<<uint32_t(want < uint64_t(n_sms) * 8 ? want : uint64_t(n_sms) * 8), 256, 0, st>>>(algo, real, n, t, d_acc4);
     ++*launches;
     return cudaGetLastError();
 }

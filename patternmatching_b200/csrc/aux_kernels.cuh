@@ -23,6 +23,9 @@ cudaError_t generate_launch(int kind, uint64_t off, uint64_t n, uint8_t* dst, co
                             uint64_t* launches);
 cudaError_t summarize_launch(const uint16_t* out, uint64_t n, uint64_t pos_base, const PatTables& t,
                              unsigned long long* d_acc4, int n_sms, cudaStream_t st, uint64_t* launches);
+// measure_success_rate (Core/src/measure.c:174-190) of one dense result against another; d_acc4 = success, partial, false_neg, false_pos
+cudaError_t classify_launch(const uint16_t* algo, const uint16_t* real, uint64_t n, const PatTables& t,
+                            unsigned long long* d_acc4, int n_sms, cudaStream_t st, uint64_t* launches);
 size_t compact_blocks(uint64_t n);
 // min_len > 1: only matches whose (longest) pattern has at least min_len bytes produce records
 cudaError_t compact_launch(const uint16_t* out, uint64_t n, uint64_t pos_base, bool expand, uint32_t min_len, const PatTables& t,

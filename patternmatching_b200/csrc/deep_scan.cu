@@ -16,10 +16,8 @@
 // 0.62 record fetches per byte on the C5b stream (tests/test_host_compiler.py prints it), 0.13 on planted traffic.
 //
 // The walk is byte-synchronous per warp (all lanes take byte k of their own segment together, eight bytes per loop
-// iteration from one 8-byte load, eight results out as one 16-byte store): the per-byte code is short and the
-// failure loop is the only data-dependent part.  A first version ran every lane as an independent state machine with
-// a shifted byte window and results staged in shared memory; it executed ~12 warp instructions per stream byte and
-// was issue-bound at 55 GB/s.
+// iteration from one 8-byte load, eight results out as one 16-byte store) and every byte is resolved in warp-wide
+// rounds with one converged record fetch per round (see step()).
 #include "deep_scan.cuh"
 #include "pm_dev.cuh"
 
@@ -48,55 +46,63 @@ struct Tabs {
     uint32_t n_hot;
 };
 
-__device__ __forceinline__ void fetch(Walk& W, const Tabs& t) {
-    ldg_rec(t.recs + size_t(W.s) * 8, W.w);
-    W.have = true; W.head = true;
-}
-
-// one stream byte: returns the longest-pattern id of the state reached
-__device__ __forceinline__ uint32_t step(Walk& W, uint32_t c, const Tabs& t) {
+// One stream byte for every lane of the warp (lanes with active == false only keep the others company).  The walk of
+// one byte may need several dependent record fetches (arrive at a cold state: its record for the longest id; failure
+// chain: the record of every cold failure state tried).  The loop below runs in warp-wide ROUNDS: in each round all
+// lanes that need a record fetch it with the SAME load instruction, then every unfinished lane advances as far as it
+// can without another fetch.  (A per-lane `for (;;)` with the fetch inside it made the hardware run the lanes' loop
+// iterations one after the other: 1-2 active lanes per LDG, every fetch latency exposed 32 times -- 50 GB/s.)
+__device__ __forceinline__ uint32_t step(Walk& W, uint32_t c, bool active, const Tabs& t) {
+    uint32_t o = 0;
+    bool done = !active;
+    bool arrived = false;   // s was just entered and is cold: only its longest id is missing
     for (;;) {
-        if (W.s < t.n_hot) {   // complete row in shared memory
-            W.s = t.s_hot[(W.s << 8) | c];
-            if (W.s < t.n_hot) return t.s_long[W.s];
-            fetch(W, t);       // a cold state's longest id lives in its record, which the next byte needs anyway
-            return W.w[1];
+        if (!done && W.s >= t.n_hot && !W.have) {
+            ldg_rec(t.recs + size_t(W.s) * 8, W.w);
+            W.have = true; W.head = true;
         }
-        if (!W.have) fetch(W, t);
-        const uint32_t kind = (W.w[0] >> 24) & 3u;
-        if (kind == 1u) {      // CHAIN: the next state of the run is s + 1
-            if ((W.w[2] & 0xFFu) == c) {
-                const uint32_t o = W.w[4] & 0xFFFFu;
-                ++W.s;
-                W.w[2] = __funnelshift_r(W.w[2], W.w[3], 8); W.w[3] >>= 8;
-                W.w[4] = __funnelshift_r(W.w[4], W.w[5], 16); W.w[5] = __funnelshift_r(W.w[5], W.w[6], 16);
-                W.w[6] = __funnelshift_r(W.w[6], W.w[7], 16); W.w[7] >>= 16;
-                W.w[0] -= 1u << 26;
-                W.head = false;
-                if ((W.w[0] >> 26) == 0) W.have = false;   // run (or this record's part of it) used up
-                return o;
-            }
-            if (W.head) { W.s = W.w[0] & 0xFFFFFFu; W.have = false; }   // failure transition; the byte is not consumed
-            else W.have = false;                                         // inside the run: s's own record has its failure link
-            continue;
-        }
-        if (kind == 0u) {      // BRANCH: goto edges in w[2..]
-            const uint32_t cnt = W.w[0] >> 26;
-            uint32_t next = 0xFFFFFFFFu;
+        if (!done) {
+            if (arrived) { o = W.w[1]; done = true; }
+            else if (W.s < t.n_hot) {                       // complete row in shared memory
+                W.s = t.s_hot[(W.s << 8) | c];
+                W.have = false;
+                if (W.s < t.n_hot) { o = t.s_long[W.s]; done = true; } else arrived = true;
+            } else {
+                const uint32_t kind = (W.w[0] >> 24) & 3u, fail = W.w[0] & 0xFFFFFFu;
+                if (kind == 1u) {                           // CHAIN: the next state of the run is s + 1
+                    if ((W.w[2] & 0xFFu) == c) {
+                        o = W.w[4] & 0xFFFFu;
+                        ++W.s;
+                        W.w[2] = __funnelshift_r(W.w[2], W.w[3], 8); W.w[3] >>= 8;
+                        W.w[4] = __funnelshift_r(W.w[4], W.w[5], 16); W.w[5] = __funnelshift_r(W.w[5], W.w[6], 16);
+                        W.w[6] = __funnelshift_r(W.w[6], W.w[7], 16); W.w[7] >>= 16;
+                        W.w[0] -= 1u << 26;
+                        W.head = false;
+                        if ((W.w[0] >> 26) == 0) W.have = false;   // this record's part of the run is used up
+                        done = true;
+                    } else {
+                        if (W.head) W.s = fail;             // failure transition; the byte is not consumed
+                        W.have = false;                     // (inside the run: s's own record has its failure link)
+                    }
+                } else if (kind == 0u) {                    // BRANCH: goto edges in w[2..]
+                    const uint32_t cnt = W.w[0] >> 26;
+                    uint32_t next = 0xFFFFFFFFu;
 #pragma unroll
-            for (int k = 0; k < 6; ++k)
-                if (uint32_t(k) < cnt && (W.w[2 + k] & 0xFFu) == c) next = W.w[2 + k] >> 8;
-            if (next != 0xFFFFFFFFu) { W.s = next; fetch(W, t); return W.w[1]; }
-            W.s = W.w[0] & 0xFFFFFFu; W.have = false;
-            continue;
+                    for (int k = 0; k < 6; ++k)
+                        if (uint32_t(k) < cnt && (W.w[2 + k] & 0xFFu) == c) next = W.w[2 + k] >> 8;
+                    W.have = false;
+                    if (next != 0xFFFFFFFFu) { W.s = next; arrived = true; }
+                    else W.s = fail;
+                } else {                                    // DENSE: a complete row
+                    W.s = __ldg(t.dense + ((size_t(W.w[2]) << 8) | c));
+                    W.have = false;
+                    if (W.s < t.n_hot) { o = t.s_long[W.s]; done = true; } else arrived = true;
+                }
+            }
         }
-        // DENSE: a complete row
-        W.s = __ldg(t.dense + ((size_t(W.w[2]) << 8) | c));
-        W.have = false;
-        if (W.s < t.n_hot) return t.s_long[W.s];
-        fetch(W, t);
-        return W.w[1];
+        if (!__any_sync(0xFFFFFFFFu, !done)) break;
     }
+    return o;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) deep_scan_kernel(const DeepParams p) {
@@ -113,37 +119,48 @@ __global__ void __launch_bounds__(kThreads, 1) deep_scan_kernel(const DeepParams
     Tabs t;
     t.s_hot = s_hot; t.s_long = s_long; t.recs = p.recs; t.dense = p.dense_rows; t.n_hot = p.n_hot;
     const uint8_t* __restrict__ stream = p.stream;
+    const int64_t lo = -int64_t(p.hist_valid), hi = int64_t(p.n);
+    const int64_t warm8 = (int64_t(p.warm) + 7) & ~int64_t(7);   // warm-up in whole 8-byte blocks (more never hurts)
 
-    for (uint64_t seg = uint64_t(blockIdx.x) * kThreads + threadIdx.x; seg < p.n_seg; seg += uint64_t(gridDim.x) * kThreads) {
-        const uint64_t s0 = seg * uint64_t(p.seg);
-        const uint64_t s1 = min(p.n, s0 + uint64_t(p.seg));
-        // warm-up: max_pat_len-1 bytes back (never before the readable history), walked but not reported
-        int64_t q0 = int64_t(s0) - int64_t(p.warm);
-        if (q0 < -int64_t(p.hist_valid)) q0 = -int64_t(p.hist_valid);
+    // the segment loop is warp-uniform (step() is a warp-wide routine): lanes without a segment run along inactive
+    const uint64_t seg_stride = uint64_t(gridDim.x) * kThreads;
+    const uint64_t warp_first = uint64_t(blockIdx.x) * kThreads + (threadIdx.x & ~31u);
+    for (uint64_t base = warp_first; base < p.n_seg; base += seg_stride) {
+        const uint64_t seg = base + (threadIdx.x & 31u);
+        const bool lane_valid = seg < p.n_seg;
+        const int64_t s0 = int64_t(seg * uint64_t(p.seg));
+        const int64_t s1 = lane_valid ? min(hi, s0 + int64_t(p.seg)) : s0;
         Walk W;
         W.s = 0; W.have = false; W.head = false;
 #pragma unroll
         for (int k = 0; k < 8; ++k) W.w[k] = 0;
-        for (; q0 < int64_t(s0) && (q0 & 7); ++q0) step(W, stream[q0], t);
 #pragma unroll 1
-        for (; q0 < int64_t(s0); q0 += 8) {
-            const uint2 v = __ldg(reinterpret_cast<const uint2*>(stream + q0));
-#pragma unroll
-            for (int k = 0; k < 8; ++k) step(W, ((k < 4 ? v.x : v.y) >> (8 * (k & 3))) & 0xFFu, t);
-        }
-        uint64_t q = s0;
-#pragma unroll 1
-        for (; q + 8 <= s1; q += 8) {
-            const uint2 v = __ldg(reinterpret_cast<const uint2*>(stream + q));
-            uint32_t r[4];
+        for (int64_t rel = -warm8; rel < int64_t(p.seg); rel += 8) {
+            const int64_t q = s0 + rel;
+            uint2 v = make_uint2(0u, 0u);
+            const bool whole = lane_valid && q >= lo && q + 8 <= s1;
+            if (whole) {
+                v = __ldg(reinterpret_cast<const uint2*>(stream + q));
+            } else if (lane_valid) {
+                for (int k = 0; k < 8; ++k) {
+                    const int64_t g = q + k;
+                    if (g >= lo && g < s1) { if (k < 4) v.x |= uint32_t(stream[g]) << (8 * k); else v.y |= uint32_t(stream[g]) << (8 * (k - 4)); }
+                }
+            }
+            uint32_t r[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const uint32_t o = step(W, ((k < 4 ? v.x : v.y) >> (8 * (k & 3))) & 0xFFu, t);
+                const bool active = lane_valid && (whole || (q + k >= lo && q + k < s1));
+                const uint32_t o = step(W, ((k < 4 ? v.x : v.y) >> (8 * (k & 3))) & 0xFFu, active, t);
                 if (k & 1) r[k >> 1] |= o << 16; else r[k >> 1] = o;
             }
-            __stcs(reinterpret_cast<uint4*>(p.out + q), make_uint4(r[0], r[1], r[2], r[3]));
+            if (rel >= 0) {
+                if (whole) __stcs(reinterpret_cast<uint4*>(p.out + q), make_uint4(r[0], r[1], r[2], r[3]));
+                else if (lane_valid)
+                    for (int k = 0; k < 8; ++k)
+                        if (q + k < s1) p.out[q + k] = uint16_t(r[k >> 1] >> (16 * (k & 1)));
+            }
         }
-        for (; q < s1; ++q) p.out[q] = uint16_t(step(W, stream[q], t));   // ragged end of the stream
     }
 }
 

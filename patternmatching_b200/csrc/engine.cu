@@ -900,6 +900,21 @@ int pm_engine_summarize(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t 
     return 0;
 }
 
+int pm_engine_classify(pm_engine* e, const uint16_t* d_algo, const uint16_t* d_real, size_t n, uint64_t counts4[4], void* cuda_stream) {
+    std::lock_guard<std::mutex> lock(e->mu);
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if ((reinterpret_cast<uintptr_t>(d_algo) & 15) || (reinterpret_cast<uintptr_t>(d_real) & 15))
+        return fail("pm_engine_classify: both results must be 16-byte aligned");
+    cudaError_t ce = pm::classify_launch(d_algo, d_real, n, e->pt, e->d_acc, e->n_sms, st, &e->launches);
+    if (ce != cudaSuccess) return cuda_fail(ce, "classify_launch");
+    unsigned long long h[4];
+    CU(cudaMemcpyAsync(h, e->d_acc, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int k = 0; k < 4; ++k) counts4[k] = h[k];
+    return 0;
+}
+
 int pm_engine_compact(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t pos_base, int expand_ancestors,
                       uint64_t* d_records, size_t cap, uint64_t* n_records, void* cuda_stream) {
     std::lock_guard<std::mutex> lock(e->mu);
