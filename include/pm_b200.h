@@ -150,7 +150,9 @@ int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n,
 /* Same pipeline; out[i] = id_of_pid[pid of the longest pattern ending at i] -- 8 bytes per position, what the
  * reference's read_char returns (pattern_id_t is a pointer, Core/src/PatternsTree.h:104; Core/src/mps.h:41-42).
  * id_of_pid has n_ids >= P + 1 entries, entry 0 = the "no pattern" id.  The translation runs on the engine's host
- * threads piece by piece while later pieces are still on the GPU.  This is what gpu_read_block calls. */
+ * threads piece by piece while later pieces are still on the GPU; when `out` is page-locked (and 16-byte aligned) the
+ * translation happens on the device instead and the ids arrive by DMA (8 B per position over PCIe, no host thread
+ * involved).  This is what gpu_read_block calls. */
 int pm_engine_scan_host_ids(pm_engine* e, int algo, const uint8_t* stream, size_t n, const uint64_t* id_of_pid,
                             size_t n_ids, uint64_t* out);
 /* Same pipeline, sparse result: only the positions whose longest match is a pattern of at least min_len bytes
@@ -215,6 +217,11 @@ uint64_t pm_engine_last_deferred(pm_engine* e);
 /* Page-locked host buffers for pm_engine_scan_host (a pageable buffer is staged through internal ones). */
 void* pm_host_alloc(size_t bytes);
 void pm_host_free(void* p);
+/* Page-lock a buffer the caller already owns and reuses for every chunk (the reference's stream_buffer / algo_results
+ * arrays, Core/src/measure.c:243-245, when they are static or heap memory that lives as long as the matcher): after
+ * this the host calls use it in place like pm_host_alloc memory.  The caller must unregister before freeing it. */
+int pm_host_register(void* p, size_t bytes);
+int pm_host_unregister(void* p);
 /* number of kernel launches issued by this engine since creation (bench.py's gpu_launches) */
 uint64_t pm_engine_launch_count(const pm_engine* e);
 

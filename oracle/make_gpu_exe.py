@@ -9,7 +9,7 @@ patternmatching_b200/libpm_b200.so.  Outputs (git-ignored, shipped to the GPU bo
                             except for the batched call at measure.c:292-294; STREAM_BUFFER_SIZE as shipped (100 KiB)
   oracle/_ref/exe_gpu_big   AC + the two GPU rows only (LMAC 0.5 MB/s and MPBG 265 B/s cannot read a large stream),
                             STREAM_BUFFER_SIZE = 16 MiB with the three chunk arrays made static (they are stack
-                            arrays in the reference, measure.c:243-245)
+                            arrays in the reference, measure.c:243-245) and page-locked once by the glue
 
 Edits are made by anchor replacement; every anchor must occur exactly once, so a reference that has changed makes
 this script fail instead of mis-patching.
@@ -69,7 +69,8 @@ def build(ref, out, big):
             units = [u for u in units if os.path.basename(u) not in ("mpbg.c", "mplmac.c")]
         os.makedirs(out, exist_ok=True)
         exe = os.path.join(out, "exe_gpu_big" if big else "exe_gpu")
-        cmd = ["gcc", "-O2", "-w", "-U_FORTIFY_SOURCE", "-I" + tmp, "-I" + os.path.join(ROOT, "include")] + units + \
+        cmd = ["gcc", "-O2", "-w", "-U_FORTIFY_SOURCE", "-I" + tmp, "-I" + os.path.join(ROOT, "include")] + \
+              (["-DMPGPU_REGISTER_BUFFERS"] if big else []) + units + \
               ["-L" + os.path.join(ROOT, "patternmatching_b200"), "-lpm_b200",
                "-Wl,-rpath,$ORIGIN/../../patternmatching_b200", "-o", exe]
         subprocess.check_call(cmd)

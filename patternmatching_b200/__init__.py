@@ -107,6 +107,8 @@ def lib():
         "pm_comm_gather_records": (C.c_int, [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64), C.c_int, vp]),
         "pm_host_alloc": (vp, [sz]),
         "pm_host_free": (None, [vp]),
+        "pm_host_register": (C.c_int, [vp, sz]),
+        "pm_host_unregister": (C.c_int, [vp]),
         "gpu_create": (vp, []), "gpu_dfa_create": (vp, []), "gpu_kr_create": (vp, []),
         "gpu_add_pattern": (None, [vp, C.c_char_p, sz, vp]),
         "gpu_compile": (None, [vp]),

@@ -85,10 +85,15 @@ __global__ void __launch_bounds__(256) summarize_kernel(const uint16_t* __restri
     auto one = [&](uint32_t pid, uint64_t pos) {
         if (!pid) return;
         ++positions;
-        h0 += splitmix64_d(pos ^ __ldg(t.pidhash + pid));
-        const uint32_t b = __ldg(t.anc_off + pid), e = __ldg(t.anc_off + pid + 1);
-        matches += e - b;
-        for (uint32_t k = b; k < e; ++k) h1 += splitmix64_d(pos ^ __ldg(t.pidhash + __ldg(t.anc_list + k)));
+        const uint64_t own = splitmix64_d(pos ^ __ldg(t.pidhash + pid));
+        h0 += own;
+        h1 += own;                                      // the range starts with pid itself
+        const uint32_t nanc = __ldg(t.chain + pid);     // 97% of the matches on binary traffic have no ancestor
+        matches += 1 + nanc;
+        if (nanc) {
+            const uint32_t b = __ldg(t.anc_off + pid) + 1;
+            for (uint32_t k = b; k < b + nanc; ++k) h1 += splitmix64_d(pos ^ __ldg(t.pidhash + __ldg(t.anc_list + k)));
+        }
     };
     // 8 positions (one 16-byte load) per thread and step; `out` is 16-byte aligned
     const uint64_t n8 = n / 8;
@@ -111,6 +116,26 @@ __global__ void __launch_bounds__(256) summarize_kernel(const uint16_t* __restri
         for (int w = 0; w < 8; ++w) s += sh[threadIdx.x][w];
         atomicAdd(&acc[threadIdx.x], (unsigned long long)s);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pid -> caller's 64-bit pattern id (the plugin's pattern_id_t, Core/src/PatternsTree.h:104): ids[i] = table[out[i]].
+// Used when the caller's result buffer is page-locked: the 8 bytes per position then leave the GPU by DMA instead of
+// being produced by host threads.  Four positions per thread: one 8-byte load, two 16-byte stores.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) expand_ids_kernel(const uint16_t* __restrict__ out, uint64_t n,
+                                                        const unsigned long long* __restrict__ table,
+                                                        unsigned long long* __restrict__ ids) {
+    const uint64_t n4 = n / 4;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint2 v = __ldcs(reinterpret_cast<const uint2*>(out) + i);
+        ulonglong2 a, b;
+        a.x = __ldg(table + (v.x & 0xFFFFu)); a.y = __ldg(table + (v.x >> 16));
+        b.x = __ldg(table + (v.y & 0xFFFFu)); b.y = __ldg(table + (v.y >> 16));
+        __stcs(reinterpret_cast<ulonglong2*>(ids) + 2 * i, a);
+        __stcs(reinterpret_cast<ulonglong2*>(ids) + 2 * i + 1, b);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) ids[n4 * 4 + threadIdx.x] = __ldg(table + out[n4 * 4 + threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -379,6 +404,15 @@ cudaError_t summarize_launch(const uint16_t* out, uint64_t n, uint64_t pos_base,
     uint64_t want = (n / 8 + 255) / 256 + 1;
     const uint32_t grid = uint32_t(want < uint64_t(n_sms) * 8 ? want : uint64_t(n_sms) * 8);
     summarize_kernel<<<grid, 256, 0, st>>>(out, n, pos_base, t, d_acc4);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t expand_ids_launch(const uint16_t* out, uint64_t n, const unsigned long long* table, unsigned long long* ids,
+                              int n_sms, cudaStream_t st, uint64_t* launches) {
+    if (n == 0) return cudaSuccess;
+    const uint64_t want = (n / 4 + 255) / 256 + 1;
+    expand_ids_kernel<<<uint32_t(want < uint64_t(n_sms) * 16 ? want : uint64_t(n_sms) * 16), 256, 0, st>>>(out, n, table, ids);
     ++*launches;
     return cudaGetLastError();
 }

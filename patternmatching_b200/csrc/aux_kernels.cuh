@@ -23,6 +23,9 @@ cudaError_t generate_launch(int kind, uint64_t off, uint64_t n, uint8_t* dst, co
                             uint64_t* launches);
 cudaError_t summarize_launch(const uint16_t* out, uint64_t n, uint64_t pos_base, const PatTables& t,
                              unsigned long long* d_acc4, int n_sms, cudaStream_t st, uint64_t* launches);
+// ids[i] = table[out[i]] (pid -> the caller's 64-bit pattern id); out 8-byte aligned, ids 16-byte aligned
+cudaError_t expand_ids_launch(const uint16_t* out, uint64_t n, const unsigned long long* table, unsigned long long* ids,
+                              int n_sms, cudaStream_t st, uint64_t* launches);
 // measure_success_rate (Core/src/measure.c:174-190) of one dense result against another; d_acc4 = success, partial, false_neg, false_pos
 cudaError_t classify_launch(const uint16_t* algo, const uint16_t* real, uint64_t n, const PatTables& t,
                             unsigned long long* d_acc4, int n_sms, cudaStream_t st, uint64_t* launches);

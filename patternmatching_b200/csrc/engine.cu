@@ -156,6 +156,12 @@ struct pm_engine {
     cudaStream_t st[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr};
     std::unique_ptr<pm::HostPool> pool;
+    // pid -> caller's id translated on the device (page-locked result buffers): the table and per-slot id buffers
+    unsigned long long* d_id_table = nullptr;
+    const uint64_t* id_table_src = nullptr;   // host table last uploaded (re-uploaded when pointer or contents change)
+    uint64_t id_table_sum = 0;
+    size_t id_table_n = 0;
+    unsigned long long* d_ids[2] = {nullptr, nullptr};
     // record path of the host pipeline (lazy)
     uint64_t* d_rec[2] = {nullptr, nullptr};
     unsigned long long* d_rec_counts[2] = {nullptr, nullptr};
@@ -456,12 +462,31 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
     const size_t H = e->halo;
     const bool in_pinned = is_pinned(stream);
     const bool direct_out = sink.out16 && is_pinned(sink.out16);   // the D2H copy lands in the caller's buffer
+    // 8-byte ids into a page-locked buffer: translated on the device and sent by DMA (8 B per position over PCIe, no
+    // host thread touches them); into a pageable buffer: 2 B per position over PCIe, translated by the host threads
+    const bool device_ids = sink.out64 && is_pinned(sink.out64) && (reinterpret_cast<uintptr_t>(sink.out64) & 15) == 0;
+    if (device_ids) {
+        uint64_t sum = 0;
+        const size_t tn = e->dict->pats.size() + 1;
+        for (size_t i = 0; i < tn; ++i) sum = sum * 1099511628211ull + sink.table[i];
+        if (!e->d_id_table || e->id_table_n != tn || e->id_table_src != sink.table || e->id_table_sum != sum) {
+            if (e->d_id_table && e->id_table_n != tn) { CU(cudaFree(e->d_id_table)); e->d_id_table = nullptr; }
+            if (!e->d_id_table) CU(cudaMalloc(reinterpret_cast<void**>(&e->d_id_table), tn * sizeof(uint64_t)));
+            CU(cudaMemcpy(e->d_id_table, sink.table, tn * sizeof(uint64_t), cudaMemcpyHostToDevice));
+            e->id_table_n = tn; e->id_table_src = sink.table; e->id_table_sum = sum;
+        }
+        for (int b = 0; b < 2; ++b)
+            if (!e->d_ids[b]) {
+                CU(cudaMalloc(reinterpret_cast<void**>(&e->d_ids[b]), e->opts.host_chunk * sizeof(uint64_t)));
+                e->scratch_bytes += e->opts.host_chunk * sizeof(uint64_t);
+            }
+    }
     // Pageable buffers are staged through the pinned ones by the pool's threads, in smaller pieces so that staging
     // piece k+1 and unloading piece k-1 overlap the transfers and the scan of piece k.
     // When host threads have work to do, a call is cut into at least ~8 pieces (512 KiB .. 4 MiB) so that the exposed
     // first stage-in and last unload stay a small part of it.
     size_t chunk = e->opts.host_chunk;
-    if (!(in_pinned && direct_out)) {
+    if (!(in_pinned && (direct_out || device_ids))) {
         chunk = std::min(chunk, kPageableChunk);
         while (chunk > (size_t(512) << 10) && n / chunk < 8) chunk >>= 1;
     }
@@ -475,7 +500,7 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
         const size_t os = ks * chunk, lens = stage ? std::min(chunk, n - os) : 0;
         const size_t from_call = stage ? std::min(os, H) : 0;
         const uint16_t* res = e->h_out[ku & 1];
-        const bool do_unload = unload && (sink.out64 || !direct_out);
+        const bool do_unload = unload && !device_ids && (sink.out64 || !direct_out);
         const bool do_stage = stage && !in_pinned;
         if (!do_unload && !do_stage) return;
         auto work = [&](int part, int parts) {
@@ -507,7 +532,13 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
         const uint8_t* src = in_pinned ? stream + o - from_call : e->h_in[b];
         CU(cudaMemcpyAsync(din + H - from_call, src, from_call + len, cudaMemcpyHostToDevice, e->st[b]));
         if (scan_device_impl(e, algo, din + H, len, hist_total, e->d_out[b], e->st[b], b)) return -1;
-        CU(cudaMemcpyAsync(direct_out ? sink.out16 + o : e->h_out[b], e->d_out[b], len * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->st[b]));
+        if (device_ids) {
+            cudaError_t ce = pm::expand_ids_launch(e->d_out[b], len, e->d_id_table, e->d_ids[b], e->n_sms, e->st[b], &e->launches);
+            if (ce != cudaSuccess) return cuda_fail(ce, "expand_ids_launch");
+            CU(cudaMemcpyAsync(sink.out64 + o, e->d_ids[b], len * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->st[b]));
+        } else {
+            CU(cudaMemcpyAsync(direct_out ? sink.out16 + o : e->h_out[b], e->d_out[b], len * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->st[b]));
+        }
         CU(cudaEventRecord(e->done[b], e->st[b]));
         return 0;
     };
@@ -644,6 +675,17 @@ void* pm_host_alloc(size_t bytes) {
     return p;
 }
 void pm_host_free(void* p) { if (p) cudaFreeHost(p); }
+int pm_host_register(void* p, size_t bytes) {
+    cudaError_t ce = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (ce == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaHostRegister");
+    return 0;
+}
+int pm_host_unregister(void* p) {
+    cudaError_t ce = cudaHostUnregister(p);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaHostUnregister");
+    return 0;
+}
 
 pm_engine* pm_engine_create(const pm_dict* dd, int device) {
     if (!dd || !dd->d.compiled) { fail("pm_engine_create: dictionary is not compiled"); return nullptr; }
@@ -711,7 +753,7 @@ void pm_engine_free(pm_engine* e) {
     if (e->rows_tex) cudaDestroyTextureObject(e->rows_tex);
     void* ptrs[] = {e->d_root2, e->d_root1, e->d_rows, e->d_row_best, e->d_cls, e->d_pat_off, e->d_pat_len, e->d_pat_bytes,
                     e->d_parent, e->d_chain, e->d_pidhash, e->d_tail_rec, e->d_l3f, e->d_anc_off, e->d_anc_list, e->d_sample_out, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_fb_meta, e->d_deep_hot, e->d_deep_long, e->d_deep_recs, e->d_deep_dense, e->d_acc,
-                    e->d_compact_counts, e->d_flags, e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1], e->d_queue[0], e->d_queue[1], e->d_qcount};
+                    e->d_compact_counts, e->d_flags, e->d_id_table, e->d_ids[0], e->d_ids[1], e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1], e->d_queue[0], e->d_queue[1], e->d_qcount};
     for (void* p : ptrs) if (p) cudaFree(p);
     pm::kr_free_tables(&e->kr);
     for (cudaEvent_t x : e->prof_events) cudaEventDestroy(x);

@@ -152,6 +152,62 @@ def test_field_and_fingerprint_identities():
         assert L.pmo_mulmod((whole - pre) % p, L.pmo_invmod(L.pmo_powmod(r, k))) == suf
 
 
+def test_fingerprints_and_inverses_equal_the_reference():
+    """The Karp-Rabin arithmetic pinned against the reference's own code (compiled unchanged into oracle/_ref/libpmref.so):
+    calc_fp / calc_fp_with_prefix (Core/src/Fingerprint.c:29-42, 57-77) and calculate_inverse (Core/src/field.c:26-72),
+    p = 2^31-1 (Core/src/mpbg.c:83).  Bytes < 0x80 only: for larger bytes the reference's pattern side sign-extends
+    `char` and lets the sum wrap, which the unsigned restatement deliberately does not reproduce -- the
+    last block shows the two really differ there."""
+    import ctypes as C
+    import os
+    from conftest import ROOT
+    path = os.path.join(ROOT, "oracle", "_ref", "libpmref.so")
+    if not os.path.exists(path):
+        pytest.fail("oracle/_ref/libpmref.so missing: run `make -C oracle` in the build container")
+    R = C.CDLL(path)
+
+    class FieldVal(C.Structure):
+        _fields_ = [("val", C.c_ulonglong), ("inv", C.c_ulonglong)]
+
+    R.calc_fp.restype = C.c_ulonglong
+    R.calc_fp.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(FieldVal), C.POINTER(FieldVal), C.c_ulonglong]
+    R.calc_fp_with_prefix.restype = C.c_ulonglong
+    R.calc_fp_with_prefix.argtypes = [C.c_char_p, C.c_size_t, C.c_ulonglong, C.c_size_t, C.POINTER(FieldVal), C.POINTER(FieldVal), C.c_ulonglong]
+    R.calculate_inverse.restype = C.c_ulonglong
+    R.calculate_inverse.argtypes = [C.c_ulonglong, C.c_ulonglong]
+    L = lib()
+    p = 2147483647
+    rng = np.random.default_rng(11)
+    for a in [1, 2, 3, 7, p - 1, p - 2, 65537, 1 << 30] + rng.integers(1, p, 200).tolist():
+        inv = R.calculate_inverse(a, p)
+        assert inv == L.pmo_invmod(a) and (inv * a) % p == 1
+    for trial in range(200):
+        r = int(L.pmo_kr_seed_r(int(rng.integers(1, 1 << 60))))
+        rv = FieldVal(r, R.calculate_inverse(r, p))
+        n = int(rng.integers(1, 348))
+        s = rng.integers(0, 128, n, dtype=np.uint8)               # the reference's sign-extension does not bite below 0x80
+        rn = FieldVal()
+        want = R.calc_fp(s.tobytes(), n, C.byref(rn), C.byref(rv), p)
+        assert want == L.pmo_fp(s.ctypes.data, n, r)
+        assert rn.val == L.pmo_powmod(r, n) and rn.inv == L.pmo_invmod(L.pmo_powmod(r, n))
+        # extending a prefix fingerprint: Fingerprint.c:57-77 == our identity fp(whole) = fp(pre) + r^k fp(suf)
+        k = int(rng.integers(0, n))
+        rk = FieldVal()
+        pre = R.calc_fp(s[:k].tobytes(), k, C.byref(rk), C.byref(rv), p) if k else 0
+        if not k:
+            rk = FieldVal(1, 1)
+        whole = R.calc_fp_with_prefix(s.tobytes(), n, pre, k, C.byref(rk), C.byref(rv), p)   # takes the WHOLE sequence and the prefix length
+        assert whole == want
+    # Q6: with bytes >= 0x80 the reference's own two sides disagree with the unsigned definition in a measurable share
+    differ = 0
+    for trial in range(300):
+        r = int(L.pmo_kr_seed_r(1000 + trial))
+        rv = FieldVal(r, R.calculate_inverse(r, p)); rn = FieldVal()
+        s = rng.integers(128, 256, 12, dtype=np.uint8)
+        differ += R.calc_fp(s.tobytes(), 12, C.byref(rn), C.byref(rv), p) != L.pmo_fp(s.ctypes.data, 12, r)
+    assert differ > 0
+
+
 def test_sharded_scan_with_halo_equals_continuous(oracle_merged):
     """Quirk Q8 on the CPU: re-scanning shards from reset with a max_pat_len-1 halo reproduces the scan."""
     o = oracle_merged
