@@ -15,9 +15,8 @@
 //     them is resolved without another fetch.
 // 0.62 record fetches per byte on the C5b stream (tests/test_host_compiler.py prints it), 0.13 on planted traffic.
 //
-// The walk is byte-synchronous per warp (all lanes take byte k of their own segment together, eight bytes per loop
-// iteration from one 8-byte load, eight results out as one 16-byte store) and every byte is resolved in warp-wide
-// rounds with one converged record fetch per round (see step()).
+// Lanes are independent state machines advanced in warp-wide rounds (see the kernel); stream bytes arrive eight at a
+// time in two registers that are shifted, results leave eight at a time as one 16-byte store.
 #include "deep_scan.cuh"
 #include "pm_dev.cuh"
 
@@ -38,35 +37,81 @@ struct Walk {
     bool head;        // CHAIN: nothing of the record has been consumed yet, so w[0] holds s's own failure link
 };
 
-struct Tabs {
-    const uint16_t* s_hot;
-    const uint16_t* s_long;
-    const uint32_t* recs;
-    const uint32_t* dense;
-    uint32_t n_hot;
+// Every lane is its own state machine over its own segment, and the warp runs them in ROUNDS: in each round a lane
+// performs at most one record fetch (all lanes that need one issue it with the same load instruction) and then
+// advances as far as it can without another fetch -- at most one stream byte.  A lane whose byte is resolved takes its
+// next byte at once; nobody waits for the lane with the longest failure chain.
+//   Why this shape: resolving one byte takes 1.6 rounds on average on the C5b stream but 4.9 for the slowest of 32
+//   lanes, so a byte-synchronous warp (all lanes on byte k together) wastes two thirds of its rounds; and a per-lane
+//   `for (;;)` with the fetch inside it made the hardware run the lanes' iterations one after the other (1-2 active
+//   lanes per LDG, every latency exposed 32 times).  Both were measured at 45-50 GB/s.
+struct LaneIO {
+    int64_t q, q_end, s0;   // next position to consume, end of the segment, first reported position
+    uint32_t in_lo, in_hi;  // the bytes at q, q+1, ... (shifted as they are consumed; refilled at multiples of 8)
+    uint32_t r[4];          // results of the current group of 8 positions
 };
 
-// One stream byte for every lane of the warp (lanes with active == false only keep the others company).  The walk of
-// one byte may need several dependent record fetches (arrive at a cold state: its record for the longest id; failure
-// chain: the record of every cold failure state tried).  The loop below runs in warp-wide ROUNDS: in each round all
-// lanes that need a record fetch it with the SAME load instruction, then every unfinished lane advances as far as it
-// can without another fetch.  (A per-lane `for (;;)` with the fetch inside it made the hardware run the lanes' loop
-// iterations one after the other: 1-2 active lanes per LDG, every fetch latency exposed 32 times -- 50 GB/s.)
-__device__ __forceinline__ uint32_t step(Walk& W, uint32_t c, bool active, const Tabs& t) {
-    uint32_t o = 0;
-    bool done = !active;
-    bool arrived = false;   // s was just entered and is cold: only its longest id is missing
-    for (;;) {
-        if (!done && W.s >= t.n_hot && !W.have) {
-            ldg_rec(t.recs + size_t(W.s) * 8, W.w);
-            W.have = true; W.head = true;
+__device__ __forceinline__ void load8(LaneIO& io, const uint8_t* __restrict__ stream, int64_t lo) {
+    // q is a multiple of 8 here, or the very first position of the segment's warm-up
+    const int64_t qa = io.q & ~int64_t(7);
+    uint32_t a = 0, b = 0;
+    if (qa >= lo && qa + 8 <= io.q_end) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(stream + qa));
+        a = v.x; b = v.y;
+    } else {
+        for (int k = 0; k < 8; ++k) {
+            const int64_t g = qa + k;
+            if (g >= lo && g < io.q_end) { if (k < 4) a |= uint32_t(stream[g]) << (8 * k); else b |= uint32_t(stream[g]) << (8 * (k - 4)); }
         }
-        if (!done) {
-            if (arrived) { o = W.w[1]; done = true; }
-            else if (W.s < t.n_hot) {                       // complete row in shared memory
-                W.s = t.s_hot[(W.s << 8) | c];
+    }
+    const uint32_t sk = uint32_t(io.q - qa) * 8;   // a start that is not a multiple of 8: drop the bytes before it
+    if (sk >= 32) { a = b >> (sk - 32); b = 0; }
+    else if (sk) { a = __funnelshift_r(a, b, sk); b >>= sk; }
+    io.in_lo = a; io.in_hi = b;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) deep_scan_kernel(const DeepParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint16_t* s_hot = reinterpret_cast<uint16_t*>(smem);                              // n_hot x 256
+    uint16_t* s_long = s_hot + (size_t(p.n_hot) << 8);                                // n_hot
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.hot_rows);
+        uint4* dst = reinterpret_cast<uint4*>(s_hot);
+        for (uint32_t i = threadIdx.x; i < (p.n_hot << 8) / 8; i += kThreads) dst[i] = __ldg(src + i);
+        for (uint32_t i = threadIdx.x; i < p.n_hot; i += kThreads) s_long[i] = __ldg(p.hot_longest + i);
+    }
+    __syncthreads();
+    const uint32_t n_hot = p.n_hot;
+    const uint8_t* __restrict__ stream = p.stream;
+    const int64_t lo = -int64_t(p.hist_valid), hi = int64_t(p.n);
+
+    for (uint64_t seg = uint64_t(blockIdx.x) * kThreads + threadIdx.x; seg < p.n_seg; seg += uint64_t(gridDim.x) * kThreads) {
+        LaneIO io;
+        io.s0 = int64_t(seg * uint64_t(p.seg));
+        io.q_end = min(hi, io.s0 + int64_t(p.seg));
+        io.q = max(lo, io.s0 - int64_t(p.warm));   // warm-up: max_pat_len-1 bytes back, walked but not reported
+        io.r[0] = io.r[1] = io.r[2] = io.r[3] = 0;
+        load8(io, stream, lo);
+        Walk W;
+        W.s = 0; W.have = false; W.head = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) W.w[k] = 0;
+        bool arrived = false;   // s was just entered and is cold: the byte is consumed, only s's longest id is missing
+#pragma unroll 1
+        while (io.q < io.q_end) {
+            // ---- one round ----
+            if (W.s >= n_hot && !W.have) {
+                ldg_rec(p.recs + size_t(W.s) * 8, W.w);
+                W.have = true; W.head = true;
+            }
+            const uint32_t c = io.in_lo & 0xFFu;
+            uint32_t o = 0;
+            bool done = false;
+            if (arrived) { o = W.w[1]; done = true; arrived = false; }
+            else if (W.s < n_hot) {                         // complete row in shared memory
+                W.s = s_hot[(W.s << 8) | c];
                 W.have = false;
-                if (W.s < t.n_hot) { o = t.s_long[W.s]; done = true; } else arrived = true;
+                if (W.s < n_hot) { o = s_long[W.s]; done = true; } else arrived = true;
             } else {
                 const uint32_t kind = (W.w[0] >> 24) & 3u, fail = W.w[0] & 0xFFFFFFu;
                 if (kind == 1u) {                           // CHAIN: the next state of the run is s + 1
@@ -94,71 +139,38 @@ __device__ __forceinline__ uint32_t step(Walk& W, uint32_t c, bool active, const
                     if (next != 0xFFFFFFFFu) { W.s = next; arrived = true; }
                     else W.s = fail;
                 } else {                                    // DENSE: a complete row
-                    W.s = __ldg(t.dense + ((size_t(W.w[2]) << 8) | c));
+                    W.s = __ldg(p.dense_rows + ((size_t(W.w[2]) << 8) | c));
                     W.have = false;
-                    if (W.s < t.n_hot) { o = t.s_long[W.s]; done = true; } else arrived = true;
+                    if (W.s < n_hot) { o = s_long[W.s]; done = true; } else arrived = true;
                 }
+            }
+            if (done) {                                     // the byte at q is resolved: report, take the next byte
+                const int64_t q = io.q;
+                if (q >= io.s0) {
+                    const uint32_t k = uint32_t(q) & 7u;
+                    // results of a group of 8 accumulate in r[] by shifting: after 8 of them r[0..3] hold positions 0..7 in order
+                    io.r[0] = __funnelshift_r(io.r[0], io.r[1], 16); io.r[1] = __funnelshift_r(io.r[1], io.r[2], 16);
+                    io.r[2] = __funnelshift_r(io.r[2], io.r[3], 16); io.r[3] = (io.r[3] >> 16) | (o << 16);
+                    if (k == 7u) __stcs(reinterpret_cast<uint4*>(p.out + (q - 7)), make_uint4(io.r[0], io.r[1], io.r[2], io.r[3]));
+                }
+                io.q = q + 1;
+                if ((io.q & 7) == 0) { if (io.q < io.q_end) load8(io, stream, lo); }
+                else { io.in_lo = __funnelshift_r(io.in_lo, io.in_hi, 8); io.in_hi >>= 8; }
             }
         }
-        if (!__any_sync(0xFFFFFFFFu, !done)) break;
-    }
-    return o;
-}
-
-__global__ void __launch_bounds__(kThreads, 1) deep_scan_kernel(const DeepParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint16_t* s_hot = reinterpret_cast<uint16_t*>(smem);                              // n_hot x 256
-    uint16_t* s_long = s_hot + (size_t(p.n_hot) << 8);                                // n_hot
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(p.hot_rows);
-        uint4* dst = reinterpret_cast<uint4*>(s_hot);
-        for (uint32_t i = threadIdx.x; i < (p.n_hot << 8) / 8; i += kThreads) dst[i] = __ldg(src + i);
-        for (uint32_t i = threadIdx.x; i < p.n_hot; i += kThreads) s_long[i] = __ldg(p.hot_longest + i);
-    }
-    __syncthreads();
-    Tabs t;
-    t.s_hot = s_hot; t.s_long = s_long; t.recs = p.recs; t.dense = p.dense_rows; t.n_hot = p.n_hot;
-    const uint8_t* __restrict__ stream = p.stream;
-    const int64_t lo = -int64_t(p.hist_valid), hi = int64_t(p.n);
-    const int64_t warm8 = (int64_t(p.warm) + 7) & ~int64_t(7);   // warm-up in whole 8-byte blocks (more never hurts)
-
-    // the segment loop is warp-uniform (step() is a warp-wide routine): lanes without a segment run along inactive
-    const uint64_t seg_stride = uint64_t(gridDim.x) * kThreads;
-    const uint64_t warp_first = uint64_t(blockIdx.x) * kThreads + (threadIdx.x & ~31u);
-    for (uint64_t base = warp_first; base < p.n_seg; base += seg_stride) {
-        const uint64_t seg = base + (threadIdx.x & 31u);
-        const bool lane_valid = seg < p.n_seg;
-        const int64_t s0 = int64_t(seg * uint64_t(p.seg));
-        const int64_t s1 = lane_valid ? min(hi, s0 + int64_t(p.seg)) : s0;
-        Walk W;
-        W.s = 0; W.have = false; W.head = false;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) W.w[k] = 0;
-#pragma unroll 1
-        for (int64_t rel = -warm8; rel < int64_t(p.seg); rel += 8) {
-            const int64_t q = s0 + rel;
-            uint2 v = make_uint2(0u, 0u);
-            const bool whole = lane_valid && q >= lo && q + 8 <= s1;
-            if (whole) {
-                v = __ldg(reinterpret_cast<const uint2*>(stream + q));
-            } else if (lane_valid) {
-                for (int k = 0; k < 8; ++k) {
-                    const int64_t g = q + k;
-                    if (g >= lo && g < s1) { if (k < 4) v.x |= uint32_t(stream[g]) << (8 * k); else v.y |= uint32_t(stream[g]) << (8 * (k - 4)); }
-                }
+        // ragged end of the stream: the last group is not full
+        const uint32_t rest = uint32_t(io.q_end - io.s0) & 7u;
+        if (rest) {
+            // the `rest` results sit in the top of r[]: shift them down to position 0
+            for (uint32_t k = rest; k < 8; ++k) {
+                io.r[0] = __funnelshift_r(io.r[0], io.r[1], 16); io.r[1] = __funnelshift_r(io.r[1], io.r[2], 16);
+                io.r[2] = __funnelshift_r(io.r[2], io.r[3], 16); io.r[3] >>= 16;
             }
-            uint32_t r[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const bool active = lane_valid && (whole || (q + k >= lo && q + k < s1));
-                const uint32_t o = step(W, ((k < 4 ? v.x : v.y) >> (8 * (k & 3))) & 0xFFu, active, t);
-                if (k & 1) r[k >> 1] |= o << 16; else r[k >> 1] = o;
-            }
-            if (rel >= 0) {
-                if (whole) __stcs(reinterpret_cast<uint4*>(p.out + q), make_uint4(r[0], r[1], r[2], r[3]));
-                else if (lane_valid)
-                    for (int k = 0; k < 8; ++k)
-                        if (q + k < s1) p.out[q + k] = uint16_t(r[k >> 1] >> (16 * (k & 1)));
+            const int64_t base = io.q_end - rest;
+            for (uint32_t k = 0; k < rest; ++k) {
+                p.out[base + k] = uint16_t(io.r[0]);
+                io.r[0] = __funnelshift_r(io.r[0], io.r[1], 16); io.r[1] = __funnelshift_r(io.r[1], io.r[2], 16);
+                io.r[2] = __funnelshift_r(io.r[2], io.r[3], 16); io.r[3] >>= 16;
             }
         }
     }
