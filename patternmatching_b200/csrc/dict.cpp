@@ -277,7 +277,8 @@ int Dict::compile() {
     const uint32_t n_rows = std::max(cont_base, n_other > cont_base ? n_other : 0u) + n2c;  // incl. unused rows below cont_base
     x.n_rows = n_rows; x.row2_base = cont_base; x.n2_cont = n2c; x.n_tail_nodes = n_tail;
     x.cont_base = cont_base;
-    x.fits_u16 = (n2c < 65536) && (uint64_t(P) + 1 <= x.cont_base) && n_rows < (1u << 24);
+    // the backward-scan tables need every pid and every 2-byte continue code in 16 bits, and walk depths in 9 bits
+    x.fits_u16 = (n2c < 65536) && (uint64_t(P) + 1 <= x.cont_base) && n_rows < (1u << 24) && max_len <= 511;
 
     // a FINAL entry of rows / root1 carries, above the 16-bit pid, the pattern's length (capped at 255) in bits 16-23:
     // the scan kernel's sparse mode tests "length >= min_len" with one compare and no lookup; everything that stores a
@@ -335,10 +336,12 @@ int Dict::compile() {
             }
         }
     }
-    if (!x.fits_u16) {   // not usable by the engine: stays uncompiled
-        error = "dictionary too large for dense uint16 results (needs P + #2-byte-continuations < 65536)";
+    if (P > 65535) {   // not usable by the engine: stays uncompiled
+        error = "dictionary too large for dense uint16 results (more than 65,535 unique patterns)";
         return -1;
     }
+    // !fits_u16 (pids fit, but P + #2-byte continuations >= 65,536, or a pattern longer than 511 bytes): the dictionary
+    // is usable, the engine serves every exact scan with the forward walkers, which have no such limit (mpac.c has none)
     compiled = true;
     return 0;
 }
@@ -557,7 +560,7 @@ struct Scalars {
 }  // namespace
 
 int Dict::save(const char* path) const {
-    if (!compiled) return -1;
+    if (!compiled || !sfx.fits_u16) return -1;   // only dictionaries with backward-scan tables are cached
     const std::string tmp = std::string(path) + ".tmp." + std::to_string(uint64_t(getpid()));
     FILE* f = fopen(tmp.c_str(), "wb");
     if (!f) return -1;

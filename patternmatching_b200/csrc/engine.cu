@@ -314,6 +314,7 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
                      cudaStream_t st, int slot) {
     if (n == 0) return 0;
     bool force_flat = false;
+    if (algo == PM_ALGO_AUTO && !e->dict->sfx.fits_u16) algo = PM_ALGO_SFX;   // routed to the forward walkers below
     if (algo == PM_ALGO_AUTO) {
         if (e->auto_choice < 0) {
             e->auto_choice = choose_algo(e, d_stream, n, hist_valid, st, slot);
@@ -325,6 +326,18 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
     if ((reinterpret_cast<uintptr_t>(d_stream) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
         return fail("pm_engine_scan_device: d_stream and d_out must be 16-byte aligned");
     const pm::Dict& d = *e->dict;
+    bool kr_after = false;
+    if (!d.sfx.fits_u16 && (algo == PM_ALGO_SFX || algo == PM_ALGO_KR)) {
+        // no backward-scan tables for this dictionary (P + 2-byte continuations >= 65,536, or a pattern > 511 bytes):
+        // the forward walkers serve it -- the compact-record walker when the automaton does not fit shared memory
+        kr_after = algo == PM_ALGO_KR;
+        if (kr_after && ensure_kr(e)) return -1;
+        d.build_deep();
+        uint32_t hot_rows = 0, hot_long = 0, fb_count = 0;
+        pm::dfa_plan_hot(d.deep.n_states, d.sfx.log2_ncp, d.deep.depth_count.data(), uint32_t(d.deep.depth_count.size()), &hot_rows, &hot_long, &fb_count);
+        force_flat = hot_rows < d.deep.n_states;
+        algo = PM_ALGO_DFA;
+    }
     if (algo == PM_ALGO_SFX) {
         pm::SfxParams p{};
         p.stream = d_stream; p.n = n; p.hist_valid = hist_valid; p.out = d_out;
@@ -358,6 +371,10 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
             p.warm = d.max_len ? d.max_len - 1 : 0;
             cudaError_t ce = pm::deep_scan_launch(p, e->n_sms, st, &e->launches);
             if (ce != cudaSuccess) return cuda_fail(ce, "deep_scan_launch");
+            if (kr_after) {
+                ce = pm::kr_scan_launch(e->kr, d_stream, n, hist_valid, d_out, e->pt, e->n_sms, st, &e->launches);
+                if (ce != cudaSuccess) return cuda_fail(ce, "kr_scan_launch");
+            }
             return 0;
         }
     }
@@ -374,6 +391,10 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
         if (e->opts.dfa_no_fb) p.fb_count = 0;
         cudaError_t ce = pm::dfa_scan_launch(p, d.sfx.cls_identity, force_flat || e->opts.dfa_flat, e->n_sms, st, &e->launches);
         if (ce != cudaSuccess) return cuda_fail(ce, "dfa_scan_launch");
+        if (kr_after) {
+            ce = pm::kr_scan_launch(e->kr, d_stream, n, hist_valid, d_out, e->pt, e->n_sms, st, &e->launches);
+            if (ce != cudaSuccess) return cuda_fail(ce, "kr_scan_launch");
+        }
         return 0;
     }
     if (algo == PM_ALGO_KR) {
@@ -454,7 +475,7 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
     if (ensure_pipe(e)) return -1;
     if (algo == PM_ALGO_DFA && ensure_dfa(e)) return -1;
     if (algo == PM_ALGO_KR && ensure_kr(e)) return -1;
-    if (n <= kSmallCall && (algo == PM_ALGO_SFX || algo == PM_ALGO_AUTO)) {
+    if (n <= kSmallCall && (algo == PM_ALGO_SFX || algo == PM_ALGO_AUTO) && e->dict->sfx.fits_u16) {
         if (scan_host_small(e, stream, n, sink)) { quiesce(e); return -1; }
         carry_history(e, stream, n);
         return 0;
@@ -580,7 +601,6 @@ uint32_t pm_dict_add_pattern(pm_dict* d, const uint8_t* pat, size_t len, uint32_
     return d->d.add_pattern(pat, len, file, line, user_id);
 }
 int pm_dict_compile(pm_dict* d) {
-    if (d->d.max_len > pm::kMaxPatLen) return fail("pattern longer than the supported maximum (353 bytes)");
     if (d->d.compile()) return fail(d->d.error);   // leaves `compiled` false when the dictionary is not usable
     return 0;
 }
@@ -867,7 +887,7 @@ int pm_engine_scan_host_records(pm_engine* e, int algo, const uint8_t* stream, s
         if (!e->h_rec_total[b]) CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_rec_total[b]), sizeof(unsigned long long)));
         if (!e->d_rec_flags[b]) CU(cudaMalloc(reinterpret_cast<void**>(&e->d_rec_flags[b]), (chunk / 32 + 16) * 4));
     }
-    const bool fused = algo == PM_ALGO_SFX && min_len >= 3;   // the scan kernel marks the qualifying positions itself
+    const bool fused = algo == PM_ALGO_SFX && min_len >= 3 && e->dict->sfx.fits_u16;   // the scan kernel marks the qualifying positions itself
     const bool in_pinned = is_pinned(stream);
     const size_t n_chunks = (n + chunk - 1) / chunk;
     uint64_t produced = 0;
@@ -983,7 +1003,7 @@ int pm_engine_scan_device_records(pm_engine* e, int algo, const uint8_t* d_strea
     if ((reinterpret_cast<uintptr_t>(d_stream) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
         return fail("pm_engine_scan_device_records: d_stream and d_out must be 16-byte aligned");
     if (e->scratch_used) CU(cudaStreamWaitEvent(st, e->scratch_free, 0));
-    const bool fused = algo == PM_ALGO_SFX && min_len >= 3;
+    const bool fused = algo == PM_ALGO_SFX && min_len >= 3 && e->dict->sfx.fits_u16;
     int rc = 0;
     unsigned long long total = 0;
     cudaError_t ce = cudaSuccess;

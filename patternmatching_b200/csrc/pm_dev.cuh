@@ -5,8 +5,7 @@
 
 namespace pm {
 
-constexpr int kHalo = 352;  // >= max supported pattern length - 1, multiple of 16 (bulk-copy granularity)
-constexpr uint32_t kMaxPatLen = kHalo + 1;
+constexpr int kHalo = 352;  // smallest history an engine keeps (>= 346 = snort's max_pat_len - 1), multiple of 16; longer patterns: more
 
 __host__ __device__ __forceinline__ uint64_t splitmix64_d(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;

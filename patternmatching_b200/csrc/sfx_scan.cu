@@ -663,7 +663,7 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
     // walk is bounded by the bytes that exist; every position that could look back past the start of the readable
     // stream is redone by the bounded walker -- together with the ragged end that does not fill a tile.
     uint32_t head = 0;
-    if (max_pat_len > 1 && p.hist_valid < uint64_t(kHalo)) {
+    if (max_pat_len > 1 && p.hist_valid < uint64_t(max_pat_len - 1)) {
         const uint64_t want = uint64_t(max_pat_len - 1);
         head = uint32_t(p.n < want ? p.n : want);
     }

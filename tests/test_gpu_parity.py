@@ -570,3 +570,44 @@ def test_sparse_mode_marks_matches_in_the_scan_kernel(kind, n, oracle_merged, en
     rec = torch.full((16,), -1, dtype=torch.int64, device=dev)
     cnt = engine_merged.scan_device_records(d_in, n, d_out, rec, 8, min_len=3)
     assert cnt >= 0 and bool((rec[8:] == -1).all().item())
+
+
+def test_dictionaries_beyond_the_backward_tables():
+    """No limit of the reference's Aho-Corasick is inherited from the table layout (mpac.c:257-291 takes anything):
+    (1) 60,000 random 4-byte patterns -- pids + 2-byte continue codes do not fit 16 bits -- and (2) patterns of 400,
+    1,000 and 5,000 bytes: every algorithm id, the sparse mode and the host path must still equal the oracle (the
+    engine routes them to the forward walkers)."""
+    rng = np.random.default_rng(21)
+    cases = []
+    pats = {bytes(rng.integers(0, 256, 4, dtype=np.uint8)) for _ in range(60000)}
+    cases.append(([p for p in pats if b"\n" not in p], None))
+    long_pats = [bytes(rng.integers(97, 101, L, dtype=np.uint8)) for L in (400, 1000, 5000)] + [b"abcabd", b"bd", b"dddd"]
+    cases.append((long_pats, long_pats))
+    for pats, plant in cases:
+        d = pm.Dictionary(); o = Oracle()
+        for i, p in enumerate(pats):
+            d.add_pattern(p, 0, i + 1); o.add_pattern(p, 0, i + 1)
+        d.compile(); o.compile()
+        eng = pm.Engine(d)
+        n = 600_000 + 9
+        if plant is None:
+            stream = rng.integers(0, 256, n, dtype=np.uint8)
+            for c in rng.integers(0, n - 8, 20000):
+                stream[c:c + 4] = np.frombuffer(pats[int(rng.integers(0, len(pats)))], np.uint8)
+        else:
+            stream = rng.integers(97, 101, n, dtype=np.uint8)
+            for c, p in zip((1000, 50_000, 200_000, 400_000, 590_000), plant[:3] + plant[:2]):
+                stream[c:c + len(p)] = np.frombuffer(p, np.uint8)[: n - c]
+        want = want_pids(o, stream)
+        for algo in (pm.ALGO_SFX, pm.ALGO_AUTO, pm.ALGO_DFA):
+            assert np.array_equal(gpu_scan(eng, stream, algo), want), algo
+        kr = gpu_scan(eng, stream, pm.ALGO_KR)
+        assert np.array_equal(kr, (o.kr_scan(stream, 0xF1A90003) + 1).astype(np.uint16))
+        eng.reset()
+        cuts = [0, 7, 100_000, 100_001, 350_000, n]
+        got = np.concatenate([eng.scan_host(stream[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+        assert np.array_equal(got, want)
+        # a shard with exactly max_pat_len-1 bytes of history equals the continuous scan
+        h = d.max_pat_len - 1
+        cut = 300_000
+        assert np.array_equal(gpu_scan(eng, stream[cut:], pm.ALGO_AUTO, hist=stream[cut - h:cut]), want[cut:])

@@ -96,14 +96,24 @@ def test_tiny_dictionary_shape():
 
 
 def test_limits_are_reported_not_silently_truncated():
+    """The reference's Aho-Corasick takes any dictionary (mpac.c:257-291).  Here: patterns of any length and any number of
+    2-byte continuations compile (the engine serves dictionaries without backward-scan tables with the forward walkers);
+    what dense uint16 results cannot name -- more than 65,535 unique patterns -- is refused with a message."""
     d = pm.Dictionary()
-    d.add_pattern(b"x" * 354, 0, 1)                                      # one byte over the supported maximum
-    with pytest.raises(pm.PmError, match="longer than the supported maximum"):
-        d.compile()
+    d.add_pattern(b"x" * 354, 0, 1)                                      # beyond the round-1 limit of 353 bytes
+    d.add_pattern(b"y" * 5000, 0, 2)                                     # beyond what the backward scan's queue items encode
+    d.compile()
+    assert d.max_pat_len == 5000 and d.n_patterns == 2
+    rng = np.random.default_rng(9)
+    d = pm.Dictionary()                                                  # P + 2-byte continue codes > 65,535
+    for i in range(60000):
+        d.add_pattern(bytes(rng.integers(0, 256, 4, dtype=np.uint8)), 0, i + 1)
+    d.compile()
+    assert d.n_patterns + d.info.n_hot2_cont > 65535
     d = pm.Dictionary()                                                  # more patterns than dense uint16 results can name
     for i in range(66000):
         d.add_pattern(b"%07d" % i, 0, i + 1)
-    with pytest.raises(pm.PmError, match="too large for dense uint16"):
+    with pytest.raises(pm.PmError, match="more than 65,535 unique patterns"):
         d.compile()
 
 
