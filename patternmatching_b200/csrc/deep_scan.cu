@@ -46,28 +46,47 @@ struct Walk {
 //   `for (;;)` with the fetch inside it made the hardware run the lanes' iterations one after the other (1-2 active
 //   lanes per LDG, every latency exposed 32 times).  Both were measured at 45-50 GB/s.
 struct LaneIO {
-    int64_t q, q_end, s0;   // next position to consume, end of the segment, first reported position
-    uint32_t in_lo, in_hi;  // the bytes at q, q+1, ... (shifted as they are consumed; refilled at multiples of 8)
+    const uint8_t* in;      // stream + s0: positions are 32-bit offsets from the segment start (negative = warm-up)
+    uint16_t* out;          // out + s0
+    int32_t rel, rel_end;   // next offset to consume, end of the segment
+    int32_t rel_lo;         // first readable offset (history limit)
+    uint32_t in_lo, in_hi;  // the bytes at rel, rel+1, ... (shifted as they are consumed; refilled at multiples of 8)
     uint32_t r[4];          // results of the current group of 8 positions
 };
 
-__device__ __forceinline__ void load8(LaneIO& io, const uint8_t* __restrict__ stream, int64_t lo) {
-    // q is a multiple of 8 here, or the very first position of the segment's warm-up
-    const int64_t qa = io.q & ~int64_t(7);
+// slow path of the refill: a group of 8 that is not entirely readable (start of the history, end of the stream) or a
+// start that is not a multiple of 8
+__device__ __noinline__ uint2 load8_slow(const uint8_t* in, int32_t rel, int32_t rel_lo, int32_t rel_end) {
+    const int32_t ra = rel & ~7;
     uint32_t a = 0, b = 0;
-    if (qa >= lo && qa + 8 <= io.q_end) {
-        const uint2 v = __ldg(reinterpret_cast<const uint2*>(stream + qa));
-        a = v.x; b = v.y;
-    } else {
-        for (int k = 0; k < 8; ++k) {
-            const int64_t g = qa + k;
-            if (g >= lo && g < io.q_end) { if (k < 4) a |= uint32_t(stream[g]) << (8 * k); else b |= uint32_t(stream[g]) << (8 * (k - 4)); }
-        }
+    for (int k = 0; k < 8; ++k) {
+        const int32_t g = ra + k;
+        if (g >= rel_lo && g < rel_end) { if (k < 4) a |= uint32_t(in[g]) << (8 * k); else b |= uint32_t(in[g]) << (8 * (k - 4)); }
     }
-    const uint32_t sk = uint32_t(io.q - qa) * 8;   // a start that is not a multiple of 8: drop the bytes before it
+    const uint32_t sk = uint32_t(rel - ra) * 8;
     if (sk >= 32) { a = b >> (sk - 32); b = 0; }
     else if (sk) { a = __funnelshift_r(a, b, sk); b >>= sk; }
-    io.in_lo = a; io.in_hi = b;
+    return make_uint2(a, b);
+}
+
+// the byte at io.rel has been resolved with result o: report it (not during the warm-up) and step to the next byte
+__device__ __forceinline__ void emit_and_advance(LaneIO& io, uint32_t o) {
+    const int32_t rel = io.rel;
+    if (rel >= 0) {
+        // results of a group of 8 accumulate in r[] by shifting: after 8 of them r[0..3] hold positions 0..7 in order
+        io.r[0] = __funnelshift_r(io.r[0], io.r[1], 16); io.r[1] = __funnelshift_r(io.r[1], io.r[2], 16);
+        io.r[2] = __funnelshift_r(io.r[2], io.r[3], 16); io.r[3] = (io.r[3] >> 16) | (o << 16);
+        if ((rel & 7) == 7) __stcs(reinterpret_cast<uint4*>(io.out + (rel - 7)), make_uint4(io.r[0], io.r[1], io.r[2], io.r[3]));
+    }
+    io.rel = rel + 1;
+    if ((io.rel & 7) == 0) {
+        if (io.rel + 8 <= io.rel_end && io.rel >= io.rel_lo) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(io.in + io.rel));
+            io.in_lo = v.x; io.in_hi = v.y;
+        } else if (io.rel < io.rel_end) { const uint2 v = load8_slow(io.in, io.rel, io.rel_lo, io.rel_end); io.in_lo = v.x; io.in_hi = v.y; }
+    } else {
+        io.in_lo = __funnelshift_r(io.in_lo, io.in_hi, 8); io.in_hi >>= 8;
+    }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) deep_scan_kernel(const DeepParams p) {
@@ -82,93 +101,86 @@ __global__ void __launch_bounds__(kThreads, 1) deep_scan_kernel(const DeepParams
     }
     __syncthreads();
     const uint32_t n_hot = p.n_hot;
-    const uint8_t* __restrict__ stream = p.stream;
-    const int64_t lo = -int64_t(p.hist_valid), hi = int64_t(p.n);
 
     for (uint64_t seg = uint64_t(blockIdx.x) * kThreads + threadIdx.x; seg < p.n_seg; seg += uint64_t(gridDim.x) * kThreads) {
         LaneIO io;
-        io.s0 = int64_t(seg * uint64_t(p.seg));
-        io.q_end = min(hi, io.s0 + int64_t(p.seg));
-        io.q = max(lo, io.s0 - int64_t(p.warm));   // warm-up: max_pat_len-1 bytes back, walked but not reported
+        const uint64_t s0 = seg * uint64_t(p.seg);
+        io.in = p.stream + s0; io.out = p.out + s0;
+        io.rel_end = int32_t(min(uint64_t(p.seg), p.n - s0));
+        io.rel_lo = -int32_t(min(uint64_t(p.warm), s0 + p.hist_valid));   // warm-up: max_pat_len-1 bytes back, never before the readable history
+        io.rel = io.rel_lo;
         io.r[0] = io.r[1] = io.r[2] = io.r[3] = 0;
-        load8(io, stream, lo);
+        { const uint2 v = load8_slow(io.in, io.rel, io.rel_lo, io.rel_end); io.in_lo = v.x; io.in_hi = v.y; }
         Walk W;
         W.s = 0; W.have = false; W.head = false;
 #pragma unroll
         for (int k = 0; k < 8; ++k) W.w[k] = 0;
         bool arrived = false;   // s was just entered and is cold: the byte is consumed, only s's longest id is missing
 #pragma unroll 1
-        while (io.q < io.q_end) {
-            // ---- one round ----
+        while (io.rel < io.rel_end) {
+            // ---- one round: at most one record fetch, then as far as the lane gets without another ----
             if (W.s >= n_hot && !W.have) {
                 ldg_rec(p.recs + size_t(W.s) * 8, W.w);
                 W.have = true; W.head = true;
             }
+            if (arrived) {                                  // the record just fetched completes the previous byte ...
+                arrived = false;
+                emit_and_advance(io, W.w[1]);
+                if (io.rel >= io.rel_end) break;            // ... and serves the next one in the same round
+            }
             const uint32_t c = io.in_lo & 0xFFu;
-            uint32_t o = 0;
-            bool done = false;
-            if (arrived) { o = W.w[1]; done = true; arrived = false; }
-            else if (W.s < n_hot) {                         // complete row in shared memory
+            if (W.s < n_hot) {                              // complete row in shared memory
                 W.s = s_hot[(W.s << 8) | c];
                 W.have = false;
-                if (W.s < n_hot) { o = s_long[W.s]; done = true; } else arrived = true;
-            } else {
-                const uint32_t kind = (W.w[0] >> 24) & 3u, fail = W.w[0] & 0xFFFFFFu;
-                if (kind == 1u) {                           // CHAIN: the next state of the run is s + 1
-                    if ((W.w[2] & 0xFFu) == c) {
-                        o = W.w[4] & 0xFFFFu;
-                        ++W.s;
-                        W.w[2] = __funnelshift_r(W.w[2], W.w[3], 8); W.w[3] >>= 8;
-                        W.w[4] = __funnelshift_r(W.w[4], W.w[5], 16); W.w[5] = __funnelshift_r(W.w[5], W.w[6], 16);
-                        W.w[6] = __funnelshift_r(W.w[6], W.w[7], 16); W.w[7] >>= 16;
-                        W.w[0] -= 1u << 26;
-                        W.head = false;
-                        if ((W.w[0] >> 26) == 0) W.have = false;   // this record's part of the run is used up
-                        done = true;
-                    } else {
-                        if (W.head) W.s = fail;             // failure transition; the byte is not consumed
-                        W.have = false;                     // (inside the run: s's own record has its failure link)
-                    }
-                } else if (kind == 0u) {                    // BRANCH: goto edges in w[2..]
-                    const uint32_t cnt = W.w[0] >> 26;
-                    uint32_t next = 0xFFFFFFFFu;
-#pragma unroll
-                    for (int k = 0; k < 6; ++k)
-                        if (uint32_t(k) < cnt && (W.w[2 + k] & 0xFFu) == c) next = W.w[2 + k] >> 8;
-                    W.have = false;
-                    if (next != 0xFFFFFFFFu) { W.s = next; arrived = true; }
-                    else W.s = fail;
-                } else {                                    // DENSE: a complete row
-                    W.s = __ldg(p.dense_rows + ((size_t(W.w[2]) << 8) | c));
-                    W.have = false;
-                    if (W.s < n_hot) { o = s_long[W.s]; done = true; } else arrived = true;
-                }
+                if (W.s < n_hot) emit_and_advance(io, s_long[W.s]); else arrived = true;
+                continue;
             }
-            if (done) {                                     // the byte at q is resolved: report, take the next byte
-                const int64_t q = io.q;
-                if (q >= io.s0) {
-                    const uint32_t k = uint32_t(q) & 7u;
-                    // results of a group of 8 accumulate in r[] by shifting: after 8 of them r[0..3] hold positions 0..7 in order
-                    io.r[0] = __funnelshift_r(io.r[0], io.r[1], 16); io.r[1] = __funnelshift_r(io.r[1], io.r[2], 16);
-                    io.r[2] = __funnelshift_r(io.r[2], io.r[3], 16); io.r[3] = (io.r[3] >> 16) | (o << 16);
-                    if (k == 7u) __stcs(reinterpret_cast<uint4*>(p.out + (q - 7)), make_uint4(io.r[0], io.r[1], io.r[2], io.r[3]));
+            const uint32_t kind = (W.w[0] >> 24) & 3u, fail = W.w[0] & 0xFFFFFFu;
+            if (kind == 1u) {                               // CHAIN: the next state of the run is s + 1
+                if ((W.w[2] & 0xFFu) == c) {
+                    const uint32_t o = W.w[4] & 0xFFFFu;
+                    ++W.s;
+                    W.w[2] = __funnelshift_r(W.w[2], W.w[3], 8); W.w[3] >>= 8;
+                    W.w[4] = __funnelshift_r(W.w[4], W.w[5], 16); W.w[5] = __funnelshift_r(W.w[5], W.w[6], 16);
+                    W.w[6] = __funnelshift_r(W.w[6], W.w[7], 16); W.w[7] >>= 16;
+                    W.w[0] -= 1u << 26;
+                    W.head = false;
+                    if ((W.w[0] >> 26) == 0) W.have = false;   // this record's part of the run is used up
+                    emit_and_advance(io, o);
+                } else {
+                    if (W.head) W.s = fail;                 // failure transition; the byte is not consumed
+                    W.have = false;                         // (inside the run: s's own record has its failure link)
                 }
-                io.q = q + 1;
-                if ((io.q & 7) == 0) { if (io.q < io.q_end) load8(io, stream, lo); }
-                else { io.in_lo = __funnelshift_r(io.in_lo, io.in_hi, 8); io.in_hi >>= 8; }
+            } else if (kind == 0u) {                        // BRANCH: goto edges in w[2..]
+                const uint32_t cnt = W.w[0] >> 26;
+                uint32_t next = 0xFFFFFFFFu;
+#pragma unroll
+                for (int k = 0; k < 6; ++k)
+                    if (uint32_t(k) < cnt && (W.w[2 + k] & 0xFFu) == c) next = W.w[2 + k] >> 8;
+                W.have = false;
+                if (next != 0xFFFFFFFFu) { W.s = next; arrived = true; }
+                else W.s = fail;
+            } else {                                        // DENSE: a complete row
+                W.s = __ldg(p.dense_rows + ((size_t(W.w[2]) << 8) | c));
+                W.have = false;
+                if (W.s < n_hot) emit_and_advance(io, s_long[W.s]); else arrived = true;
             }
         }
+        if (arrived) {   // the last byte of the segment ended in a cold state: its longest id still has to be fetched
+            ldg_rec(p.recs + size_t(W.s) * 8, W.w);
+            emit_and_advance(io, W.w[1]);
+        }
         // ragged end of the stream: the last group is not full
-        const uint32_t rest = uint32_t(io.q_end - io.s0) & 7u;
+        const uint32_t rest = uint32_t(io.rel_end) & 7u;
         if (rest) {
             // the `rest` results sit in the top of r[]: shift them down to position 0
             for (uint32_t k = rest; k < 8; ++k) {
                 io.r[0] = __funnelshift_r(io.r[0], io.r[1], 16); io.r[1] = __funnelshift_r(io.r[1], io.r[2], 16);
                 io.r[2] = __funnelshift_r(io.r[2], io.r[3], 16); io.r[3] >>= 16;
             }
-            const int64_t base = io.q_end - rest;
+            const int32_t base = io.rel_end - int32_t(rest);
             for (uint32_t k = 0; k < rest; ++k) {
-                p.out[base + k] = uint16_t(io.r[0]);
+                io.out[base + k] = uint16_t(io.r[0]);
                 io.r[0] = __funnelshift_r(io.r[0], io.r[1], 16); io.r[1] = __funnelshift_r(io.r[1], io.r[2], 16);
                 io.r[2] = __funnelshift_r(io.r[2], io.r[3], 16); io.r[3] >>= 16;
             }
