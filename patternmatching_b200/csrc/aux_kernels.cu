@@ -367,28 +367,28 @@ cudaError_t compact_bitmap_launch(const uint32_t* flags, const uint16_t* out, ui
 cudaError_t generate_launch(int kind, uint64_t off, uint64_t n, uint8_t* dst, const PatTables& t, cudaStream_t st,
                             uint64_t* launches) {
     if (n == 0) return cudaSuccess;
-    if (n > (uint64_t(1) << 34)) return cudaErrorInvalidValue;   // 16 GiB per call: the grids below are sized in 32 bits
-    const uint32_t words = uint32_t((n + 7) / 8), blocks4k = uint32_t((n + 4095) / 4096);
+    if (n > (uint64_t(1) << 38)) return cudaErrorInvalidValue;   // 256 GiB per call: the grids below are sized in 32 bits
+    const uint64_t words = (n + 7) / 8, blocks4k = (n + 4095) / 4096;
     switch (kind) {
         case 0:
         case 1:
-            gen_uniform_kernel<<<(words + 255) / 256, 256, 0, st>>>(off, n, dst);
+            gen_uniform_kernel<<<uint32_t((words + 255) / 256), 256, 0, st>>>(off, n, dst);
             ++*launches;
             if (kind == 1) {
-                gen_plant_kernel<<<(blocks4k + 127) / 128, 128, 0, st>>>(off, n, dst, t);
+                gen_plant_kernel<<<uint32_t((blocks4k + 127) / 128), 128, 0, st>>>(off, n, dst, t);
                 ++*launches;
             }
             break;
         case 2:
-            gen_almost_kernel<<<(blocks4k + 63) / 64, 64, 0, st>>>(off, n, dst, t);
+            gen_almost_kernel<<<uint32_t((blocks4k + 63) / 64), 64, 0, st>>>(off, n, dst, t);
             ++*launches;
             break;
         case 3:
-            gen_ab_kernel<<<(words + 255) / 256, 256, 0, st>>>(off, n, dst);
+            gen_ab_kernel<<<uint32_t((words + 255) / 256), 256, 0, st>>>(off, n, dst);
             ++*launches;
             break;
         case 4:
-            gen_ascii_kernel<<<(words + 255) / 256, 256, 0, st>>>(off, n, dst);
+            gen_ascii_kernel<<<uint32_t((words + 255) / 256), 256, 0, st>>>(off, n, dst);
             ++*launches;
             break;
         default:
