@@ -123,10 +123,13 @@ __device__ __forceinline__ void flag_set(const SfxParams& p, uint64_t pos, bool 
     if (on) atomicOr(w, bit); else atomicAnd(w, ~bit);
 }
 
-// a deferred walk's result: dense slot, and in sparse mode its flag bit (the scan kernel left it clear)
+// a deferred walk's result: dense slot, and in sparse mode (kFlags) its flag bit (the scan kernel left it clear).
+// The mode is a template parameter of the deep kernel: a run-time test of p.flags here cost the dense mode 552 bytes
+// of register spills at 64 registers per thread (deep kernel 1.15 -> 1.77 ms per 16 GiB of planted traffic).
+template <bool kFlags>
 __device__ __forceinline__ void put_result(const SfxParams& p, uint64_t pos, uint32_t pid) {
     p.out[pos] = uint16_t(pid);
-    if (p.flags != nullptr && is_long(p, pid)) flag_set(p, pos, true);
+    if constexpr (kFlags) { if (is_long(p, pid)) flag_set(p, pos, true); }
 }
 
 // Where the main kernel finds its tables.  The 2-byte root table sits in shared memory (LSU pipe); the rows of
@@ -434,7 +437,7 @@ __device__ __forceinline__ uint64_t load8_merge(const uint8_t* a, uint64_t hi, u
     return sh == 56 ? hi : ((hi << (56 - sh)) | (lo >> (sh + 8)));
 }
 
-template <bool kIdentCls>
+template <bool kIdentCls, bool kFlags>
 __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
     __shared__ uint32_t s_tails, s_next_a, s_next_b;   // tail items so far; next unclaimed item of each phase
     uint64_t* q_strip = p.queue + size_t(blockIdx.x) * p.q_per_cta;
@@ -493,10 +496,10 @@ __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
                     if (v[s] & kTail) {  // hand over to phase B
                         const uint32_t t = atomicAdd(&s_tails, 1u);
                         if (t < cap_tails) q_strip[p.q_per_cta - 1 - t] = (pos[s] << 25) | (uint32_t(k[s]) << 16) | (v[s] & 0xFFFFu);
-                        else put_result(p, pos[s], sfx_finish(p, v[s], k[s], p.stream + pos[s], avail));  // strip full
+                        else put_result<kFlags>(p, pos[s], sfx_finish(p, v[s], k[s], p.stream + pos[s], avail));  // strip full
                         st[s] = kIdle;
                     } else if (!(v[s] & kCont)) {
-                        put_result(p, pos[s], v[s]);
+                        put_result<kFlags>(p, pos[s], v[s]);
                         st[s] = kIdle;
                     } else if (hist_left[s] == 0) {
                         st[s] = kHist;
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
                 }
                 // the walk needs a byte that does not exist (start of the stream): the row's own best pattern
                 if ((st[s] == kHist || st[s] == kRow) && k[s] >= avail) {
-                    put_result(p, pos[s], __ldg(p.row_best + (v[s] & 0xFFFFFFu)));
+                    put_result<kFlags>(p, pos[s], __ldg(p.row_best + (v[s] & 0xFFFFFFu)));
                     st[s] = kIdle;
                 }
             }
@@ -568,23 +571,23 @@ __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
                     const uint32_t left = lim[s] - k[s];
                     k[s] += same < left ? same : left;
                     if (same < 8 || k[s] >= lim[s]) {
-                        if (k[s] < next_term[s]) { put_result(p, pos[s], best_start[s]); st[s] = kIdle; }       // no further terminal reached
-                        else if (k[s] >= len[s]) { put_result(p, pos[s], pid[s]); st[s] = kIdle; }              // the whole pattern
+                        if (k[s] < next_term[s]) { put_result<kFlags>(p, pos[s], best_start[s]); st[s] = kIdle; }       // no further terminal reached
+                        else if (k[s] >= len[s]) { put_result<kFlags>(p, pos[s], pid[s]); st[s] = kIdle; }              // the whole pattern
                         else st[s] = kChain;   // the longest pattern of the chain with length <= k
                     }
                 } else if (st[s] == kChain) {
                     if (ld_len[s] > k[s]) {
                         pid[s] = ld_par[s];
-                        if (pid[s] == 0) { put_result(p, pos[s], 0); st[s] = kIdle; }
+                        if (pid[s] == 0) { put_result<kFlags>(p, pos[s], 0); st[s] = kIdle; }
                     } else {
-                        put_result(p, pos[s], pid[s]);
+                        put_result<kFlags>(p, pos[s], pid[s]);
                         st[s] = kIdle;
                     }
                 }
                 // a tail item that cannot advance at all (k already at its limit) is resolved by the same rules
                 if (st[s] == kCmp && k[s] >= lim[s]) {
-                    if (k[s] < next_term[s]) { put_result(p, pos[s], best_start[s]); st[s] = kIdle; }
-                    else if (k[s] >= len[s]) { put_result(p, pos[s], pid[s]); st[s] = kIdle; }
+                    if (k[s] < next_term[s]) { put_result<kFlags>(p, pos[s], best_start[s]); st[s] = kIdle; }
+                    else if (k[s] >= len[s]) { put_result<kFlags>(p, pos[s], pid[s]); st[s] = kIdle; }
                     else st[s] = kChain;
                 }
             }
@@ -648,7 +651,8 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
         ++*launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        auto deep = ident_cls ? sfx_deep_kernel<true> : sfx_deep_kernel<false>;
+        auto deep = p.flags != nullptr ? (ident_cls ? sfx_deep_kernel<true, true> : sfx_deep_kernel<false, true>)
+                                       : (ident_cls ? sfx_deep_kernel<true, false> : sfx_deep_kernel<false, false>);
         deep<<<grid, 1024, 0, st>>>(p);  // CTA b drains the strip of scan CTA b
         ++*launches;
         e = cudaGetLastError();
