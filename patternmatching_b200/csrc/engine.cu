@@ -57,6 +57,7 @@ constexpr size_t kMaxCtas = 1024;  // upper bound of scan CTAs per launch (one p
 constexpr size_t kPatPad = 16;  // zero bytes in front of the device copy of the pattern text (8-byte windows)
 constexpr size_t kSmallCall = size_t(256) << 10;   // host calls up to this many bytes take the single-launch path
 constexpr size_t kPageableChunk = size_t(4) << 20; // pipeline piece when a buffer has to be staged by host threads
+constexpr int kSlots = 4;   // pipeline slots of the host path: pieces on the GPU + pieces being unloaded by the host threads
 constexpr size_t kQueueMaxPerCta = size_t(256) << 10;  // deferred-walk slots per scan CTA (2 MiB); beyond that walks finish inline
 
 // Diagnostic / A-B switches, read ONCE when an engine is created.
@@ -65,6 +66,7 @@ struct EngineOpts {
     uint32_t l3_min = 4, l3_min_b = 4;
     size_t host_chunk = size_t(16) << 20;  // bytes per pipeline slot for pinned buffers (PM_HOST_CHUNK_MIB)
     int host_threads = 0;                  // staging threads (PM_HOST_THREADS; default: half the host's cores, at most 16)
+    int ids_on_device = -1;                // PM_HOST_IDS=device|host: where pids become 8-byte ids for page-locked result buffers (-1 = by thread count)
     static EngineOpts from_env() {
         EngineOpts o;
         o.sfx_no_tex = getenv("PM_SFX_NO_TEX") != nullptr;
@@ -81,6 +83,7 @@ struct EngineOpts {
         const unsigned hw = std::thread::hardware_concurrency();
         o.host_threads = int(std::max(1u, std::min<unsigned>((hw ? hw : 2) / 2, 16)));
         if (const char* v = getenv("PM_HOST_THREADS")) { const int t = atoi(v); if (t >= 1 && t <= 256) o.host_threads = t; }
+        if (const char* v = getenv("PM_HOST_IDS")) o.ids_on_device = (v[0] == 'd') ? 1 : 0;
         return o;
     }
 };
@@ -131,10 +134,10 @@ struct pm_engine {
     uint32_t* d_flags = nullptr;          // sparse mode: one bit per position (pm_engine_scan_device_records), grown on demand
     size_t flags_words = 0;
     // deferred-walk queues of the sfx scan, one per pipeline slot (slot 0 also serves pm_engine_scan_device)
-    uint64_t* d_queue[2] = {nullptr, nullptr};
-    uint32_t* d_qcount = nullptr;         // 2 x 2 x kMaxCtas counters
-    size_t queue_cap[2] = {0, 0};
-    size_t last_ctas[2] = {0, 0};         // scan CTAs of the last sfx launch that used the slot
+    uint64_t* d_queue[kSlots] = {};
+    uint32_t* d_qcount = nullptr;         // kSlots x 2 x kMaxCtas counters
+    size_t queue_cap[kSlots] = {};
+    size_t last_ctas[kSlots] = {};        // scan CTAs of the last sfx launch that used the slot
     // slot-0 scratch is shared by successive pm_engine_scan_device calls whatever stream they are given: the next
     // call waits (on the device) for the previous one through this event
     cudaEvent_t scratch_free = nullptr;
@@ -149,19 +152,19 @@ struct pm_engine {
     size_t prof_used = 0;
     // host pipeline (lazy)
     bool pipe_ready = false;
-    uint8_t* d_in[2] = {nullptr, nullptr};
-    uint16_t* d_out[2] = {nullptr, nullptr};
-    uint8_t* h_in[2] = {nullptr, nullptr};
-    uint16_t* h_out[2] = {nullptr, nullptr};
-    cudaStream_t st[2] = {nullptr, nullptr};
-    cudaEvent_t done[2] = {nullptr, nullptr};
+    uint8_t* d_in[kSlots] = {};
+    uint16_t* d_out[kSlots] = {};
+    uint8_t* h_in[kSlots] = {};
+    uint16_t* h_out[kSlots] = {};
+    cudaStream_t st[kSlots] = {};
+    cudaEvent_t done[kSlots] = {};
     std::unique_ptr<pm::HostPool> pool;
     // pid -> caller's id translated on the device (page-locked result buffers): the table and per-slot id buffers
     unsigned long long* d_id_table = nullptr;
     const uint64_t* id_table_src = nullptr;   // host table last uploaded (re-uploaded when pointer or contents change)
     uint64_t id_table_sum = 0;
     size_t id_table_n = 0;
-    unsigned long long* d_ids[2] = {nullptr, nullptr};
+    unsigned long long* d_ids[kSlots] = {};
     // record path of the host pipeline (lazy)
     uint64_t* d_rec[2] = {nullptr, nullptr};
     unsigned long long* d_rec_counts[2] = {nullptr, nullptr};
@@ -216,7 +219,7 @@ int ensure_kr(pm_engine* e) {
 int ensure_pipe(pm_engine* e) {
     if (e->pipe_ready) return 0;
     const size_t chunk = e->opts.host_chunk;
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kSlots; ++b) {
         CU(cudaMalloc(reinterpret_cast<void**>(&e->d_in[b]), e->halo + chunk + 16));
         CU(cudaMalloc(reinterpret_cast<void**>(&e->d_out[b]), chunk * sizeof(uint16_t)));
         CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_in[b]), e->halo + chunk));
@@ -232,7 +235,7 @@ int ensure_pipe(pm_engine* e) {
 
 // both pipeline streams idle: nothing is in flight into a caller's buffer any more (called before an error return)
 void quiesce(pm_engine* e) {
-    for (int b = 0; b < 2; ++b) if (e->st[b]) cudaStreamSynchronize(e->st[b]);
+    for (int b = 0; b < kSlots; ++b) if (e->st[b]) cudaStreamSynchronize(e->st[b]);
 }
 
 bool is_pinned(const void* p) {
@@ -483,9 +486,12 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
     const size_t H = e->halo;
     const bool in_pinned = is_pinned(stream);
     const bool direct_out = sink.out16 && is_pinned(sink.out16);   // the D2H copy lands in the caller's buffer
-    // 8-byte ids into a page-locked buffer: translated on the device and sent by DMA (8 B per position over PCIe, no
-    // host thread touches them); into a pageable buffer: 2 B per position over PCIe, translated by the host threads
-    const bool device_ids = sink.out64 && is_pinned(sink.out64) && (reinterpret_cast<uintptr_t>(sink.out64) & 15) == 0;
+    // 8-byte ids: translated by the host threads from the 2-byte pids (2 B per position over PCIe; the box's host writes
+    // 107-131 GB/s of ids with 8-16 threads, scripts/microbench/host_mem.cpp), or -- into a page-locked buffer, when the
+    // engine has fewer than four host threads (or PM_HOST_IDS=device) -- translated on the device and sent by DMA (8 B per
+    // position over PCIe: 6-7 GB/s of stream at most)
+    const bool ids_pinned = sink.out64 && is_pinned(sink.out64) && (reinterpret_cast<uintptr_t>(sink.out64) & 15) == 0;
+    const bool device_ids = ids_pinned && (e->opts.ids_on_device >= 0 ? e->opts.ids_on_device == 1 : e->opts.host_threads < 4);
     if (device_ids) {
         uint64_t sum = 0;
         const size_t tn = e->dict->pats.size() + 1;
@@ -496,53 +502,54 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
             CU(cudaMemcpy(e->d_id_table, sink.table, tn * sizeof(uint64_t), cudaMemcpyHostToDevice));
             e->id_table_n = tn; e->id_table_src = sink.table; e->id_table_sum = sum;
         }
-        for (int b = 0; b < 2; ++b)
+        for (int b = 0; b < kSlots; ++b)
             if (!e->d_ids[b]) {
                 CU(cudaMalloc(reinterpret_cast<void**>(&e->d_ids[b]), e->opts.host_chunk * sizeof(uint64_t)));
                 e->scratch_bytes += e->opts.host_chunk * sizeof(uint64_t);
             }
     }
-    // Pageable buffers are staged through the pinned ones by the pool's threads, in smaller pieces so that staging
-    // piece k+1 and unloading piece k-1 overlap the transfers and the scan of piece k.
-    // When host threads have work to do, a call is cut into at least ~8 pieces (512 KiB .. 4 MiB) so that the exposed
-    // first stage-in and last unload stay a small part of it.
+    // What the host threads have to do per piece: stage its bytes into pinned memory (pageable stream) and unload its
+    // results (translate to ids, or copy the pids into a pageable buffer).  Such calls are cut into at least ~8 pieces
+    // (512 KiB .. 4 MiB) so that the exposed first stage-in and last unload stay a small part of the call.
+    const bool do_stage = !in_pinned;
+    const bool do_unload = !device_ids && (sink.out64 != nullptr || !direct_out);
     size_t chunk = e->opts.host_chunk;
-    if (!(in_pinned && (direct_out || device_ids))) {
+    if (do_stage || do_unload) {
         chunk = std::min(chunk, kPageableChunk);
         while (chunk > (size_t(512) << 10) && n / chunk < 8) chunk >>= 1;
     }
     const size_t n_chunks = (n + chunk - 1) / chunk;
     pm::HostPool& pool = *e->pool;
-    // One pool run per pipeline step does BOTH host copies that are due: unloading piece k-2 (translate / copy its
-    // results out of the pinned buffer) and staging piece k (copy its bytes into the pinned buffer) -- every wake-up of
-    // the workers costs tens of microseconds, comparable to the copies themselves for small pieces.
-    auto host_step = [&](bool unload, size_t ku, bool stage, size_t ks) {
-        const size_t ou = ku * chunk, lenu = unload ? std::min(chunk, n - ou) : 0;
-        const size_t os = ks * chunk, lens = stage ? std::min(chunk, n - os) : 0;
-        const size_t from_call = stage ? std::min(os, H) : 0;
-        const uint16_t* res = e->h_out[ku & 1];
-        const bool do_unload = unload && !device_ids && (sink.out64 || !direct_out);
-        const bool do_stage = stage && !in_pinned;
-        if (!do_unload && !do_stage) return;
-        auto work = [&](int part, int parts) {
-            size_t lo, hi;
-            if (do_unload) {
-                pm::HostPool::slice(lenu, part, parts, 512, &lo, &hi);
-                if (hi > lo) {
-                    if (sink.out64) pm::HostPool::expand_range(res, lo, hi, sink.table, sink.out64 + ou);
-                    else memcpy(sink.out16 + ou + lo, res + lo, (hi - lo) * sizeof(uint16_t));
-                }
-            }
-            if (do_stage) {
-                pm::HostPool::slice(from_call + lens, part, parts, 4096, &lo, &hi);
-                if (hi > lo) memcpy(e->h_in[ks & 1] + lo, stream + os - from_call + lo, hi - lo);
-            }
-        };
-        if (lenu + lens < (size_t(128) << 10)) work(0, 1);   // not worth waking anybody
-        else pool.run(work);
+    // The pipeline: piece k is staged by the pool (job), then copied in / scanned / copied out on stream k % kSlots;
+    // two pieces later its results have arrived and the pool unloads them (another job) while the GPU works on the next
+    // pieces; its slot is reused by piece k + kSlots once that job is done.  Jobs are asynchronous (host_pool.hpp): the
+    // calling thread only waits for the one it needs next, and works on it while it waits.
+    constexpr size_t kLag = 2;   // pieces submitted to the GPU before the oldest one is unloaded
+    static_assert(kLag < size_t(kSlots), "a slot's results are unloaded before the slot is reused");
+    pm::HostPool::Ticket staged[kSlots], unloaded[kSlots];
+    auto drain = [&]() {   // nothing of this call is in flight any more: streams idle, no job touches the caller's buffers
+        quiesce(e);
+        for (int b = 0; b < kSlots; ++b) { pool.wait(staged[b]); pool.wait(unloaded[b]); }
+    };
+    auto stage = [&](size_t k) {
+        const size_t o = k * chunk, len = std::min(chunk, n - o), from_call = std::min(o, H);
+        uint8_t* dst = e->h_in[k % kSlots];
+        const uint8_t* src = stream + o - from_call;
+        return pool.submit(from_call + len, size_t(256) << 10, [dst, src](size_t lo, size_t hi) { memcpy(dst + lo, src + lo, hi - lo); });
+    };
+    auto unload = [&](size_t k) {
+        const size_t o = k * chunk, len = std::min(chunk, n - o);
+        const uint16_t* res = e->h_out[k % kSlots];
+        if (sink.out64) {
+            uint64_t* dst = sink.out64 + o;
+            const uint64_t* table = sink.table;
+            return pool.submit(len, size_t(64) << 10, [res, table, dst](size_t lo, size_t hi) { pm::HostPool::expand_range(res, lo, hi, table, dst); });
+        }
+        uint16_t* dst = sink.out16 + o;
+        return pool.submit(len, size_t(256) << 10, [res, dst](size_t lo, size_t hi) { memcpy(dst + lo, res + lo, (hi - lo) * sizeof(uint16_t)); });
     };
     auto submit = [&](size_t k) -> int {   // piece k is staged (or pinned in place): enqueue copy in, scan, copy out
-        const int b = int(k & 1);
+        const int b = int(k % kSlots);
         const size_t o = k * chunk, len = std::min(chunk, n - o);
         // history in front of the chunk: from this call's own bytes when there are enough, else the carried tail
         const size_t from_call = std::min(o, H);
@@ -563,15 +570,26 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
         CU(cudaEventRecord(e->done[b], e->st[b]));
         return 0;
     };
-    for (size_t k = 0; k < n_chunks + 2; ++k) {
-        const bool unload = k >= 2, stage = k < n_chunks;
-        if (unload) {   // piece k-2 has left the device (its slot's buffers are reused by piece k)
-            cudaError_t ce = cudaEventSynchronize(e->done[k & 1]);
-            if (ce != cudaSuccess) { quiesce(e); return cuda_fail(ce, "cudaEventSynchronize"); }
+    for (size_t k = 0; k < n_chunks + kLag; ++k) {
+        const int b = int(k % kSlots);
+        // (a) stage piece k: its slot's pinned input was consumed by piece k - kSlots, whose completion was awaited at
+        //     step k - kSlots + kLag
+        if (k < n_chunks && do_stage) staged[b] = stage(k);
+        // (b) piece k - kLag has left the device: hand its results to the pool
+        if (k >= kLag) {
+            const size_t ku = k - kLag;
+            cudaError_t ce = cudaEventSynchronize(e->done[ku % kSlots]);
+            if (ce != cudaSuccess) { drain(); return cuda_fail(ce, "cudaEventSynchronize"); }
+            if (do_unload) unloaded[ku % kSlots] = unload(ku);
         }
-        host_step(unload, k - 2, stage, k);
-        if (stage && submit(k)) { quiesce(e); return -1; }
+        // (c) piece k goes to the GPU once the previous user of its slot has been unloaded and its own bytes are staged
+        if (k < n_chunks) {
+            pool.wait(unloaded[b]); unloaded[b].reset();
+            pool.wait(staged[b]); staged[b].reset();
+            if (submit(k)) { drain(); return -1; }
+        }
     }
+    for (int b = 0; b < kSlots; ++b) pool.wait(unloaded[b]);
     carry_history(e, stream, n);
     return 0;
 }
@@ -755,7 +773,7 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
         if (cudaCreateTextureObject(&e->rows_tex, &rd, &td, nullptr) != cudaSuccess) { e->rows_tex = 0; cudaGetLastError(); }
     }
     if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_acc), 8 * sizeof(unsigned long long)) != cudaSuccess) ok = false;
-    if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_qcount), 4 * kMaxCtas * sizeof(uint32_t)) != cudaSuccess) ok = false;
+    if (ok && cudaMalloc(reinterpret_cast<void**>(&e->d_qcount), size_t(kSlots) * 2 * kMaxCtas * sizeof(uint32_t)) != cudaSuccess) ok = false;
     if (ok && cudaEventCreateWithFlags(&e->scratch_free, cudaEventDisableTiming) != cudaSuccess) ok = false;
     if (!ok) { if (g_err.empty()) cuda_fail(cudaGetLastError(), "pm_engine_create"); pm_engine_free(e); return nullptr; }
     e->pt.n_patterns = uint32_t(P);
@@ -773,8 +791,16 @@ void pm_engine_free(pm_engine* e) {
     if (e->rows_tex) cudaDestroyTextureObject(e->rows_tex);
     void* ptrs[] = {e->d_root2, e->d_root1, e->d_rows, e->d_row_best, e->d_cls, e->d_pat_off, e->d_pat_len, e->d_pat_bytes,
                     e->d_parent, e->d_chain, e->d_pidhash, e->d_tail_rec, e->d_l3f, e->d_anc_off, e->d_anc_list, e->d_sample_out, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_fb_meta, e->d_deep_hot, e->d_deep_long, e->d_deep_recs, e->d_deep_dense, e->d_acc,
-                    e->d_compact_counts, e->d_flags, e->d_id_table, e->d_ids[0], e->d_ids[1], e->d_in[0], e->d_in[1], e->d_out[0], e->d_out[1], e->d_queue[0], e->d_queue[1], e->d_qcount};
+                    e->d_compact_counts, e->d_flags, e->d_id_table, e->d_qcount};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (int b = 0; b < kSlots; ++b) {
+        void* slot_ptrs[] = {e->d_ids[b], e->d_in[b], e->d_out[b], e->d_queue[b]};
+        for (void* p : slot_ptrs) if (p) cudaFree(p);
+        if (e->h_in[b]) cudaFreeHost(e->h_in[b]);
+        if (e->h_out[b]) cudaFreeHost(e->h_out[b]);
+        if (e->st[b]) cudaStreamDestroy(e->st[b]);
+        if (e->done[b]) cudaEventDestroy(e->done[b]);
+    }
     pm::kr_free_tables(&e->kr);
     for (cudaEvent_t x : e->prof_events) cudaEventDestroy(x);
     if (e->scratch_free) cudaEventDestroy(e->scratch_free);
@@ -783,10 +809,6 @@ void pm_engine_free(pm_engine* e) {
         if (e->d_rec_counts[b]) cudaFree(e->d_rec_counts[b]);
         if (e->d_rec_flags[b]) cudaFree(e->d_rec_flags[b]);
         if (e->h_rec_total[b]) cudaFreeHost(e->h_rec_total[b]);
-        if (e->h_in[b]) cudaFreeHost(e->h_in[b]);
-        if (e->h_out[b]) cudaFreeHost(e->h_out[b]);
-        if (e->st[b]) cudaStreamDestroy(e->st[b]);
-        if (e->done[b]) cudaEventDestroy(e->done[b]);
     }
     delete e;
 }
