@@ -92,7 +92,12 @@ enum {
     PM_ALGO_SFX = 0, /* exact: per-position backward walk of the reversed-pattern trie (default) */
     PM_ALGO_DFA = 1, /* exact: per-thread forward walk of the flat Aho-Corasick DFA */
     PM_ALGO_KR  = 2, /* randomized: Karp-Rabin suffix-stage fingerprints (mpbg/bgps/kmprt style) */
-    PM_ALGO_AUTO = 3 /* exact: SFX unless a sample of the stream shows deep walks (then DFA); see pm_engine_auto_choice */
+    PM_ALGO_AUTO = 3, /* exact: SFX unless a sample of the stream shows deep walks (then DFA); see pm_engine_auto_choice */
+    /* The reference's MPBG as shipped (Core/src/mpbg.c:132-145), position for position: its fingerprint stages never fire
+     * (SURVEY Q5), so it reports the longest pattern of <= 8 bytes ending at each position (the patterns its exact KMP
+     * path handles, Core/src/bgps.c:459-464).  Deterministic, pinned by tests/golden/ref_snort.json (mpbg_file / mpbg_line:
+     * the reference's own per-position output).  PM_ALGO_KR is the repaired variant (patterns > 8 bytes by fingerprints). */
+    PM_ALGO_MPBG = 5
 };
 enum {
     PM_STREAM_UNIFORM = 0, /* uniform bytes (splitmix64 counter generator) */
@@ -263,6 +268,7 @@ size_t gpu_read_block(void* obj, const char* buf, size_t n, void** out);
 /* same object, other kernels behind it */
 void* gpu_dfa_create(void);
 void* gpu_kr_create(void);
+void* gpu_mpbg_create(void);
 
 /* Layout-compatible with MpsElem (Core/src/mps.h:71-80); pattern_id_t spelled void*. */
 typedef struct {
@@ -280,6 +286,7 @@ typedef struct {
 void mps_gpu_register_into(pm_mps_elem* slot);     /* exact, suffix-trie scan   */
 void mps_gpu_dfa_register_into(pm_mps_elem* slot); /* exact, forward DFA walker */
 void mps_gpu_kr_register_into(pm_mps_elem* slot);  /* randomized Karp-Rabin     */
+void mps_gpu_mpbg_register_into(pm_mps_elem* slot); /* PM_ALGO_MPBG: what the reference's MPBG reports */
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpm_b200.so")
 
 ALGO_SFX, ALGO_DFA, ALGO_KR, ALGO_AUTO = 0, 1, 2, 3
-ALGOS = {"sfx": ALGO_SFX, "dfa": ALGO_DFA, "kr": ALGO_KR, "auto": ALGO_AUTO}
+ALGO_MPBG = 5   # the reference's MPBG as shipped, position for position (pm_b200.h: PM_ALGO_MPBG)
+ALGOS = {"sfx": ALGO_SFX, "dfa": ALGO_DFA, "kr": ALGO_KR, "auto": ALGO_AUTO, "mpbg": ALGO_MPBG}
 STREAM_UNIFORM, STREAM_PLANTED, STREAM_ALMOST, STREAM_AB = 0, 1, 2, 3
 STREAMS = {"uniform": 0, "planted": 1, "almost": 2, "ab": 3, "ascii": 4}
 HALO = 352  # bytes of history that make a shard scan identical to the continuous scan (>= max_pat_len-1)
@@ -109,7 +110,7 @@ def lib():
         "pm_host_free": (None, [vp]),
         "pm_host_register": (C.c_int, [vp, sz]),
         "pm_host_unregister": (C.c_int, [vp]),
-        "gpu_create": (vp, []), "gpu_dfa_create": (vp, []), "gpu_kr_create": (vp, []),
+        "gpu_create": (vp, []), "gpu_dfa_create": (vp, []), "gpu_kr_create": (vp, []), "gpu_mpbg_create": (vp, []),
         "gpu_add_pattern": (None, [vp, C.c_char_p, sz, vp]),
         "gpu_compile": (None, [vp]),
         "gpu_read_char": (vp, [vp, C.c_char]),
@@ -120,6 +121,7 @@ def lib():
         "mps_gpu_register_into": (None, [C.POINTER(MpsElemStruct)]),
         "mps_gpu_dfa_register_into": (None, [C.POINTER(MpsElemStruct)]),
         "mps_gpu_kr_register_into": (None, [C.POINTER(MpsElemStruct)]),
+        "mps_gpu_mpbg_register_into": (None, [C.POINTER(MpsElemStruct)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -491,7 +493,7 @@ class MpsGpu:
     ``pattern ids`` are opaque non-zero integers (pattern_id_t is a pointer in the reference;
     0 / None is null_pattern_id)."""
 
-    _CREATE = {"sfx": "gpu_create", "dfa": "gpu_dfa_create", "kr": "gpu_kr_create"}
+    _CREATE = {"sfx": "gpu_create", "dfa": "gpu_dfa_create", "kr": "gpu_kr_create", "mpbg": "gpu_mpbg_create"}
 
     def __init__(self, algo="sfx"):
         self.L = lib()

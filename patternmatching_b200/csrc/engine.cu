@@ -66,7 +66,10 @@ struct EngineOpts {
     uint32_t l3_min = 4, l3_min_b = 4;
     size_t host_chunk = size_t(16) << 20;  // bytes per pipeline slot for pinned buffers (PM_HOST_CHUNK_MIB)
     int host_threads = 0;                  // staging threads (PM_HOST_THREADS; default: half the host's cores, at most 16)
-    int ids_on_device = -1;                // PM_HOST_IDS=device|host: where pids become 8-byte ids for page-locked result buffers (-1 = by thread count)
+    // PM_HOST_IDS=device|host|<N>: where pids become 8-byte ids when the result buffer is page-locked: every piece on the
+    // device (1), every piece by the host threads (0), or every N-th piece on the device and the rest by the host threads
+    // (both resources at once: the PCIe link and the host's store bandwidth); -1 = chosen from the thread count
+    int ids_device_every = -1;
     static EngineOpts from_env() {
         EngineOpts o;
         o.sfx_no_tex = getenv("PM_SFX_NO_TEX") != nullptr;
@@ -83,7 +86,7 @@ struct EngineOpts {
         const unsigned hw = std::thread::hardware_concurrency();
         o.host_threads = int(std::max(1u, std::min<unsigned>((hw ? hw : 2) / 2, 16)));
         if (const char* v = getenv("PM_HOST_THREADS")) { const int t = atoi(v); if (t >= 1 && t <= 256) o.host_threads = t; }
-        if (const char* v = getenv("PM_HOST_IDS")) o.ids_on_device = (v[0] == 'd') ? 1 : 0;
+        if (const char* v = getenv("PM_HOST_IDS")) o.ids_device_every = v[0] == 'd' ? 1 : v[0] == 'h' ? 0 : std::max(0, atoi(v));
         return o;
     }
 };
@@ -165,6 +168,7 @@ struct pm_engine {
     uint64_t id_table_sum = 0;
     size_t id_table_n = 0;
     unsigned long long* d_ids[kSlots] = {};
+    size_t ids_cap = 0;                       // positions per d_ids buffer
     // record path of the host pipeline (lazy)
     uint64_t* d_rec[2] = {nullptr, nullptr};
     unsigned long long* d_rec_counts[2] = {nullptr, nullptr};
@@ -316,6 +320,15 @@ int choose_algo(pm_engine* e, const uint8_t* d_stream, size_t n, size_t hist_val
 int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid, uint16_t* d_out,
                      cudaStream_t st, int slot) {
     if (n == 0) return 0;
+    if (algo == PM_ALGO_MPBG) {
+        // the reference's MPBG, position for position: exact scan, then every answer demoted to the longest pattern of
+        // <= 8 bytes on its PatternsTree chain (short_only_kernel; pinned by tests/golden/ref_snort.json: mpbg_file/line)
+        if (ensure_kr(e)) return -1;
+        if (scan_device_impl(e, PM_ALGO_SFX, d_stream, n, hist_valid, d_out, st, slot)) return -1;
+        cudaError_t ce = pm::kr_short_only_launch(e->kr, d_out, n, e->n_sms, st, &e->launches);
+        if (ce != cudaSuccess) return cuda_fail(ce, "kr_short_only_launch");
+        return 0;
+    }
     bool force_flat = false;
     if (algo == PM_ALGO_AUTO && !e->dict->sfx.fits_u16) algo = PM_ALGO_SFX;   // routed to the forward walkers below
     if (algo == PM_ALGO_AUTO) {
@@ -477,7 +490,7 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
     if (n == 0) return 0;
     if (ensure_pipe(e)) return -1;
     if (algo == PM_ALGO_DFA && ensure_dfa(e)) return -1;
-    if (algo == PM_ALGO_KR && ensure_kr(e)) return -1;
+    if ((algo == PM_ALGO_KR || algo == PM_ALGO_MPBG) && ensure_kr(e)) return -1;
     if (n <= kSmallCall && (algo == PM_ALGO_SFX || algo == PM_ALGO_AUTO) && e->dict->sfx.fits_u16) {
         if (scan_host_small(e, stream, n, sink)) { quiesce(e); return -1; }
         carry_history(e, stream, n);
@@ -491,8 +504,15 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
     // engine has fewer than four host threads (or PM_HOST_IDS=device) -- translated on the device and sent by DMA (8 B per
     // position over PCIe: 6-7 GB/s of stream at most)
     const bool ids_pinned = sink.out64 && is_pinned(sink.out64) && (reinterpret_cast<uintptr_t>(sink.out64) & 15) == 0;
-    const bool device_ids = ids_pinned && (e->opts.ids_on_device >= 0 ? e->opts.ids_on_device == 1 : e->opts.host_threads < 4);
-    if (device_ids) {
+    // every dev_every-th piece is translated on the device (0 = none, 1 = all).  Default: none with >= 4 host threads.
+    // Mixing the two was measured on the B200 box (1 GiB, page-locked buffers, 8 / 12 threads): host only 10.8 / 12.2 GB/s,
+    // every 5th piece on the device 11.2 / 10.4, every 3rd 9.5 / 9.5, device only 6.3 / 6.3 -- the DMA writes of 8-byte
+    // ids compete with the host threads for the same memory system, so the mix gains nothing.
+    const size_t dev_every = !ids_pinned ? 0 : e->opts.ids_device_every >= 0 ? size_t(e->opts.ids_device_every)
+                                             : (e->opts.host_threads < 4 ? 1 : 0);
+    const bool device_ids = dev_every == 1;
+    auto dev_piece = [&](size_t k) { return dev_every != 0 && k % dev_every == dev_every - 1; };
+    if (dev_every != 0) {
         uint64_t sum = 0;
         const size_t tn = e->dict->pats.size() + 1;
         for (size_t i = 0; i < tn; ++i) sum = sum * 1099511628211ull + sink.table[i];
@@ -502,11 +522,6 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
             CU(cudaMemcpy(e->d_id_table, sink.table, tn * sizeof(uint64_t), cudaMemcpyHostToDevice));
             e->id_table_n = tn; e->id_table_src = sink.table; e->id_table_sum = sum;
         }
-        for (int b = 0; b < kSlots; ++b)
-            if (!e->d_ids[b]) {
-                CU(cudaMalloc(reinterpret_cast<void**>(&e->d_ids[b]), e->opts.host_chunk * sizeof(uint64_t)));
-                e->scratch_bytes += e->opts.host_chunk * sizeof(uint64_t);
-            }
     }
     // What the host threads have to do per piece: stage its bytes into pinned memory (pageable stream) and unload its
     // results (translate to ids, or copy the pids into a pageable buffer).  Such calls are cut into at least ~8 pieces
@@ -519,6 +534,15 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
         while (chunk > (size_t(512) << 10) && n / chunk < 8) chunk >>= 1;
     }
     const size_t n_chunks = (n + chunk - 1) / chunk;
+    if (dev_every != 0 && e->ids_cap < chunk) {   // per-slot id buffers of the pieces translated on the device
+        quiesce(e);
+        for (int b = 0; b < kSlots; ++b) {
+            if (e->d_ids[b]) { CU(cudaFree(e->d_ids[b])); e->d_ids[b] = nullptr; }
+            CU(cudaMalloc(reinterpret_cast<void**>(&e->d_ids[b]), chunk * sizeof(uint64_t)));
+        }
+        e->scratch_bytes += (chunk - e->ids_cap) * sizeof(uint64_t) * kSlots;
+        e->ids_cap = chunk;
+    }
     pm::HostPool& pool = *e->pool;
     // The pipeline: piece k is staged by the pool (job), then copied in / scanned / copied out on stream k % kSlots;
     // two pieces later its results have arrived and the pool unloads them (another job) while the GPU works on the next
@@ -560,7 +584,7 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
         const uint8_t* src = in_pinned ? stream + o - from_call : e->h_in[b];
         CU(cudaMemcpyAsync(din + H - from_call, src, from_call + len, cudaMemcpyHostToDevice, e->st[b]));
         if (scan_device_impl(e, algo, din + H, len, hist_total, e->d_out[b], e->st[b], b)) return -1;
-        if (device_ids) {
+        if (dev_piece(k)) {
             cudaError_t ce = pm::expand_ids_launch(e->d_out[b], len, e->d_id_table, e->d_ids[b], e->n_sms, e->st[b], &e->launches);
             if (ce != cudaSuccess) return cuda_fail(ce, "expand_ids_launch");
             CU(cudaMemcpyAsync(sink.out64 + o, e->d_ids[b], len * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->st[b]));
@@ -580,7 +604,7 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
             const size_t ku = k - kLag;
             cudaError_t ce = cudaEventSynchronize(e->done[ku % kSlots]);
             if (ce != cudaSuccess) { drain(); return cuda_fail(ce, "cudaEventSynchronize"); }
-            if (do_unload) unloaded[ku % kSlots] = unload(ku);
+            if (do_unload && !dev_piece(ku)) unloaded[ku % kSlots] = unload(ku);
         }
         // (c) piece k goes to the GPU once the previous user of its slot has been unloaded and its own bytes are staged
         if (k < n_chunks) {

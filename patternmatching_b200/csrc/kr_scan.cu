@@ -197,7 +197,34 @@ __global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) 
     }
 }
 
+// The reference's MPBG as shipped (Core/src/mpbg.c:132-145): its fingerprint stages never fire, so what it
+// reports at a position is the longest pattern of <= 8 bytes ending there -- the patterns its exact KMP path handles
+// (bgps.c:459-464).  That is short_of[] of the exact answer: out[i] = short_of[out[i]], eight positions per thread.
+__global__ void __launch_bounds__(256) short_only_kernel(uint16_t* __restrict__ out, uint64_t n, const uint16_t* __restrict__ short_of) {
+    const uint64_t n8 = n / 8;
+    uint4* o8 = reinterpret_cast<uint4*>(out);
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint4 v = o8[i];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t lo = w[k] & 0xFFFFu, hi = w[k] >> 16;
+            w[k] = (lo ? uint32_t(__ldg(short_of + lo)) : 0u) | ((hi ? uint32_t(__ldg(short_of + hi)) : 0u) << 16);
+        }
+        o8[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) { const uint64_t i = n8 * 8 + threadIdx.x; out[i] = __ldg(short_of + out[i]); }
+}
+
 }  // namespace
+
+cudaError_t kr_short_only_launch(const KrDevTables& t, uint16_t* out, uint64_t n, int n_sms, cudaStream_t st, uint64_t* launches) {
+    if (n == 0) return cudaSuccess;
+    const uint64_t want = (n / 8 + 255) / 256 + 1;
+    short_only_kernel<<<uint32_t(want < uint64_t(n_sms) * 8 ? want : uint64_t(n_sms) * 8), 256, 0, st>>>(out, n, t.short_of);
+    ++*launches;
+    return cudaGetLastError();
+}
 
 cudaError_t kr_upload_tables(const Dict& d, const KrTables& k, KrDevTables* t, size_t* bytes) {
     *t = KrDevTables();

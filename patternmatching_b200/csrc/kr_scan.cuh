@@ -28,4 +28,8 @@ void kr_free_tables(KrDevTables* t);
 cudaError_t kr_scan_launch(const KrDevTables& t, const uint8_t* stream, uint64_t n, uint64_t hist_valid, uint16_t* out,
                            const PatTables& pt, int n_sms, cudaStream_t st, uint64_t* launches);
 
+// out[i] = short_of[out[i]] in place: the observable behaviour of the reference's MPBG (only patterns of <= 8 bytes are
+// ever reported, Core/src/mpbg.c:132-145 + SURVEY Q5); `out` holds the exact dense result on entry, 16-byte aligned.
+cudaError_t kr_short_only_launch(const KrDevTables& t, uint16_t* out, uint64_t n, int n_sms, cudaStream_t st, uint64_t* launches);
+
 }  // namespace pm

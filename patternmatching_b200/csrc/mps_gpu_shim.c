@@ -40,6 +40,7 @@ static void* create_with(int algo) {
 void* gpu_create(void) { return create_with(PM_ALGO_AUTO); }  /* exact; picks the kernel from a sample of the stream */
 void* gpu_dfa_create(void) { return create_with(PM_ALGO_DFA); }
 void* gpu_kr_create(void) { return create_with(PM_ALGO_KR); }
+void* gpu_mpbg_create(void) { return create_with(PM_ALGO_MPBG); }   /* the reference's MPBG, position for position */
 
 void gpu_add_pattern(void* obj, char* pat, size_t len, void* pattern_id) {
     GpuMps* g = (GpuMps*)obj;
@@ -109,3 +110,4 @@ static void fill(pm_mps_elem* e, const char* name, void* (*create)(void)) {
 void mps_gpu_register_into(pm_mps_elem* slot) { fill(slot, "B200 exact dictionary scan", gpu_create); }
 void mps_gpu_dfa_register_into(pm_mps_elem* slot) { fill(slot, "B200 Aho-Corasick DFA", gpu_dfa_create); }
 void mps_gpu_kr_register_into(pm_mps_elem* slot) { fill(slot, "B200 Karp-Rabin stages", gpu_kr_create); }
+void mps_gpu_mpbg_register_into(pm_mps_elem* slot) { fill(slot, "B200 MPBG (as shipped)", gpu_mpbg_create); }

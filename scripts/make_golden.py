@@ -57,9 +57,14 @@ def run_config(name):
     ref.pmref_success(1, stream.ctypes.data, n, cnt)
     lmac_counts = list(cnt)
     mpbg_counts = None
+    mf = ml = None
     if algo_mask & 4:
         ref.pmref_success(2, stream.ctypes.data, n, cnt)
         mpbg_counts = list(cnt)
+        # what the reference's MPBG reports at every position (mpbg.c:132-145 as shipped)
+        mf = np.empty(n, np.uint32); ml = np.empty(n, np.uint32)
+        ref.pmref_reset(2)
+        ref.pmref_scan(2, stream.ctypes.data, n, mf.ctypes.data, ml.ctypes.data)
     # reference pattern list
     P = ref.pmref_n_patterns()
     pats = {}
@@ -91,6 +96,18 @@ def run_config(name):
     of = np.where(longest >= 0, files[np.maximum(longest, 0)], 0xFFFFFFFF).astype(np.uint32)
     ol = np.where(longest >= 0, lines[np.maximum(longest, 0)], 0xFFFFFFFF).astype(np.uint32)
     assert np.array_equal(of, fo) and np.array_equal(ol, lo), "oracle longest-match differs from reference"
+    if mf is not None:
+        # The reference's MPBG never reports a pattern of more than 8 bytes (its fingerprint stages do not fire);
+        # patterns of <= 8 bytes go through its exact KMP (bgps.c:459-464).  So its answer is the longest pattern of <= 8
+        # bytes ending at the position = the first pattern of <= 8 bytes on the PatternsTree chain of the AC's answer.
+        want_f = np.full(n, 0xFFFFFFFF, np.uint32); want_l = np.full(n, 0xFFFFFFFF, np.uint32)
+        for i in range(n):
+            q = int(longest[i])
+            while q >= 0 and len(o.pattern(q)[3]) > 8:
+                q = o.pattern(q)[2]
+            if q >= 0:
+                want_f[i], want_l[i] = o.pattern(q)[0], o.pattern(q)[1]
+        assert np.array_equal(want_f, mf) and np.array_equal(want_l, ml), "reference MPBG differs from the <= 8-byte rule"
     s = o.summary(stream)
     assert (s.positions, s.matches, s.fnv) == (pos.value, mat.value, chk.value), (s.positions, s.matches, hex(s.fnv))
     assert (s.hsum_longest, s.hsum_all) == (hs[0], hs[1])
@@ -111,6 +128,9 @@ def run_config(name):
     }
     if algo_mask & 4:
         gold["mpbg_total_mem"] = int(ref.pmref_total_mem(2))
+        # per-position answer of the reference's MPBG, same encoding as longest_*
+        gold["mpbg_file"] = [int(x) if x != 0xFFFFFFFF else -1 for x in mf]
+        gold["mpbg_line"] = [int(x) if x != 0xFFFFFFFF else -1 for x in ml]
     os.makedirs(GOLD, exist_ok=True)
     with open(os.path.join(GOLD, f"ref_{name}.json"), "w") as fh:
         json.dump(gold, fh, separators=(",", ":"))

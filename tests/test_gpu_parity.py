@@ -15,6 +15,49 @@ pytestmark = pytest.mark.gpu
 EXACT = [pm.ALGO_SFX, pm.ALGO_DFA]
 
 
+def test_mpbg_mode_equals_the_reference_mpbg_position_for_position():
+    """PM_ALGO_MPBG against the per-position output of the reference's own mpbg_read_char (mpbg.c:132-145, unmodified
+    sources, config C1) -- tests/golden/ref_snort.json: mpbg_file / mpbg_line -- on the device path, the host path in ragged
+    calls, and through the plugin surface (gpu_mpbg_create)."""
+    gold = json.load(open(os.path.join(GOLDEN, "ref_snort.json")))
+    d = pm.Dictionary()
+    for p in dict_paths("snort"):
+        d.add_file(p)
+    d.compile()
+    eng = pm.Engine(d)
+    stream = np.fromfile(os.path.join(DATA, gold["stream"]), dtype=np.uint8)
+    files, lines = d.id_arrays()
+    gf = np.array(gold["mpbg_file"], np.int64); gl = np.array(gold["mpbg_line"], np.int64)
+
+    def as_ids(got):
+        return np.where(got > 0, files[got].astype(np.int64), -1), np.where(got > 0, lines[got].astype(np.int64), -1)
+
+    f, l = as_ids(gpu_scan(eng, stream, pm.ALGO_MPBG))
+    assert np.array_equal(f, gf) and np.array_equal(l, gl)
+    eng.reset()
+    parts, o = [], 0
+    for k in (1, 7, 1000, 3333, stream.size):
+        k = min(k, stream.size - o)
+        parts.append(eng.scan_host(stream[o:o + k], algo=pm.ALGO_MPBG)); o += k
+    f, l = as_ids(np.concatenate(parts))
+    assert np.array_equal(f, gf) and np.array_equal(l, gl)
+    # its success classification against the exact result reproduces the reference's own counts (results.csv row of MPBG)
+    torch, dev = torch_dev()
+    exact = torch.from_numpy(gpu_scan(eng, stream, pm.ALGO_SFX).view(np.int16).copy()).to(dev)
+    mp = torch.from_numpy(gpu_scan(eng, stream, pm.ALGO_MPBG).view(np.int16).copy()).to(dev)
+    c = eng.classify(mp, exact, stream.size)
+    assert [c["success"], c["partial"], c["false_neg"], c["false_pos"]] == gold["mpbg_vs_ac_counts"]
+    # the plugin object: ids are the opaque values given to add_pattern
+    m = pm.MpsGpu("mpbg")
+    for pid in range(1, d.n_patterns + 1):
+        m.add_pattern(d.pattern(pid)[4], pid)
+    m.compile(); m.reset()
+    got = np.asarray(m.read_block(stream.tobytes()), np.int64)
+    f, l = as_ids(got)
+    assert np.array_equal(f, gf) and np.array_equal(l, gl)
+    m.free()
+
+
 def torch_dev():
     import torch
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"

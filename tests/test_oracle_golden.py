@@ -46,6 +46,10 @@ def test_oracle_matches_reference_golden(name):
             demoted[i] = q
         c = o.classify(demoted, longest)
         assert [c["success"], c["partial"], c["false_neg"], c["false_pos"]] == gold["mpbg_vs_ac_counts"]
+        # ... and, position for position, the reference MPBG's own output (pmref_scan over mpbg_read_char, mpbg.c:132-145)
+        mf = np.where(demoted >= 0, files[np.maximum(demoted, 0)].astype(np.int64), -1)
+        ml = np.where(demoted >= 0, lines[np.maximum(demoted, 0)].astype(np.int64), -1)
+        assert np.array_equal(mf, np.array(gold["mpbg_file"])) and np.array_equal(ml, np.array(gold["mpbg_line"]))
 
 
 def test_parser_quirk_q1():
