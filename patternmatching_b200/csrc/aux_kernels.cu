@@ -79,16 +79,38 @@ __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
     return v;
 }
 
-__global__ void __launch_bounds__(256) summarize_kernel(const uint16_t* __restrict__ out, uint64_t n, uint64_t pos_base,
-                                                       PatTables t, unsigned long long* __restrict__ acc) {
+// One persistent CTA per SM.  What a position costs is the gather of its pattern's digest key: 8 bytes from a 445 KB
+// table (merged dictionary) that no L1 holds -- as plain global loads ~25 L1 wavefronts per warp and position: 58 ms for
+// the 16 GiB result, 9 % of the HBM rate.  The positions of any traffic are dominated by the SHORTEST patterns (the one-
+// and two-byte patterns answer 89 % of the matching positions of binary traffic), so their keys live in shared memory
+// behind a 2-byte pid -> slot map: two shared-memory gathers (~3.5 + ~7 wavefronts) instead of the global one; everything
+// else takes the general path below.
+constexpr int kSumThreads = 1024;
+
+__global__ void __launch_bounds__(kSumThreads, 1) summarize_kernel(const uint16_t* __restrict__ out, uint64_t n, uint64_t pos_base,
+                                                                  PatTables t, unsigned long long* __restrict__ acc) {
+    extern __shared__ __align__(16) uint8_t sum_smem[];
+    uint64_t* s_own = reinterpret_cast<uint64_t*>(sum_smem);
+    uint64_t* s_anc = s_own + t.n_hot;
+    uint16_t* s_map = reinterpret_cast<uint16_t*>(s_anc + t.n_hot);
+    for (uint32_t i = threadIdx.x; i < t.n_hot; i += kSumThreads) { s_own[i] = __ldg(t.hot_own + i); s_anc[i] = __ldg(t.hot_anc + i); }
+    for (uint32_t i = threadIdx.x; i <= t.n_patterns; i += kSumThreads) s_map[i] = __ldg(t.hot_map + i);
+    __syncthreads();
     uint64_t positions = 0, matches = 0, h0 = 0, h1 = 0;
     auto one = [&](uint32_t pid, uint64_t pos) {
         if (!pid) return;
         ++positions;
+        const uint32_t m = s_map[pid];
+        if (m != 0xFFFFu) {
+            const uint64_t own = splitmix64_d(pos ^ s_own[m & 0x7FFFu]);
+            h0 += own; h1 += own; ++matches;
+            if (m & 0x8000u) { h1 += splitmix64_d(pos ^ s_anc[m & 0x7FFFu]); ++matches; }
+            return;
+        }
         const uint64_t own = splitmix64_d(pos ^ __ldg(t.pidhash + pid));
         h0 += own;
         h1 += own;                                      // the range starts with pid itself
-        const uint32_t nanc = __ldg(t.chain + pid);     // 97% of the matches on binary traffic have no ancestor
+        const uint32_t nanc = __ldg(t.chain + pid);
         matches += 1 + nanc;
         if (nanc) {
             const uint32_t b = __ldg(t.anc_off + pid) + 1;
@@ -106,14 +128,14 @@ __global__ void __launch_bounds__(256) summarize_kernel(const uint16_t* __restri
         for (int k = 0; k < 8; ++k) one((w[k >> 1] >> (16 * (k & 1))) & 0xFFFF, pos_base + i * 8 + k);
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 7)) one(out[n8 * 8 + threadIdx.x], pos_base + n8 * 8 + threadIdx.x);
-    __shared__ uint64_t sh[4][8];
+    __shared__ uint64_t sh[4][kSumThreads / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint64_t v[4] = {warp_sum(positions), warp_sum(matches), warp_sum(h0), warp_sum(h1)};
     if (lane == 0) for (int k = 0; k < 4; ++k) sh[k][wid] = v[k];
     __syncthreads();
     if (threadIdx.x < 4) {
         uint64_t s = 0;
-        for (int w = 0; w < 8; ++w) s += sh[threadIdx.x][w];
+        for (int w = 0; w < kSumThreads / 32; ++w) s += sh[threadIdx.x][w];
         atomicAdd(&acc[threadIdx.x], (unsigned long long)s);
     }
 }
@@ -401,9 +423,12 @@ cudaError_t summarize_launch(const uint16_t* out, uint64_t n, uint64_t pos_base,
                              unsigned long long* d_acc4, int n_sms, cudaStream_t st, uint64_t* launches) {
     cudaError_t e = cudaMemsetAsync(d_acc4, 0, 4 * sizeof(unsigned long long), st);
     if (e != cudaSuccess || n == 0) return e;
-    uint64_t want = (n / 8 + 255) / 256 + 1;
-    const uint32_t grid = uint32_t(want < uint64_t(n_sms) * 8 ? want : uint64_t(n_sms) * 8);
-    summarize_kernel<<<grid, 256, 0, st>>>(out, n, pos_base, t, d_acc4);
+    const uint64_t want = (n / 8 + kSumThreads - 1) / kSumThreads + 1;
+    const uint32_t grid = uint32_t(want < uint64_t(n_sms) ? want : uint64_t(n_sms));
+    const size_t smem = size_t(t.n_hot) * 16 + (size_t(t.n_patterns) + 1) * 2 + 16;
+    e = cudaFuncSetAttribute(summarize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    summarize_kernel<<<grid, kSumThreads, smem, st>>>(out, n, pos_base, t, d_acc4);
     ++*launches;
     return cudaGetLastError();
 }

@@ -17,7 +17,15 @@ struct PatTables {
     const uint64_t* pidhash;  // splitmix64(((file+1) << 32) | line), see oracle/pm_oracle.h match_digest
     const uint32_t* anc_off;  // output links flattened to ranges: the patterns ending where pid ends are
     const uint16_t* anc_list; // anc_list[anc_off[pid] .. anc_off[pid+1]) (pid first, then its ancestors)
+    // summary fast path (summarize_kernel keeps these in shared memory): the shortest patterns -- those that match at
+    // most positions of any traffic -- with at most one ancestor.  hot_map[pid] = slot | 0x8000 when the pattern has an
+    // ancestor, 0xFFFF = not in the table; hot_own[slot] = pidhash of the pattern, hot_anc[slot] = pidhash of its ancestor.
+    const uint16_t* hot_map;  // n_patterns + 1 entries
+    const uint64_t* hot_own;
+    const uint64_t* hot_anc;
+    uint32_t n_hot;
 };
+constexpr uint32_t kSummaryHotMax = 3072;   // slots of the summary fast path
 
 cudaError_t generate_launch(int kind, uint64_t off, uint64_t n, uint8_t* dst, const PatTables& t, cudaStream_t st,
                             uint64_t* launches);

@@ -9,14 +9,17 @@
 //   * states are numbered depth-first below depth 2, so a run of single-child states is a run of consecutive ids and
 //     ONE record carries the bytes and longest-pattern ids of up to eight steps of the run (kind CHAIN): following a
 //     pattern's text costs one fetch per eight bytes and a few register shifts per byte;
-//   * a branching state's record holds its goto edges (<= 6; busier states point at a complete 256-entry row), its
-//     failure link and its own longest-pattern id: arriving, reporting and leaving cost one fetch;
-//   * the root and the depth-1 states keep complete DFA rows in shared memory (u16): a failure chain that reaches
-//     them is resolved without another fetch.
+//   * a branching state's record holds its goto edges (<= 6), its failure link and its own longest-pattern id:
+//     arriving, reporting and leaving cost one fetch;
+//   * busier states (DENSE) own a complete 256-entry DFA row and are recognised by their id alone: one 4-byte load per
+//     byte, no record, no failure chain;
+//   * the root and the depth-1 states keep complete DFA rows in shared memory (u16), and so do the longest-pattern ids
+//     of every state a shared-memory row or a DENSE row usually leads to (depth <= 2 and DENSE states).
 // 0.62 record fetches per byte on the C5b stream (tests/test_host_compiler.py prints it), 0.13 on planted traffic.
 //
-// Lanes are independent state machines advanced in warp-wide rounds (see the kernel); stream bytes arrive eight at a
-// time in two registers that are shifted, results leave eight at a time as one 16-byte store.
+// Lanes are independent state machines advanced in warp-wide ROUNDS of one straight-line instruction sequence (see the
+// kernel); stream bytes arrive eight at a time, one group ahead of their use, results leave eight at a time as one
+// 16-byte store.
 #include "deep_scan.cuh"
 #include "pm_dev.cuh"
 
@@ -30,159 +33,161 @@ __device__ __forceinline__ void ldg_rec(const uint32_t* ptr, uint32_t (&w)[8]) {
                  : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(ptr));
 }
 
-struct Walk {
-    uint32_t s;       // current state
-    uint32_t w[8];    // record of s (CHAIN: shifted as the run is consumed), valid when `have`
-    bool have;        // w belongs to s
-    bool head;        // CHAIN: nothing of the record has been consumed yet, so w[0] holds s's own failure link
-};
-
-// Every lane is its own state machine over its own segment, and the warp runs them in ROUNDS: in each round a lane
-// performs at most one record fetch (all lanes that need one issue it with the same load instruction) and then
-// advances as far as it can without another fetch -- at most one stream byte.  A lane whose byte is resolved takes its
-// next byte at once; nobody waits for the lane with the longest failure chain.
-//   Why this shape: resolving one byte takes 1.6 rounds on average on the C5b stream but 4.9 for the slowest of 32
-//   lanes, so a byte-synchronous warp (all lanes on byte k together) wastes two thirds of its rounds; and a per-lane
-//   `for (;;)` with the fetch inside it made the hardware run the lanes' iterations one after the other (1-2 active
-//   lanes per LDG, every latency exposed 32 times).  Both were measured at 45-50 GB/s.
-struct LaneIO {
-    const uint8_t* in;      // stream + s0: positions are 32-bit offsets from the segment start (negative = warm-up)
-    uint16_t* out;          // out + s0
-    int32_t rel, rel_end;   // next offset to consume, end of the segment
-    int32_t rel_lo;         // first readable offset (history limit)
-    uint32_t in_lo, in_hi;  // the bytes at rel, rel+1, ... (shifted as they are consumed; refilled at multiples of 8)
-    uint32_t r[4];          // results of the current group of 8 positions
-};
-
-// slow path of the refill: a group of 8 that is not entirely readable (start of the history, end of the stream) or a
-// start that is not a multiple of 8
-__device__ __noinline__ uint2 load8_slow(const uint8_t* in, int32_t rel, int32_t rel_lo, int32_t rel_end) {
-    const int32_t ra = rel & ~7;
+// The 8 stream bytes of group g (a multiple of 8, relative to the segment start): one aligned 8-byte load when the whole
+// group is readable, byte by byte at the two ends of the readable range [lo, hi).
+__device__ __forceinline__ uint2 load_group(const uint8_t* in, int32_t g, int32_t lo, int32_t hi) {
+    if (g >= lo && g + 8 <= hi) return __ldg(reinterpret_cast<const uint2*>(in + g));
     uint32_t a = 0, b = 0;
-    for (int k = 0; k < 8; ++k) {
-        const int32_t g = ra + k;
-        if (g >= rel_lo && g < rel_end) { if (k < 4) a |= uint32_t(in[g]) << (8 * k); else b |= uint32_t(in[g]) << (8 * (k - 4)); }
+    if (g + 8 > lo && g < hi) {
+        for (int k = 0; k < 8; ++k) {
+            const int32_t q = g + k;
+            if (q >= lo && q < hi) { if (k < 4) a |= uint32_t(in[q]) << (8 * k); else b |= uint32_t(in[q]) << (8 * (k - 4)); }
+        }
     }
-    const uint32_t sk = uint32_t(rel - ra) * 8;
-    if (sk >= 32) { a = b >> (sk - 32); b = 0; }
-    else if (sk) { a = __funnelshift_r(a, b, sk); b >>= sk; }
     return make_uint2(a, b);
 }
 
-// the byte at io.rel has been resolved with result o: report it (not during the warm-up) and step to the next byte
-__device__ __forceinline__ void emit_and_advance(LaneIO& io, uint32_t o) {
-    const int32_t rel = io.rel;
-    if (rel >= 0) {
-        // results of a group of 8 accumulate in r[] by shifting: after 8 of them r[0..3] hold positions 0..7 in order
-        io.r[0] = __funnelshift_r(io.r[0], io.r[1], 16); io.r[1] = __funnelshift_r(io.r[1], io.r[2], 16);
-        io.r[2] = __funnelshift_r(io.r[2], io.r[3], 16); io.r[3] = (io.r[3] >> 16) | (o << 16);
-        if ((rel & 7) == 7) __stcs(reinterpret_cast<uint4*>(io.out + (rel - 7)), make_uint4(io.r[0], io.r[1], io.r[2], io.r[3]));
-    }
-    io.rel = rel + 1;
-    if ((io.rel & 7) == 0) {
-        if (io.rel + 8 <= io.rel_end && io.rel >= io.rel_lo) {
-            const uint2 v = __ldg(reinterpret_cast<const uint2*>(io.in + io.rel));
-            io.in_lo = v.x; io.in_hi = v.y;
-        } else if (io.rel < io.rel_end) { const uint2 v = load8_slow(io.in, io.rel, io.rel_lo, io.rel_end); io.in_lo = v.x; io.in_hi = v.y; }
-    } else {
-        io.in_lo = __funnelshift_r(io.in_lo, io.in_hi, 8); io.in_hi >>= 8;
-    }
-}
-
+// Every lane walks its own segment; the warp advances all of them in ROUNDS.  One round, the same for every lane:
+//   1. issue this round's table load -- the 32-byte record of a cold state that is not in registers yet, or the 4-byte
+//      DENSE-row entry for the current byte -- every lane that needs one with the same instruction;
+//   2. report the byte consumed in the previous round (its longest-pattern id is known by now: it came with that
+//      round's transition, or it is word 1 of the record just fetched);
+//   3. make one transition on the current byte: shared-memory row, DENSE entry, the next step of a CHAIN record, a
+//      BRANCH record's goto edge -- or, without consuming the byte, a failure link.
+// A round consumes at most one byte and contains at most one dependent global load; nobody waits for the lane with the
+// longest failure chain (a byte-synchronous warp wastes two thirds of its rounds on the C5b stream: 1.6 rounds per byte
+// on average, 4.9 for the slowest of 32 lanes), and the per-lane bookkeeping is one straight-line sequence instead of
+// the nested, separately diverging paths of the first generations of this kernel (9.5 warp instructions per stream byte
+// with 9.8 of 32 lanes active, profiles/r02_deep_kernel.md).
 __global__ void __launch_bounds__(kThreads, 1) deep_scan_kernel(const DeepParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint16_t* s_hot = reinterpret_cast<uint16_t*>(smem);                              // n_hot x 256
-    uint16_t* s_long = s_hot + (size_t(p.n_hot) << 8);                                // n_hot
+    uint16_t* s_long = s_hot + (size_t(p.n_hot) << 8);                                // n_small
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.hot_rows);
         uint4* dst = reinterpret_cast<uint4*>(s_hot);
         for (uint32_t i = threadIdx.x; i < (p.n_hot << 8) / 8; i += kThreads) dst[i] = __ldg(src + i);
-        for (uint32_t i = threadIdx.x; i < p.n_hot; i += kThreads) s_long[i] = __ldg(p.hot_longest + i);
+        for (uint32_t i = threadIdx.x; i < p.n_small; i += kThreads) s_long[i] = __ldg(p.hot_longest + i);
     }
     __syncthreads();
-    const uint32_t n_hot = p.n_hot;
+    const uint32_t n_hot = p.n_hot, dense_end = p.dense_end, n_small = p.n_small;
 
     for (uint64_t seg = uint64_t(blockIdx.x) * kThreads + threadIdx.x; seg < p.n_seg; seg += uint64_t(gridDim.x) * kThreads) {
-        LaneIO io;
         const uint64_t s0 = seg * uint64_t(p.seg);
-        io.in = p.stream + s0; io.out = p.out + s0;
-        io.rel_end = int32_t(min(uint64_t(p.seg), p.n - s0));
-        io.rel_lo = -int32_t(min(uint64_t(p.warm), s0 + p.hist_valid));   // warm-up: max_pat_len-1 bytes back, never before the readable history
-        io.rel = io.rel_lo;
-        io.r[0] = io.r[1] = io.r[2] = io.r[3] = 0;
-        { const uint2 v = load8_slow(io.in, io.rel, io.rel_lo, io.rel_end); io.in_lo = v.x; io.in_hi = v.y; }
-        Walk W;
-        W.s = 0; W.have = false; W.head = false;
+        const uint8_t* in = p.stream + s0;
+        uint16_t* out = p.out + s0;
+        const int32_t rel_end = int32_t(min(uint64_t(p.seg), p.n - s0));
+        const int32_t rel_lo = -int32_t(min(uint64_t(p.warm), s0 + p.hist_valid));   // warm-up: max_pat_len-1 bytes back, never before the readable history
+        const int32_t rd_hi = int32_t(min(uint64_t(p.seg) + 16, p.n - s0));           // bytes after the segment are readable up to the end of the stream
+        int32_t rel = rel_lo;        // next byte to consume
+        int32_t orel = rel_lo;       // next position to report
+        uint32_t cur_lo, cur_hi, nxt_lo, nxt_hi;   // bytes rel.. of the current group; the whole next group
+        {
+            const int32_t g = rel & ~7;
+            const uint2 a = load_group(in, g, rel_lo, rd_hi), b = load_group(in, g + 8, rel_lo, rd_hi);
+            const uint32_t sk = uint32_t(rel - g) * 8;
+            cur_lo = a.x; cur_hi = a.y;
+            if (sk >= 32) { cur_lo = cur_hi >> (sk - 32); cur_hi = 0; }
+            else if (sk) { cur_lo = __funnelshift_r(cur_lo, cur_hi, sk); cur_hi >>= sk; }
+            nxt_lo = b.x; nxt_hi = b.y;
+        }
+        uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;   // results of the current group of 8 positions, shifted in from the top
+        uint32_t s = 0;              // current state
+        uint32_t w[8];               // its record (CHAIN: shifted as the run is consumed), valid when `have`
 #pragma unroll
-        for (int k = 0; k < 8; ++k) W.w[k] = 0;
-        bool arrived = false;   // s was just entered and is cold: the byte is consumed, only s's longest id is missing
+        for (int k = 0; k < 8; ++k) w[k] = 0;
+        bool have = false;           // w belongs to s
+        bool head = false;           // CHAIN: nothing of the record has been consumed yet, so w[0] holds s's own failure link
+        bool pend = false;           // the byte consumed in the previous round has not been reported yet
+        bool pend_cold = false;      // ... and its longest id is word 1 of the record this round fetches
+        uint32_t pend_val = 0;
 #pragma unroll 1
-        while (io.rel < io.rel_end) {
-            // ---- one round: at most one record fetch, then as far as the lane gets without another ----
-            if (W.s >= n_hot && !W.have) {
-                ldg_rec(p.recs + size_t(W.s) * 8, W.w);
-                W.have = true; W.head = true;
+        for (;;) {
+            const bool active = rel < rel_end;
+            if (!active && !pend) break;
+            const uint32_t c = cur_lo & 0xFFu;
+            // ---- 1. this round's table load ----
+            const bool is_hot = s < n_hot;
+            const bool is_dense = !is_hot && s < dense_end;
+            const bool fetch = !is_hot && !is_dense && !have;
+            uint32_t dv = 0;
+            if (fetch) ldg_rec(p.recs + size_t(s) * 8, w);
+            if (is_dense && active) dv = __ldg(p.dense_rows + (((s - n_hot) << 8) | c));
+            have = have || fetch;
+            head = head || fetch;
+            // ---- 2. report the previous byte ----
+            if (pend) {
+                const uint32_t o = pend_cold ? w[1] : pend_val;
+                r0 = __funnelshift_r(r0, r1, 16); r1 = __funnelshift_r(r1, r2, 16);
+                r2 = __funnelshift_r(r2, r3, 16); r3 = (r3 >> 16) | (o << 16);
+                if ((orel & 7) == 7 && orel >= 0) __stcs(reinterpret_cast<uint4*>(out + (orel - 7)), make_uint4(r0, r1, r2, r3));
+                ++orel;
+                pend = false;
             }
-            if (arrived) {                                  // the record just fetched completes the previous byte ...
-                arrived = false;
-                emit_and_advance(io, W.w[1]);
-                if (io.rel >= io.rel_end) break;            // ... and serves the next one in the same round
-            }
-            const uint32_t c = io.in_lo & 0xFFu;
-            if (W.s < n_hot) {                              // complete row in shared memory
-                W.s = s_hot[(W.s << 8) | c];
-                W.have = false;
-                if (W.s < n_hot) emit_and_advance(io, s_long[W.s]); else arrived = true;
-                continue;
-            }
-            const uint32_t kind = (W.w[0] >> 24) & 3u, fail = W.w[0] & 0xFFFFFFu;
-            if (kind == 1u) {                               // CHAIN: the next state of the run is s + 1
-                if ((W.w[2] & 0xFFu) == c) {
-                    const uint32_t o = W.w[4] & 0xFFFFu;
-                    ++W.s;
-                    W.w[2] = __funnelshift_r(W.w[2], W.w[3], 8); W.w[3] >>= 8;
-                    W.w[4] = __funnelshift_r(W.w[4], W.w[5], 16); W.w[5] = __funnelshift_r(W.w[5], W.w[6], 16);
-                    W.w[6] = __funnelshift_r(W.w[6], W.w[7], 16); W.w[7] >>= 16;
-                    W.w[0] -= 1u << 26;
-                    W.head = false;
-                    if ((W.w[0] >> 26) == 0) W.have = false;   // this record's part of the run is used up
-                    emit_and_advance(io, o);
-                } else {
-                    if (W.head) W.s = fail;                 // failure transition; the byte is not consumed
-                    W.have = false;                         // (inside the run: s's own record has its failure link)
-                }
-            } else if (kind == 0u) {                        // BRANCH: goto edges in w[2..]
-                const uint32_t cnt = W.w[0] >> 26;
-                uint32_t next = 0xFFFFFFFFu;
+            if (!active) continue;   // only the last report was left
+            // ---- 3. one transition on c ----
+            bool consumed, known = false;
+            uint32_t ns, val = 0;
+            if (is_hot) {
+                ns = s_hot[(s << 8) | c];
+                consumed = true; have = false;
+            } else if (is_dense) {
+                ns = dv;
+                consumed = true; have = false;
+            } else {
+                const uint32_t kind = (w[0] >> 24) & 3u, fail = w[0] & 0xFFFFFFu;
+                if (kind == 1u) {                               // CHAIN: the next state of the run is s + 1
+                    if ((w[2] & 0xFFu) == c) {
+                        val = w[4] & 0xFFFFu; known = true;
+                        ns = s + 1; consumed = true;
+                        w[2] = __funnelshift_r(w[2], w[3], 8); w[3] >>= 8;
+                        w[4] = __funnelshift_r(w[4], w[5], 16); w[5] = __funnelshift_r(w[5], w[6], 16);
+                        w[6] = __funnelshift_r(w[6], w[7], 16); w[7] >>= 16;
+                        w[0] -= 1u << 26;
+                        head = false;
+                        have = (w[0] >> 26) != 0;               // false: this record's part of the run is used up
+                    } else {
+                        ns = head ? fail : s;                   // failure transition; the byte is not consumed
+                        consumed = false; have = false;         // (inside the run: s's own record has its failure link)
+                    }
+                } else {                                        // BRANCH (kind 0): goto edges in w[2..7]; LEAF (kind 3): none
+                    uint32_t next = 0xFFFFFFFFu;
 #pragma unroll
-                for (int k = 0; k < 6; ++k)
-                    if (uint32_t(k) < cnt && (W.w[2 + k] & 0xFFu) == c) next = W.w[2 + k] >> 8;
-                W.have = false;
-                if (next != 0xFFFFFFFFu) { W.s = next; arrived = true; }
-                else W.s = fail;
-            } else {                                        // DENSE: a complete row
-                W.s = __ldg(p.dense_rows + ((size_t(W.w[2]) << 8) | c));
-                W.have = false;
-                if (W.s < n_hot) emit_and_advance(io, s_long[W.s]); else arrived = true;
+                    for (int k = 0; k < 6; ++k) {
+                        const uint32_t t = w[2 + k] ^ c;        // low byte zero = the edge's byte is c; the child sits above it
+                        if ((t & 0xFFu) == 0) next = t >> 8;
+                    }
+                    consumed = kind == 0u && next != 0xFFFFFFFFu;
+                    ns = consumed ? next : fail;
+                    have = false;
+                }
             }
+            if (consumed) {
+                if (!known && ns < n_small) { val = s_long[ns]; known = true; }
+                pend = true; pend_cold = !known; pend_val = val;
+                ++rel;
+                if ((rel & 7) == 0) {
+                    cur_lo = nxt_lo; cur_hi = nxt_hi;
+                    const uint2 v = load_group(in, rel + 8, rel_lo, rd_hi);   // used eight bytes from now
+                    nxt_lo = v.x; nxt_hi = v.y;
+                } else {
+                    cur_lo = __funnelshift_r(cur_lo, cur_hi, 8); cur_hi >>= 8;
+                }
+            }
+            s = ns;
         }
-        if (arrived) {   // the last byte of the segment ended in a cold state: its longest id still has to be fetched
-            ldg_rec(p.recs + size_t(W.s) * 8, W.w);
-            emit_and_advance(io, W.w[1]);
-        }
-        // ragged end of the stream: the last group is not full
-        const uint32_t rest = uint32_t(io.rel_end) & 7u;
+        // ragged end of the stream: the last group is not full; its `rest` results sit in the top of r
+        const uint32_t rest = uint32_t(rel_end) & 7u;
         if (rest) {
-            // the `rest` results sit in the top of r[]: shift them down to position 0
             for (uint32_t k = rest; k < 8; ++k) {
-                io.r[0] = __funnelshift_r(io.r[0], io.r[1], 16); io.r[1] = __funnelshift_r(io.r[1], io.r[2], 16);
-                io.r[2] = __funnelshift_r(io.r[2], io.r[3], 16); io.r[3] >>= 16;
+                r0 = __funnelshift_r(r0, r1, 16); r1 = __funnelshift_r(r1, r2, 16);
+                r2 = __funnelshift_r(r2, r3, 16); r3 >>= 16;
             }
-            const int32_t base = io.rel_end - int32_t(rest);
+            const int32_t base = rel_end - int32_t(rest);
             for (uint32_t k = 0; k < rest; ++k) {
-                io.out[base + k] = uint16_t(io.r[0]);
-                io.r[0] = __funnelshift_r(io.r[0], io.r[1], 16); io.r[1] = __funnelshift_r(io.r[1], io.r[2], 16);
-                io.r[2] = __funnelshift_r(io.r[2], io.r[3], 16); io.r[3] >>= 16;
+                out[base + k] = uint16_t(r0);
+                r0 = __funnelshift_r(r0, r1, 16); r1 = __funnelshift_r(r1, r2, 16);
+                r2 = __funnelshift_r(r2, r3, 16); r3 >>= 16;
             }
         }
     }
@@ -190,12 +195,12 @@ __global__ void __launch_bounds__(kThreads, 1) deep_scan_kernel(const DeepParams
 
 }  // namespace
 
-size_t deep_smem_bytes(uint32_t n_hot) { return (size_t(n_hot) << 9) + size_t((n_hot + 7) & ~7u) * 2; }
+size_t deep_smem_bytes(uint32_t n_hot, uint32_t n_small) { return (size_t(n_hot) << 9) + size_t((n_small + 7) & ~7u) * 2; }
 
 cudaError_t deep_scan_launch(const DeepParams& p_in, int n_sms, cudaStream_t st, uint64_t* launches) {
     DeepParams p = p_in;
     if (p.n == 0) return cudaSuccess;
-    const size_t smem = deep_smem_bytes(p.n_hot);
+    const size_t smem = deep_smem_bytes(p.n_hot, p.n_small);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     // segments: about 4 KiB each (the warm-up is max_pat_len-1 bytes), cut so that the persistent grid's lanes get the
     // same number of them; multiples of 16 bytes (8-byte loads, 16-byte result stores)

@@ -457,48 +457,59 @@ void Dict::build_deep() const {
             s = fail[s];
         }
     };
-    // numbering: depth <= 1, then depth 2 (both breadth-first = their current order), then depth >= 3 depth-first
-    uint32_t n_le1 = 0, n_le2 = 0;
-    for (uint32_t v = 0; v < t.n; ++v) { n_le1 += t.depth[v] <= 1; n_le2 += t.depth[v] <= 2; }
-    std::vector<uint32_t> nid(t.n, 0);
-    for (uint32_t v = 0; v < n_le2; ++v) nid[v] = v;   // breadth-first ids of depth <= 2 are already 0 .. n_le2-1
+    // numbering: depth <= 1 ("hot"), then every DENSE state (more than 6 children, any depth >= 2), then the other depth-2
+    // states -- all of these are "small" ids whose longest pid lives in shared memory -- then the rest depth-first
+    auto n_children = [&](uint32_t v) { return t.off[v + 1] - t.off[v]; };
+    auto is_dense = [&](uint32_t v) { return t.depth[v] >= 2 && n_children(v) > 6; };
+    uint32_t n_le1 = 0;
+    for (uint32_t v = 0; v < t.n; ++v) n_le1 += t.depth[v] <= 1;
+    std::vector<uint32_t> nid(t.n, 0xFFFFFFFFu);
+    uint32_t next = 0;
+    for (uint32_t v = 0; v < n_le1; ++v) nid[v] = next++;   // breadth-first ids of depth <= 1 are already 0 .. n_le1-1
+    for (uint32_t v = n_le1; v < t.n; ++v) if (is_dense(v)) nid[v] = next++;
+    const uint32_t dense_end = next;
+    std::vector<uint32_t> d2;
+    for (uint32_t v = n_le1; v < t.n && t.depth[v] == 2; ++v) { d2.push_back(v); if (nid[v] == 0xFFFFFFFFu) nid[v] = next++; }
+    const uint32_t n_small = next;
     {
-        uint32_t next = n_le2;
         std::vector<uint32_t> stack;
-        for (uint32_t v = n_le1; v < n_le2; ++v) {      // subtrees of the depth-2 states, in order
+        for (uint32_t v : d2) {      // subtrees of the depth-2 states, in order
             for (uint32_t k = t.off[v + 1]; k-- > t.off[v];) stack.push_back(t.child[k]);
             while (!stack.empty()) {
                 const uint32_t u = stack.back();
                 stack.pop_back();
-                nid[u] = next++;
+                if (nid[u] == 0xFFFFFFFFu) nid[u] = next++;   // DENSE states already have their id
                 for (uint32_t k = t.off[u + 1]; k-- > t.off[u];) stack.push_back(t.child[k]);   // reversed: smallest byte on top
             }
         }
     }
     std::vector<uint32_t> old_of(t.n, 0);
     for (uint32_t v = 0; v < t.n; ++v) old_of[nid[v]] = v;
-    x.n_hot = n_le1; x.n_hot_targets = n_le2;
-    if (n_le2 > 65535 || t.n >= (1u << 24) || pats.size() > 65535) return;   // usable stays false
+    x.n_hot = n_le1; x.n_dense = dense_end - n_le1; x.n_small = n_small;
+    if (n_small > 65535 || t.n >= (1u << 24) || pats.size() > 65535) return;   // usable stays false
     x.hot_rows.assign(size_t(n_le1) << 8, 0);
-    x.hot_longest.assign(n_le1, 0);
-    for (uint32_t s = 0; s < n_le1; ++s) {
-        x.hot_longest[s] = uint16_t(longest[s]);
+    x.hot_longest.assign(n_small, 0);
+    for (uint32_t id = 0; id < n_small; ++id) x.hot_longest[id] = uint16_t(longest[old_of[id]]);
+    for (uint32_t s = 0; s < n_le1; ++s)
         for (uint32_t b = 0; b < 256; ++b) x.hot_rows[(size_t(s) << 8) | b] = uint16_t(nid[delta(s, uint8_t(b))]);
+    x.dense_rows.assign(size_t(x.n_dense) << 8, 0);
+    for (uint32_t id = n_le1; id < dense_end; ++id) {
+        const uint32_t v = old_of[id];
+        for (uint32_t b = 0; b < 256; ++b) x.dense_rows[(size_t(id - n_le1) << 8) | b] = nid[delta(v, uint8_t(b))];
     }
     x.recs.assign(size_t(t.n) * 8, 0);
-    for (uint32_t id = n_le1; id < t.n; ++id) {
+    for (uint32_t id = dense_end; id < t.n; ++id) {
         const uint32_t v = old_of[id];
         uint32_t* r = x.recs.data() + size_t(id) * 8;
-        const uint32_t nc = t.off[v + 1] - t.off[v];
+        const uint32_t nc = n_children(v);
         r[1] = longest[v];
         uint32_t kind = 0, count = 0;
-        if (nc == 1 && t.depth[v] >= 3) {           // CHAIN: follow single children while they are id + 1
+        if (nc == 1 && nid[t.child[t.off[v]]] == id + 1) {   // CHAIN: follow single children while they are the next id
             kind = 1;
             uint32_t u = v;
             uint64_t labels = 0;
-            while (count < 8 && t.off[u + 1] - t.off[u] == 1) {
+            while (count < 8 && n_children(u) == 1 && nid[t.child[t.off[u]]] == id + count + 1) {
                 const uint32_t c = t.child[t.off[u]];
-                // depth-first numbering makes the only child the next id
                 labels |= uint64_t(t.byte[t.off[u]]) << (8 * count);
                 r[4 + count / 2] |= (longest[c] & 0xFFFFu) << (16 * (count & 1));
                 ++count;
@@ -506,15 +517,13 @@ void Dict::build_deep() const {
             }
             r[2] = uint32_t(labels); r[3] = uint32_t(labels >> 32);
             ++x.n_chain;
-        } else if (nc <= 6) {                        // BRANCH (also leaves and depth-2 states with one child)
-            for (uint32_t k = t.off[v]; k < t.off[v + 1]; ++k) r[2 + count++] = (nid[t.child[k]] << 8) | t.byte[k];
+        } else if (nc == 0) {                          // LEAF: every byte follows the failure link
+            kind = 3;
             ++x.n_branch;
-        } else {                                     // DENSE
-            kind = 2;
-            r[2] = x.n_dense++;
-            const size_t base = x.dense_rows.size();
-            x.dense_rows.resize(base + 256);
-            for (uint32_t b = 0; b < 256; ++b) x.dense_rows[base + b] = nid[delta(v, uint8_t(b))];
+        } else {                                       // BRANCH: 1 .. 6 goto edges; unused slots repeat the first edge
+            for (uint32_t k = t.off[v]; k < t.off[v + 1]; ++k) r[2 + count++] = (nid[t.child[k]] << 8) | t.byte[k];
+            for (uint32_t k = count; k < 6; ++k) r[2 + k] = r[2];
+            ++x.n_branch;
         }
         r[0] = nid[fail[v]] | (kind << 24) | (count << 26);
     }

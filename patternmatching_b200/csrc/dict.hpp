@@ -80,19 +80,21 @@ struct DfaTables {
 // (Core/src/mpac.c:147-210) kept as goto + failure -- NOT completed to a dense DFA -- in one 32-byte record per
 // state, 23 MB for snort+et instead of the dense table's 734 MB, so that it is L2-resident.
 //   state numbering: the root and the depth-1 states first ("hot": their complete DFA rows live in shared memory as
-//   u16), then the depth-2 states in breadth-first order, then every deeper state in depth-first pre-order with
-//   children in byte order -- the first child of a state of depth >= 3 is always state + 1, so a run of single-child
-//   states ("chain") is a run of consecutive ids and one record describes up to eight steps of it.
-//   record of state s (8 x u32):  w0 = failure state | kind << 24 | count << 26,  w1 = longest pid at s,
-//     kind 0 BRANCH: count <= 6 goto edges, w2.. = child << 8 | byte (sorted by byte); a miss follows the failure link
+//   u16), then every DENSE state (more than 6 children: a complete 256-entry DFA row in dense_rows, found from the id
+//   alone: row = id - n_hot), then the remaining depth-2 states -- the ids below n_small, whose longest pids live in
+//   shared memory -- then every deeper state in depth-first pre-order with children in byte order: the only child of
+//   a single-child state is state + 1 (unless it is DENSE), so a run of single-child states ("chain") is a run of
+//   consecutive ids and one record describes up to eight steps of it.
+//   record of state s >= n_hot + n_dense (8 x u32):  w0 = failure state | kind << 24 | count << 26,  w1 = longest pid at s,
+//     kind 0 BRANCH: 1 .. 6 goto edges, w2..w7 = child << 8 | byte (unused slots repeat the first edge); a miss follows the failure link
 //     kind 1 CHAIN : count <= 8 steps: bytes of states s+1 .. s+count in w2,w3, their longest pids (u16) in w4..w7
-//     kind 2 DENSE : more than 6 children: w2 = index of a complete 256-entry DFA row in dense_rows
+//     kind 3 LEAF  : no goto edge: every byte follows the failure link
 struct DeepTables {
-    uint32_t n_states = 0, n_hot = 0, n_hot_targets = 0;   // hot rows point at states < n_hot_targets (fit u16)
+    uint32_t n_states = 0, n_hot = 0, n_small = 0;   // hot rows point at states < n_small (fit u16)
     std::vector<uint16_t> hot_rows;      // [hot state << 8 | byte] -> next state (complete DFA transition)
-    std::vector<uint16_t> hot_longest;   // [hot state] -> longest pid
-    std::vector<uint32_t> recs;          // 8 words per state (records of the hot states are unused)
-    std::vector<uint32_t> dense_rows;    // 256 entries per DENSE state
+    std::vector<uint16_t> hot_longest;   // [state < n_small] -> longest pid (hot, DENSE and depth-2 states)
+    std::vector<uint32_t> recs;          // 8 words per state (records of the hot and DENSE states are unused)
+    std::vector<uint32_t> dense_rows;    // [(state - n_hot) << 8 | byte] -> next state, 256 entries per DENSE state
     uint32_t n_dense = 0, n_chain = 0, n_branch = 0;
     std::vector<uint32_t> depth_count;   // states per depth (forward trie)
     bool usable = false;                 // false: the automaton does not fit this layout (ids >= 2^24, > 65535 pids, ...)

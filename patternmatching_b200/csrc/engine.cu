@@ -114,6 +114,8 @@ struct pm_engine {
     uint32_t* d_anc_off = nullptr;
     uint16_t* d_anc_list = nullptr;
     uint64_t* d_pidhash = nullptr;
+    uint16_t* d_hot_map = nullptr;            // summary fast path (PatTables::hot_*)
+    uint64_t *d_hot_own = nullptr, *d_hot_anc = nullptr;
     pm::PatTables pt{};
     // dfa tables (device copies made on first use; the host tables belong to the dictionary, see Dict::build_dfa)
     uint32_t* d_delta = nullptr;
@@ -383,6 +385,7 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
             pm::DeepParams p{};
             p.stream = d_stream; p.n = n; p.hist_valid = hist_valid; p.out = d_out;
             p.hot_rows = e->d_deep_hot; p.hot_longest = e->d_deep_long; p.n_hot = d.deep.n_hot;
+            p.dense_end = d.deep.n_hot + d.deep.n_dense; p.n_small = d.deep.n_small;
             p.recs = e->d_deep_recs; p.dense_rows = e->d_deep_dense;
             p.warm = d.max_len ? d.max_len - 1 : 0;
             cudaError_t ce = pm::deep_scan_launch(p, e->n_sms, st, &e->launches);
@@ -782,6 +785,23 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
         parent[i + 1] = uint16_t(d.pats[i].parent); chain[i + 1] = uint16_t(d.pats[i].chain);
         pidhash[i + 1] = pm::splitmix64(((uint64_t(d.pats[i].file) + 1) << 32) | d.pats[i].line);
     }
+    // summary fast path: the shortest patterns with at most one ancestor, up to kSummaryHotMax of them (and as many as fit
+    // shared memory beside the 2-byte pid -> slot map)
+    std::vector<uint16_t> hot_map(P + 1, 0xFFFFu);
+    std::vector<uint64_t> hot_own, hot_anc;
+    {
+        std::vector<uint32_t> order;
+        for (uint32_t pid = 1; pid <= P; ++pid) if (d.pats[pid - 1].chain <= 1) order.push_back(pid);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return d.pats[a - 1].len < d.pats[b - 1].len; });
+        const size_t room = (size_t(200) << 10) > (P + 1) * 2 ? ((size_t(200) << 10) - (P + 1) * 2) / 16 : 0;
+        const size_t n_hot = std::min<size_t>({order.size(), size_t(pm::kSummaryHotMax), room});
+        for (size_t k = 0; k < n_hot; ++k) {
+            const uint32_t pid = order[k], par = d.pats[pid - 1].parent;
+            hot_map[pid] = uint16_t(k | (par ? 0x8000u : 0u));
+            hot_own.push_back(pidhash[pid]);
+            hot_anc.push_back(par ? pidhash[par] : 0);
+        }
+    }
     std::vector<uint8_t> padded_bytes(kPatPad + d.bytes.size() + 16, 0);
     std::copy(d.bytes.begin(), d.bytes.end(), padded_bytes.begin() + kPatPad);
     bool ok = up(d.sfx.root2, &e->d_root2) && up(d.sfx.root1, &e->d_root1) && up(d.sfx.rows, &e->d_rows) &&
@@ -789,7 +809,8 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
               up(len, &e->d_pat_len) && up(padded_bytes, &e->d_pat_bytes) && up(parent, &e->d_parent) &&
               up(d.sfx.tail_rec, &e->d_tail_rec) && up(d.sfx.l3f, &e->d_l3f) &&
               up(d.anc_off, &e->d_anc_off) && up(d.anc_list, &e->d_anc_list) &&
-              up(chain, &e->d_chain) && up(pidhash, &e->d_pidhash);
+              up(chain, &e->d_chain) && up(pidhash, &e->d_pidhash) &&
+              up(hot_map, &e->d_hot_map) && up(hot_own, &e->d_hot_own) && up(hot_anc, &e->d_hot_anc);
     if (ok) {  // the rows table also as a linear texture: the scan kernel reads level 3 through the TEX pipe (sfx_scan.cu)
         cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = e->d_rows;
         rd.res.linear.desc = cudaCreateChannelDesc<unsigned int>(); rd.res.linear.sizeInBytes = d.sfx.rows.size() * sizeof(uint32_t);
@@ -804,6 +825,7 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
     e->pt.off = e->d_pat_off; e->pt.len = e->d_pat_len; e->pt.bytes = e->d_pat_bytes + kPatPad;
     e->pt.parent = e->d_parent; e->pt.chain = e->d_chain; e->pt.pidhash = e->d_pidhash;
     e->pt.anc_off = e->d_anc_off; e->pt.anc_list = e->d_anc_list;
+    e->pt.hot_map = e->d_hot_map; e->pt.hot_own = e->d_hot_own; e->pt.hot_anc = e->d_hot_anc; e->pt.n_hot = uint32_t(hot_own.size());
     return e;
 }
 
@@ -814,7 +836,7 @@ void pm_engine_free(pm_engine* e) {
     e->pool.reset();
     if (e->rows_tex) cudaDestroyTextureObject(e->rows_tex);
     void* ptrs[] = {e->d_root2, e->d_root1, e->d_rows, e->d_row_best, e->d_cls, e->d_pat_off, e->d_pat_len, e->d_pat_bytes,
-                    e->d_parent, e->d_chain, e->d_pidhash, e->d_tail_rec, e->d_l3f, e->d_anc_off, e->d_anc_list, e->d_sample_out, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_fb_meta, e->d_deep_hot, e->d_deep_long, e->d_deep_recs, e->d_deep_dense, e->d_acc,
+                    e->d_parent, e->d_chain, e->d_pidhash, e->d_hot_map, e->d_hot_own, e->d_hot_anc, e->d_tail_rec, e->d_l3f, e->d_anc_off, e->d_anc_list, e->d_sample_out, e->d_delta, e->d_longest, e->d_dfa_cls, e->d_fb_meta, e->d_deep_hot, e->d_deep_long, e->d_deep_recs, e->d_deep_dense, e->d_acc,
                     e->d_compact_counts, e->d_flags, e->d_id_table, e->d_qcount};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int b = 0; b < kSlots; ++b) {

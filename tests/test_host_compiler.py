@@ -162,53 +162,77 @@ def test_plugin_registration_fills_an_mpselem():
 
 
 def emulate_deep_walk(d, stream):
-    """Host emulation of deep_scan.cu's per-lane state machine over the compact goto + failure records
-    (dict.hpp: DeepTables): the table builder is host logic and is checked here without a GPU."""
+    """Host emulation of deep_scan.cu's per-lane rounds over the compact goto + failure records (dict.hpp: DeepTables):
+    per round at most one table load (a record, or a DENSE-row entry), the report of the byte consumed in the round before,
+    and one transition.  The table builder is host logic and is checked here without a GPU."""
     recs = d.table("deep.recs", np.uint32).reshape(-1, 8)
     hot = d.table("deep.hot_rows", np.uint16).reshape(-1, 256)
-    hot_long = d.table("deep.hot_longest", np.uint16)
+    small_long = d.table("deep.hot_longest", np.uint16)
     dense = d.table("deep.dense_rows", np.uint32).reshape(-1, 256)
-    n_hot = hot.shape[0]
+    n_hot, n_small = hot.shape[0], small_long.size
+    dense_end = n_hot + dense.shape[0]
     out = np.zeros(stream.size, np.uint16)
-    s, q, n, fetches = 0, 0, stream.size, 0
-    while q < n:
-        c = int(stream[q])
-        if s < n_hot:
-            s = int(hot[s, c])
-            out[q] = hot_long[s] if s < n_hot else recs[s, 1]
-            q += 1
+    n = stream.size
+    s, rel, orel, fetches, rounds = 0, 0, 0, 0, 0
+    have = head = pend = pend_cold = False
+    pend_val = 0
+    w = None
+    while rel < n or pend:
+        rounds += 1
+        active = rel < n
+        c = int(stream[rel]) if active else 0
+        is_hot = s < n_hot
+        is_dense = (not is_hot) and s < dense_end
+        if (not is_hot) and (not is_dense) and not have:
+            w = [int(x) for x in recs[s]]; fetches += 1
+            have = head = True
+        if pend:
+            out[orel] = w[1] if pend_cold else pend_val
+            orel += 1; pend = False
+        if not active:
             continue
-        w = recs[s]
-        fetches += 1
-        kind, cnt, fail = (int(w[0]) >> 24) & 3, int(w[0]) >> 26, int(w[0]) & 0xFFFFFF
-        if kind == 1:
-            labels = int(w[2]) | (int(w[3]) << 32)
-            longs = int(w[4]) | (int(w[5]) << 32) | (int(w[6]) << 64) | (int(w[7]) << 96)
-            j = 0
-            while j < cnt and q < n and int(stream[q]) == (labels >> (8 * j)) & 0xFF:
-                out[q] = (longs >> (16 * j)) & 0xFFFF
-                q += 1; j += 1
-            s = fail if (j == 0 and q < n) else s + j
-        elif kind == 0:
-            nxt = [int(x) >> 8 for x in w[2:2 + cnt] if (int(x) & 0xFF) == c]
-            if nxt:
-                s = nxt[0]; out[q] = recs[s, 1]; q += 1
-            else:
-                s = fail
+        known, val = False, 0
+        if is_hot:
+            ns, consumed, have = int(hot[s, c]), True, False
+        elif is_dense:
+            ns, consumed, have = int(dense[s - n_hot, c]), True, False; fetches += 1
         else:
-            s = int(dense[int(w[2]), c])
-            out[q] = hot_long[s] if s < n_hot else recs[s, 1]
-            q += 1
-    return out, fetches
+            kind, cnt, fail = (w[0] >> 24) & 3, w[0] >> 26, w[0] & 0xFFFFFF
+            if kind == 1:
+                if (w[2] & 0xFF) == c:
+                    val, known, ns, consumed = w[4] & 0xFFFF, True, s + 1, True
+                    labels = (w[2] | (w[3] << 32)) >> 8
+                    longs = (w[4] | (w[5] << 32) | (w[6] << 64) | (w[7] << 96)) >> 16
+                    w[2], w[3] = labels & 0xFFFFFFFF, labels >> 32
+                    w[4], w[5], w[6], w[7] = (longs & 0xFFFFFFFF, (longs >> 32) & 0xFFFFFFFF, (longs >> 64) & 0xFFFFFFFF, longs >> 96)
+                    w[0] -= 1 << 26
+                    head = False
+                    have = (w[0] >> 26) != 0
+                else:
+                    ns, consumed, have = (fail if head else s), False, False
+            else:
+                nxt = None
+                for k in range(6):
+                    if (w[2 + k] & 0xFF) == c:
+                        nxt = w[2 + k] >> 8
+                consumed = kind == 0 and nxt is not None
+                ns, have = (nxt if consumed else fail), False
+        if consumed:
+            if (not known) and ns < n_small:
+                val, known = int(small_long[ns]), True
+            pend, pend_cold, pend_val = True, not known, val
+            rel += 1
+        s = ns
+    return out, fetches, rounds
 
 
 def test_deep_automaton_records_walk_like_the_oracle(dict_merged, oracle_merged):
     for kind, n in (("almost", 60000), ("planted", 30000), ("ascii", 20000)):
         stream = oracle_merged.gen(kind, 4096 * 3, n)
-        got, fetches = emulate_deep_walk(dict_merged, stream)
+        got, fetches, rounds = emulate_deep_walk(dict_merged, stream)
         want = (oracle_merged.scan(stream) + 1).astype(np.uint16)
         assert np.array_equal(got, want), kind
-        print(f"deep records on {kind}: {fetches / n:.3f} record fetches per byte")
+        print(f"deep records on {kind}: {fetches / n:.3f} table loads and {rounds / n:.3f} rounds per byte")
     # a small-alphabet dictionary: long chains, heavy failure traffic
     pats = [b"a" * k for k in range(1, 41)] + [b"ab" * k + b"c" for k in range(1, 20)] + [b"bca", b"cab", b"abcabcabd"]
     d = pm.Dictionary(); o = Oracle()
@@ -217,5 +241,5 @@ def test_deep_automaton_records_walk_like_the_oracle(dict_merged, oracle_merged)
     d.compile(); o.compile()
     rng = np.random.default_rng(2)
     stream = rng.choice(np.frombuffer(b"aaabbc", np.uint8), 50000)
-    got, _ = emulate_deep_walk(d, stream)
+    got, _, _ = emulate_deep_walk(d, stream)
     assert np.array_equal(got, (o.scan(stream) + 1).astype(np.uint16))
