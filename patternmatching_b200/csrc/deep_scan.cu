@@ -93,83 +93,80 @@ __global__ void __launch_bounds__(kThreads, 1) deep_scan_kernel(const DeepParams
         }
         uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;   // results of the current group of 8 positions, shifted in from the top
         uint32_t s = 0;              // current state
-        uint32_t w[8];               // its record (CHAIN: shifted as the run is consumed), valid when `have`
+        uint32_t w[8];               // a record (CHAIN: shifted as the run is consumed; bit 30 of w[0]: part of it has been consumed)
 #pragma unroll
         for (int k = 0; k < 8; ++k) w[k] = 0;
-        bool have = false;           // w belongs to s
-        bool head = false;           // CHAIN: nothing of the record has been consumed yet, so w[0] holds s's own failure link
-        bool pend = false;           // the byte consumed in the previous round has not been reported yet
-        bool pend_cold = false;      // ... and its longest id is word 1 of the record this round fetches
+        constexpr uint32_t kNone = 0xFFFFFFFFu;
+        uint32_t hs = kNone;         // the state w describes (kNone: nothing usable in w)
+        // The byte consumed in the previous round is reported one round later (orel == rel - 1 then): its longest id is
+        // pend_val, or -- kNone -- word 1 of the record the next round fetches.  Everything a lane carries from round to
+        // round is a number: flags cost the compiler a register shuffle each at every join of the diverging paths.
         uint32_t pend_val = 0;
 #pragma unroll 1
         for (;;) {
             const bool active = rel < rel_end;
+            const bool pend = orel < rel;
             if (!active && !pend) break;
             const uint32_t c = cur_lo & 0xFFu;
             // ---- 1. this round's table load ----
             const bool is_hot = s < n_hot;
             const bool is_dense = !is_hot && s < dense_end;
-            const bool fetch = !is_hot && !is_dense && !have;
+            const bool fetch = s >= dense_end && hs != s;
             uint32_t dv = 0;
-            if (fetch) ldg_rec(p.recs + size_t(s) * 8, w);
+            if (fetch) { ldg_rec(p.recs + size_t(s) * 8, w); hs = s; }
             if (is_dense && active) dv = __ldg(p.dense_rows + (((s - n_hot) << 8) | c));
-            have = have || fetch;
-            head = head || fetch;
             // ---- 2. report the previous byte ----
             if (pend) {
-                const uint32_t o = pend_cold ? w[1] : pend_val;
+                const uint32_t o = pend_val == kNone ? w[1] : pend_val;
                 r0 = __funnelshift_r(r0, r1, 16); r1 = __funnelshift_r(r1, r2, 16);
                 r2 = __funnelshift_r(r2, r3, 16); r3 = (r3 >> 16) | (o << 16);
                 if ((orel & 7) == 7 && orel >= 0) __stcs(reinterpret_cast<uint4*>(out + (orel - 7)), make_uint4(r0, r1, r2, r3));
                 ++orel;
-                pend = false;
             }
             if (!active) continue;   // only the last report was left
             // ---- 3. one transition on c ----
-            bool consumed, known = false;
-            uint32_t ns, val = 0;
+            uint32_t ns, val = kNone;   // val: the longest id at ns when this round already knows it
+            bool consumed = true;
             if (is_hot) {
                 ns = s_hot[(s << 8) | c];
-                consumed = true; have = false;
             } else if (is_dense) {
                 ns = dv;
-                consumed = true; have = false;
             } else {
-                const uint32_t kind = (w[0] >> 24) & 3u, fail = w[0] & 0xFFFFFFu;
-                if (kind == 1u) {                               // CHAIN: the next state of the run is s + 1
+                const uint32_t w0 = w[0], fail = w0 & 0xFFFFFFu;
+                hs = kNone;
+                if (w0 & (1u << 24)) {                          // CHAIN (kind 1): the next state of the run is s + 1
                     if ((w[2] & 0xFFu) == c) {
-                        val = w[4] & 0xFFFFu; known = true;
-                        ns = s + 1; consumed = true;
+                        val = w[4] & 0xFFFFu;
+                        ns = s + 1;
                         w[2] = __funnelshift_r(w[2], w[3], 8); w[3] >>= 8;
                         w[4] = __funnelshift_r(w[4], w[5], 16); w[5] = __funnelshift_r(w[5], w[6], 16);
                         w[6] = __funnelshift_r(w[6], w[7], 16); w[7] >>= 16;
-                        w[0] -= 1u << 26;
-                        head = false;
-                        have = (w[0] >> 26) != 0;               // false: this record's part of the run is used up
+                        w[0] = (w0 - (1u << 26)) | (1u << 30);
+                        if (w[0] & (15u << 26)) hs = ns;        // steps left in this record: it now describes s + 1
                     } else {
-                        ns = head ? fail : s;                   // failure transition; the byte is not consumed
-                        consumed = false; have = false;         // (inside the run: s's own record has its failure link)
+                        ns = (w0 & (1u << 30)) ? s : fail;      // failure transition (inside the run: s's own record has its link)
+                        consumed = false;
                     }
-                } else {                                        // BRANCH (kind 0): goto edges in w[2..7]; LEAF (kind 3): none
-                    uint32_t next = 0xFFFFFFFFu;
+                } else {                                        // BRANCH (kind 0): goto edges in w[2..7]; LEAF (kind 2): none
+                    uint32_t next = kNone;
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
                         const uint32_t t = w[2 + k] ^ c;        // low byte zero = the edge's byte is c; the child sits above it
                         if ((t & 0xFFu) == 0) next = t >> 8;
                     }
-                    consumed = kind == 0u && next != 0xFFFFFFFFu;
+                    consumed = !(w0 & (2u << 24)) && next != kNone;
                     ns = consumed ? next : fail;
-                    have = false;
                 }
             }
             if (consumed) {
-                if (!known && ns < n_small) { val = s_long[ns]; known = true; }
-                pend = true; pend_cold = !known; pend_val = val;
+                if (val == kNone && ns < n_small) val = s_long[ns];
+                pend_val = val;
                 ++rel;
                 if ((rel & 7) == 0) {
                     cur_lo = nxt_lo; cur_hi = nxt_hi;
-                    const uint2 v = load_group(in, rel + 8, rel_lo, rd_hi);   // used eight bytes from now
-                    nxt_lo = v.x; nxt_hi = v.y;
+                    // the group after the next one (used eight bytes from now); rel + 8 > rel_lo always holds here
+                    if (rel + 16 <= rd_hi) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(in + rel + 8)); nxt_lo = v.x; nxt_hi = v.y; }
+                    else { const uint2 v = load_group(in, rel + 8, rel_lo, rd_hi); nxt_lo = v.x; nxt_hi = v.y; }
                 } else {
                     cur_lo = __funnelshift_r(cur_lo, cur_hi, 8); cur_hi >>= 8;
                 }

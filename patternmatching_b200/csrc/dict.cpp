@@ -518,7 +518,7 @@ void Dict::build_deep() const {
             r[2] = uint32_t(labels); r[3] = uint32_t(labels >> 32);
             ++x.n_chain;
         } else if (nc == 0) {                          // LEAF: every byte follows the failure link
-            kind = 3;
+            kind = 2;
             ++x.n_branch;
         } else {                                       // BRANCH: 1 .. 6 goto edges; unused slots repeat the first edge
             for (uint32_t k = t.off[v]; k < t.off[v + 1]; ++k) r[2 + count++] = (nid[t.child[k]] << 8) | t.byte[k];

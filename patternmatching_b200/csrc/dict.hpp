@@ -88,7 +88,7 @@ struct DfaTables {
 //   record of state s >= n_hot + n_dense (8 x u32):  w0 = failure state | kind << 24 | count << 26,  w1 = longest pid at s,
 //     kind 0 BRANCH: 1 .. 6 goto edges, w2..w7 = child << 8 | byte (unused slots repeat the first edge); a miss follows the failure link
 //     kind 1 CHAIN : count <= 8 steps: bytes of states s+1 .. s+count in w2,w3, their longest pids (u16) in w4..w7
-//     kind 3 LEAF  : no goto edge: every byte follows the failure link
+//     kind 2 LEAF  : no goto edge: every byte follows the failure link
 struct DeepTables {
     uint32_t n_states = 0, n_hot = 0, n_small = 0;   // hot rows point at states < n_small (fit u16)
     std::vector<uint16_t> hot_rows;      // [hot state << 8 | byte] -> next state (complete DFA transition)

@@ -666,8 +666,10 @@ cudaError_t sfx_scan_launch(const SfxParams& p_in, bool ident_cls, int n_sms, ui
     // Start of a stream: visit 0 reads no bytes before the stream unless 4 bytes of history exist, and a deferred
     // walk is bounded by the bytes that exist; every position that could look back past the start of the readable
     // stream is redone by the bounded walker -- together with the ragged end that does not fill a tile.
+    // (The second condition: with fewer than 4 bytes of history visit 0 does not load them at all -- hist4 in the scan
+    // kernel -- so the first max_pat_len-1 positions are redone even when the history covers every pattern.)
     uint32_t head = 0;
-    if (max_pat_len > 1 && p.hist_valid < uint64_t(max_pat_len - 1)) {
+    if (max_pat_len > 1 && (p.hist_valid < uint64_t(max_pat_len - 1) || p.hist_valid < 4)) {
         const uint64_t want = uint64_t(max_pat_len - 1);
         head = uint32_t(p.n < want ? p.n : want);
     }

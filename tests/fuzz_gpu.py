@@ -16,7 +16,7 @@ def make_case(rng):
     sym = np.array([b for b in range(base, base + alpha) if b != 10] or [97], dtype=np.uint8)
     n_pat = int(rng.choice([1, 5, 50, 500, 5000]))
     max_len = int(rng.choice([1, 2, 3, 4, 5, 8, 9, 17, 64, 353]))
-    pats = set()
+    pats, pat_list = set(), []   # the list keeps insertion order: cases depend on the seed only, not on hash randomisation
     stems = [bytes(rng.choice(sym, int(rng.integers(1, max_len + 1)))) for _ in range(8)]
     tries = 0
     while len(pats) < n_pat and tries < 20 * n_pat:
@@ -29,9 +29,9 @@ def make_case(rng):
         elif mode == 2:  # shared prefix
             st = stems[int(rng.integers(0, 8))]; p = (st + p)[:max_len]
         elif mode == 3 and pats:  # nested: a suffix of an existing pattern
-            q = list(pats)[int(rng.integers(0, len(pats)))]; p = q[int(rng.integers(0, len(q))):]
-        if p:
-            pats.add(p)
+            q = pat_list[int(rng.integers(0, len(pat_list)))]; p = q[int(rng.integers(0, len(q))):]
+        if p and p not in pats:
+            pats.add(p); pat_list.append(p)
     pats = sorted(pats)
     n = int(rng.choice([1, 100, 511, 512, 513, 5000, 70000, 300001]))
     stream = rng.choice(sym, n).astype(np.uint8)

@@ -107,6 +107,28 @@ def test_reference_stream_matches_golden(name):
         assert "%016x" % s["hsum_longest"] == gold["hsum_longest"] and "%016x" % s["hsum_all"] == gold["hsum_all"]
 
 
+@pytest.mark.parametrize("max_len", [1, 2, 3, 4, 5, 9])
+def test_short_history_with_short_patterns(max_len):
+    """1 .. 5 bytes of history in front of a scan whose longest pattern is as short: the history covers every pattern
+    (hist_valid >= max_pat_len - 1), yet the scan kernel's first visit loads the bytes before the stream only when there
+    are at least four of them -- the first positions have to be redone by the bounded walker (regression: round 2)."""
+    rng = np.random.default_rng(100 + max_len)
+    sym = np.frombuffer(b"abc", np.uint8)
+    pats = sorted({bytes(rng.choice(sym, int(rng.integers(1, max_len + 1)))) for _ in range(40)} | {bytes(rng.choice(sym, max_len))})
+    d = pm.Dictionary(); o = Oracle()
+    for i, p in enumerate(pats):
+        d.add_pattern(p, 0, i + 1); o.add_pattern(p, 0, i + 1)
+    d.compile(); o.compile()
+    eng = pm.Engine(d)
+    stream = rng.choice(sym, 5000).astype(np.uint8)
+    want = want_pids(o, stream)
+    for hist in (1, 2, 3, 4, 5):
+        for n in (1, 100, 600, 4000):
+            for algo in (pm.ALGO_SFX, pm.ALGO_DFA, pm.ALGO_AUTO):
+                got = gpu_scan(eng, stream[hist:hist + n], algo, hist=stream[:hist])
+                assert np.array_equal(got, want[hist:hist + n]), (max_len, hist, n, algo)
+
+
 def test_tiny_appendix_a_example():
     d = pm.Dictionary().add_bytes(TINY_DICT).compile()
     o = Oracle(); o.add_dict_bytes(TINY_DICT); o.compile()
