@@ -144,6 +144,14 @@ int pm_engine_set_kr_seed(pm_engine* e, uint64_t seed);
 int pm_engine_scan_device(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid,
                           uint16_t* d_out, void* cuda_stream);
 
+/* Same scan with 32-bit results: d_out[i] = pid of the longest pattern ending at i as a 32-bit number, for dictionaries of
+ * ANY size.  A dictionary of more than 65,535 unique patterns (Core/src/mpac.c:257-291 accepts any number) is compiled
+ * into parts of at most 49,152 patterns; the engine scans once per part and keeps the longer answer per position.  Such
+ * an engine refuses the 16-bit entry points (pm_engine_scan_device, pm_engine_scan_host, records, summary) with a
+ * message; pm_engine_scan_host_ids / gpu_read_block (8-byte ids) serve it like any other.  d_out 16-byte aligned. */
+int pm_engine_scan_device32(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid,
+                            uint32_t* d_out, void* cuda_stream);
+
 /* Scan a HOST buffer: pinned double-buffered H2D copy, scan, D2H of the dense uint16 result,
  * synchronous.  State is carried across calls exactly like consecutive read_char calls until
  * pm_engine_reset().  replaces: the chunk loop of measure_single_instance_stats (measure.c:281-304).

@@ -84,6 +84,7 @@ def lib():
         "pm_engine_total_mem": (sz, [vp]),
         "pm_engine_set_kr_seed": (C.c_int, [vp, u64]),
         "pm_engine_scan_device": (C.c_int, [vp, C.c_int, vp, sz, sz, vp, vp]),
+        "pm_engine_scan_device32": (C.c_int, [vp, C.c_int, vp, sz, sz, vp, vp]),
         "pm_engine_scan_host": (C.c_int, [vp, C.c_int, vp, sz, vp]),
         "pm_engine_scan_device_records": (C.c_int, [vp, C.c_int, vp, sz, sz, u64, u32, vp, vp, sz, C.POINTER(u64), vp]),
         "pm_engine_scan_host_ids": (C.c_int, [vp, C.c_int, vp, sz, vp, sz, vp]),
@@ -314,6 +315,11 @@ class Engine:
     def scan_device(self, d_stream, n, d_out, hist_valid=0, algo=ALGO_SFX, cuda_stream=0):
         self._check(self.L.pm_engine_scan_device(self.h, algo, _ptr(d_stream), n, hist_valid, _ptr(d_out), cuda_stream),
                     "pm_engine_scan_device")
+
+    def scan_device32(self, d_stream, n, d_out32, hist_valid=0, algo=ALGO_SFX, cuda_stream=0):
+        """32-bit results (any number of patterns): d_out32[i] = global pid of the longest pattern ending at i."""
+        self._check(self.L.pm_engine_scan_device32(self.h, algo, _ptr(d_stream), n, hist_valid, _ptr(d_out32), cuda_stream),
+                    "pm_engine_scan_device32")
 
     def scan_device_records(self, d_stream, n, d_out, d_records, cap, min_len=4, hist_valid=0, pos_base=0, algo=ALGO_SFX,
                             cuda_stream=0):

@@ -161,6 +161,33 @@ __global__ void __launch_bounds__(256) expand_ids_kernel(const uint16_t* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// 32-bit results.  out32[i] = global pid of one part's 16-bit answer (local pid + base, 0 stays 0); unless `first`, the
+// LONGER of that and what out32[i] already holds: two different patterns that end at the same position have different
+// lengths, so the longest over all parts of a dictionary is the longest over the whole dictionary.  Four positions per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) merge_parts_kernel(uint32_t* __restrict__ out32, const uint16_t* __restrict__ part, uint64_t n,
+                                                         uint32_t base, const uint32_t* __restrict__ glen, bool first) {
+    auto one = [&](uint32_t t, uint32_t o) -> uint32_t {
+        const uint32_t g = t ? t + base : 0u;
+        if (first || o == 0) return g;
+        if (g == 0) return o;
+        return __ldg(glen + o) > __ldg(glen + g) ? o : g;
+    };
+    const uint64_t n4 = n / 4;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint2 v = __ldcs(reinterpret_cast<const uint2*>(part) + i);
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (!first) o = reinterpret_cast<const uint4*>(out32)[i];
+        o.x = one(v.x & 0xFFFFu, o.x); o.y = one(v.x >> 16, o.y); o.z = one(v.y & 0xFFFFu, o.z); o.w = one(v.y >> 16, o.w);
+        reinterpret_cast<uint4*>(out32)[i] = o;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const uint64_t i = n4 * 4 + threadIdx.x;
+        out32[i] = one(part[i], first ? 0u : out32[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Success classification of one dense result against another (Core/src/measure.c:174-190 on pids): per position
 // equal -> success; the algorithm's answer is a PatternsTree ancestor of the real one -> partial success; the algorithm
 // reported nothing -> false negative; anything else -> false positive.  acc[0..3] = success, partial, false_neg, false_pos.
@@ -438,6 +465,15 @@ cudaError_t expand_ids_launch(const uint16_t* out, uint64_t n, const unsigned lo
     if (n == 0) return cudaSuccess;
     const uint64_t want = (n / 4 + 255) / 256 + 1;
     expand_ids_kernel<<<uint32_t(want < uint64_t(n_sms) * 16 ? want : uint64_t(n_sms) * 16), 256, 0, st>>>(out, n, table, ids);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t merge_parts_launch(uint32_t* out32, const uint16_t* part, uint64_t n, uint32_t base, const uint32_t* glen, bool first,
+                               int n_sms, cudaStream_t st, uint64_t* launches) {
+    if (n == 0) return cudaSuccess;
+    const uint64_t want = (n / 4 + 255) / 256 + 1;
+    merge_parts_kernel<<<uint32_t(want < uint64_t(n_sms) * 16 ? want : uint64_t(n_sms) * 16), 256, 0, st>>>(out32, part, n, base, glen, first);
     ++*launches;
     return cudaGetLastError();
 }

@@ -34,6 +34,9 @@ cudaError_t summarize_launch(const uint16_t* out, uint64_t n, uint64_t pos_base,
 // ids[i] = table[out[i]] (pid -> the caller's 64-bit pattern id); out 8-byte aligned, ids 16-byte aligned
 cudaError_t expand_ids_launch(const uint16_t* out, uint64_t n, const unsigned long long* table, unsigned long long* ids,
                               int n_sms, cudaStream_t st, uint64_t* launches);
+// out32[i] = part[i] + base as a global pid (0 stays 0); unless `first`, the longer (glen, by global pid) of that and out32[i]
+cudaError_t merge_parts_launch(uint32_t* out32, const uint16_t* part, uint64_t n, uint32_t base, const uint32_t* glen, bool first,
+                               int n_sms, cudaStream_t st, uint64_t* launches);
 // measure_success_rate (Core/src/measure.c:174-190) of one dense result against another; d_acc4 = success, partial, false_neg, false_pos
 cudaError_t classify_launch(const uint16_t* algo, const uint16_t* real, uint64_t n, const PatTables& t,
                             unsigned long long* d_acc4, int n_sms, cudaStream_t st, uint64_t* launches);

@@ -188,6 +188,28 @@ bool Dict::is_pattern_suffix(uint32_t first, uint32_t second) const {  // Patter
     return false;
 }
 
+// More than 65,535 unique patterns (dict.hpp: parts): the PatternsTree relation has been computed over the whole
+// dictionary; every part is compiled like a dictionary of its own.  mpac.c:257-291 accepts any number of patterns.
+int Dict::compile_parts() {
+    const uint32_t P = uint32_t(pats.size());
+    for (uint32_t first = 1; first <= P; first += kPartPatterns) {
+        std::unique_ptr<Dict> part(new Dict());
+        const uint32_t last = std::min<uint64_t>(P, uint64_t(first) + kPartPatterns - 1);
+        for (uint32_t pid = first; pid <= last; ++pid) {
+            const Pattern& q = pats[pid - 1];
+            part->add_pattern(bytes.data() + q.off, q.len, q.file, q.line, q.user);
+        }
+        if (part->compile()) { error = part->error; return -1; }
+        part_first.push_back(first);
+        parts.push_back(std::move(part));
+    }
+    part_first.push_back(P + 1);
+    sfx.fits_u16 = false;
+    multi = true;
+    compiled = true;
+    return 0;
+}
+
 int Dict::compile() {
     if (compiled) { error = "dictionary already compiled"; return -1; }
     n_ac_states = uint32_t(fwd_->size());
@@ -216,6 +238,7 @@ int Dict::compile() {
         for (uint32_t q = pats[i].parent; q; q = pats[q - 1].parent) ++c;
         pats[i].chain = c;
     }
+    if (P > 65535) return compile_parts();
     anc_off.assign(size_t(P) + 2, 0);
     anc_list.clear();
     for (uint32_t pid = 1; pid <= P; ++pid) {
@@ -335,10 +358,6 @@ int Dict::compile() {
                 x.root2[(a << 8) | t.byte[k]] = uint16_t(code);
             }
         }
-    }
-    if (P > 65535) {   // not usable by the engine: stays uncompiled
-        error = "dictionary too large for dense uint16 results (more than 65,535 unique patterns)";
-        return -1;
     }
     // !fits_u16 (pids fit, but P + #2-byte continuations >= 65,536, or a pattern longer than 511 bytes): the dictionary
     // is usable, the engine serves every exact scan with the forward walkers, which have no such limit (mpac.c has none)

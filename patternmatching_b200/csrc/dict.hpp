@@ -13,6 +13,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -151,12 +152,22 @@ class Dict {
     uint32_t n_files = 0, max_len = 0;
     uint32_t n_ac_states = 1;
     bool compiled = false;
+    // More than 65,535 unique patterns: dense uint16 results cannot name them.  The dictionary is then cut into PARTS of
+    // at most kPartPatterns patterns (consecutive pids), each a complete dictionary of its own with all its tables; an
+    // engine scans the stream once per part and keeps, per position, the longer of the parts' answers (two different
+    // patterns ending at the same position have different lengths) as a 32-bit global pid.  parents / chains below are
+    // global in either case.  part k holds the global pids [part_first[k], part_first[k + 1]).
+    static constexpr uint32_t kPartPatterns = 49152;
+    bool multi = false;
+    std::vector<std::unique_ptr<Dict>> parts;
+    std::vector<uint32_t> part_first;
     SfxTables sfx;
     mutable DfaTables dfa;            // see build_dfa()
     mutable DeepTables deep;          // see build_deep()
     std::string error;
 
   private:
+    int compile_parts();
     // forward trie (also the de-dup structure): hash of (state << 8 | byte) -> child
     struct Trie;
     Trie* fwd_;

@@ -65,7 +65,8 @@ struct EngineOpts {
     bool sfx_no_tex = false, sfx_no_l3 = false, dfa_no_fb = false, dfa_flat = false, dfa_deep = false, dfa_no_fused = false;
     uint32_t l3_min = 4, l3_min_b = 4;
     size_t host_chunk = size_t(16) << 20;  // bytes per pipeline slot for pinned buffers (PM_HOST_CHUNK_MIB)
-    int host_threads = 0;                  // staging threads (PM_HOST_THREADS; default: half the host's cores, at most 16)
+    int host_threads = 0;                  // staging threads (PM_HOST_THREADS; default: half of this rank's share of the host's cores, at most 16)
+    int cpu_first = 0, cpu_count = 0;      // this rank's share of the CPUs (the workers are pinned inside it)
     // PM_HOST_IDS=device|host|<N>: where pids become 8-byte ids when the result buffer is page-locked: every piece on the
     // device (1), every piece by the host threads (0), or every N-th piece on the device and the rest by the host threads
     // (both resources at once: the PCIe link and the host's store bandwidth); -1 = chosen from the thread count
@@ -81,10 +82,19 @@ struct EngineOpts {
         if (const char* v = getenv("PM_SFX_L3_MIN")) o.l3_min = o.l3_min_b = uint32_t(atoi(v));
         if (const char* v = getenv("PM_SFX_L3_MIN_B")) o.l3_min_b = uint32_t(atoi(v));
         if (const char* v = getenv("PM_HOST_CHUNK_MIB")) { const long m = atol(v); if (m >= 1 && m <= 1024) o.host_chunk = size_t(m) << 20; }
-        // half of the host's cores (at most 16): on the 16-vCPU B200 box 8 staging threads gave the best host-path
-        // numbers, 16 (one per core, competing with the CUDA driver's own threads and the caller) were slower
-        const unsigned hw = std::thread::hardware_concurrency();
-        o.host_threads = int(std::max(1u, std::min<unsigned>((hw ? hw : 2) / 2, 16)));
+        // One process per GPU (torchrun sets LOCAL_WORLD_SIZE / LOCAL_RANK): the ranks of a box split its cores, and each
+        // pins its workers inside its own share -- eight ranks that all take "half the cores" and pin them to the same
+        // CPUs starve each other.  Within the share: half of the cores (at most 16): on the 16-vCPU B200 box 8 threads
+        // gave the best host-path numbers, 16 (one per core, competing with the CUDA driver's own threads and the
+        // caller) were slower.
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        unsigned lws = 1, lrank = 0;
+        if (const char* v = getenv("LOCAL_WORLD_SIZE")) lws = unsigned(std::max(1, atoi(v)));
+        if (const char* v = getenv("LOCAL_RANK")) lrank = unsigned(std::max(0, atoi(v)));
+        const unsigned share = std::max(1u, hw / lws);
+        o.cpu_first = int((lrank % lws) * share);
+        o.cpu_count = int(share);
+        o.host_threads = int(std::max(1u, std::min<unsigned>(share >= 4 ? share / 2 : share, 16)));
         if (const char* v = getenv("PM_HOST_THREADS")) { const int t = atoi(v); if (t >= 1 && t <= 256) o.host_threads = t; }
         if (const char* v = getenv("PM_HOST_IDS")) o.ids_device_every = v[0] == 'd' ? 1 : v[0] == 'h' ? 0 : std::max(0, atoi(v));
         return o;
@@ -176,6 +186,13 @@ struct pm_engine {
     unsigned long long* d_rec_counts[2] = {nullptr, nullptr};
     unsigned long long* h_rec_total[2] = {nullptr, nullptr};
     uint32_t* d_rec_flags[2] = {nullptr, nullptr};   // sparse-mode bitmaps of the two pipeline slots
+    // dictionaries of more than 65,535 patterns (pm::Dict::multi): one complete sub-engine per part; this object only
+    // keeps the stream state, the host pipeline buffers and the merge scratch
+    std::vector<pm_engine*> parts;
+    uint32_t* d_glen = nullptr;               // pattern length by GLOBAL pid (the merge keeps the longer answer)
+    uint16_t* d_tmp16 = nullptr;              // one part's dense answer for a slice
+    size_t tmp16_cap = 0;
+    uint32_t *d_out32 = nullptr, *h_out32 = nullptr;   // host path of multi-part engines: one piece of 32-bit results
     // stream state carried between host calls (== ac->current_state of the reference): the last `halo` bytes, right-aligned
     std::vector<uint8_t> h_hist;
     size_t hist_valid = 0;
@@ -234,7 +251,7 @@ int ensure_pipe(pm_engine* e) {
         CU(cudaEventCreateWithFlags(&e->done[b], cudaEventDisableTiming));
         e->scratch_bytes += e->halo + chunk + 16 + chunk * sizeof(uint16_t);
     }
-    e->pool.reset(new pm::HostPool(e->opts.host_threads));
+    e->pool.reset(new pm::HostPool(e->opts.host_threads, e->opts.cpu_first, e->opts.cpu_count));
     e->pipe_ready = true;
     return 0;
 }
@@ -322,6 +339,8 @@ int choose_algo(pm_engine* e, const uint8_t* d_stream, size_t n, size_t hist_val
 int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid, uint16_t* d_out,
                      cudaStream_t st, int slot) {
     if (n == 0) return 0;
+    if (!e->parts.empty())
+        return fail("this dictionary has more than 65,535 patterns: 16-bit results cannot name them; use pm_engine_scan_device32");
     if (algo == PM_ALGO_MPBG) {
         // the reference's MPBG, position for position: exact scan, then every answer demoted to the longest pattern of
         // <= 8 bytes on its PatternsTree chain (short_only_kernel; pinned by tests/golden/ref_snort.json: mpbg_file/line)
@@ -445,6 +464,51 @@ int ensure_compact_counts(pm_engine* e, size_t need) {
     return 0;
 }
 
+// ---- 32-bit results: any number of patterns --------------------------------------------------------------------
+
+constexpr size_t kSlice32 = size_t(64) << 20;   // positions per slice of a 32-bit scan (bounds the 16-bit scratch: 128 MiB)
+
+int ensure_tmp16(pm_engine* e, size_t need) {
+    if (need <= e->tmp16_cap) return 0;
+    if (e->d_tmp16) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->d_tmp16)); }
+    e->scratch_bytes -= e->tmp16_cap * sizeof(uint16_t);
+    e->d_tmp16 = nullptr; e->tmp16_cap = 0;
+    CU(cudaMalloc(reinterpret_cast<void**>(&e->d_tmp16), need * sizeof(uint16_t)));
+    e->tmp16_cap = need;
+    e->scratch_bytes += need * sizeof(uint16_t);
+    return 0;
+}
+
+// out32[i] = global pid of the longest pattern ending at i.  A single-part engine widens its 16-bit answer; a
+// multi-part engine scans once per part and keeps the longer answer (pm::merge_parts_launch).
+int scan_device32_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid, uint32_t* d_out,
+                       cudaStream_t st) {
+    if (n == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(d_stream) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
+        return fail("pm_engine_scan_device32: d_stream and d_out must be 16-byte aligned");
+    if (ensure_tmp16(e, std::min(n, kSlice32))) return -1;
+    const pm::Dict& d = *e->dict;
+    for (size_t off = 0; off < n; off += kSlice32) {
+        const size_t len = std::min(kSlice32, n - off);
+        const size_t hv = hist_valid + off;   // everything before the slice is readable
+        if (e->parts.empty()) {
+            if (scan_device_impl(e, algo, d_stream + off, len, hv, e->d_tmp16, st)) return -1;
+            cudaError_t ce = pm::merge_parts_launch(d_out + off, e->d_tmp16, len, 0, nullptr, true, e->n_sms, st, &e->launches);
+            if (ce != cudaSuccess) return cuda_fail(ce, "merge_parts_launch");
+        } else {
+            for (size_t k = 0; k < e->parts.size(); ++k) {
+                pm_engine* part = e->parts[k];
+                if (algo == PM_ALGO_KR) part->kr_seed = e->kr_seed;
+                if (scan_device_impl(part, algo, d_stream + off, len, hv, e->d_tmp16, st)) return -1;
+                cudaError_t ce = pm::merge_parts_launch(d_out + off, e->d_tmp16, len, d.part_first[k] - 1, e->d_glen, k == 0,
+                                                        e->n_sms, st, &e->launches);
+                if (ce != cudaSuccess) return cuda_fail(ce, "merge_parts_launch");
+            }
+        }
+    }
+    return 0;
+}
+
 // ---- host-buffer pipeline -------------------------------------------------------------------------------------
 
 // what a host scan hands back for every position
@@ -488,10 +552,46 @@ int scan_host_small(pm_engine* e, const uint8_t* stream, size_t n, const HostSin
     return 0;
 }
 
+// Host path of a multi-part engine: 8-byte ids only (16-bit pids cannot name its patterns).  Piece by piece and
+// synchronous: copy in, one scan + merge per part, 32-bit global pids back, translated by the host threads.
+int scan_host_ids_multi(pm_engine* e, int algo, const uint8_t* stream, size_t n, const HostSink& sink) {
+    const size_t H = e->halo, chunk = e->opts.host_chunk;
+    if (!e->d_out32) {
+        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_out32), chunk * sizeof(uint32_t)));
+        CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_out32), chunk * sizeof(uint32_t)));
+        e->scratch_bytes += chunk * sizeof(uint32_t);
+    }
+    const bool in_pinned = is_pinned(stream);
+    cudaStream_t st = e->st[0];
+    for (size_t o = 0; o < n; o += chunk) {
+        const size_t len = std::min(chunk, n - o);
+        const size_t from_call = std::min(o, H), hist_total = std::min(e->hist_valid + o, H);
+        uint8_t* din = e->d_in[0];
+        if (from_call < H) CU(cudaMemcpyAsync(din, e->h_hist.data() + from_call, H - from_call, cudaMemcpyHostToDevice, st));
+        const uint8_t* src = stream + o - from_call;
+        if (!in_pinned) { e->pool->copy(e->h_in[0], src, from_call + len); src = e->h_in[0]; }
+        CU(cudaMemcpyAsync(din + H - from_call, src, from_call + len, cudaMemcpyHostToDevice, st));
+        if (scan_device32_impl(e, algo, din + H, len, hist_total, e->d_out32, st)) return -1;
+        CU(cudaMemcpyAsync(e->h_out32, e->d_out32, len * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const uint32_t* res = e->h_out32;
+        const uint64_t* table = sink.table;
+        uint64_t* dst = sink.out64 + o;
+        e->pool->run(len, size_t(64) << 10, [res, table, dst](size_t lo, size_t hi) { for (size_t j = lo; j < hi; ++j) dst[j] = table[res[j]]; });
+    }
+    carry_history(e, stream, n);
+    return 0;
+}
+
 int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, const HostSink& sink) {
     CU(cudaSetDevice(e->device));
     if (n == 0) return 0;
     if (ensure_pipe(e)) return -1;
+    if (!e->parts.empty()) {
+        if (!sink.out64) return fail("this dictionary has more than 65,535 patterns: 16-bit results cannot name them; use gpu_read_block / pm_engine_scan_host_ids / pm_engine_scan_device32");
+        if (scan_host_ids_multi(e, algo, stream, n, sink)) { quiesce(e); return -1; }
+        return 0;
+    }
     if (algo == PM_ALGO_DFA && ensure_dfa(e)) return -1;
     if ((algo == PM_ALGO_KR || algo == PM_ALGO_MPBG) && ensure_kr(e)) return -1;
     if (n <= kSmallCall && (algo == PM_ALGO_SFX || algo == PM_ALGO_AUTO) && e->dict->sfx.fits_u16) {
@@ -752,8 +852,12 @@ int pm_host_unregister(void* p) {
     return 0;
 }
 
+static pm_engine* engine_create(const pm::Dict* dict, int device);
 pm_engine* pm_engine_create(const pm_dict* dd, int device) {
     if (!dd || !dd->d.compiled) { fail("pm_engine_create: dictionary is not compiled"); return nullptr; }
+    return engine_create(&dd->d, device);
+}
+static pm_engine* engine_create(const pm::Dict* dict, int device) {
     int count = 0;
     cudaError_t ce = cudaGetDeviceCount(&count);
     if (ce != cudaSuccess || count == 0) {
@@ -763,13 +867,28 @@ pm_engine* pm_engine_create(const pm_dict* dd, int device) {
     if ((ce = cudaSetDevice(device)) != cudaSuccess) { cuda_fail(ce, "cudaSetDevice"); return nullptr; }
     pm_engine* e = new (std::nothrow) pm_engine();
     if (!e) return nullptr;
-    e->dict = &dd->d;
+    e->dict = dict;
     e->device = device;
     e->opts = EngineOpts::from_env();
     cudaDeviceGetAttribute(&e->n_sms, cudaDevAttrMultiProcessorCount, device);
-    const pm::Dict& d = dd->d;
+    const pm::Dict& d = *dict;
     e->halo = std::max<size_t>(pm::kHalo, (size_t(d.max_len ? d.max_len - 1 : 0) + 15) / 16 * 16);
     e->h_hist.assign(e->halo, 0);
+    if (d.multi) {
+        // more than 65,535 patterns: one complete sub-engine per part; this object keeps the stream state, the host
+        // pipeline and the merge scratch (pattern lengths by global pid)
+        std::vector<uint32_t> glen(d.pats.size() + 1, 0);
+        for (size_t i = 0; i < d.pats.size(); ++i) glen[i + 1] = d.pats[i].len;
+        bool ok = upload(glen, &e->d_glen, &e->table_bytes) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&e->scratch_free, cudaEventDisableTiming) == cudaSuccess;
+        for (size_t k = 0; ok && k < d.parts.size(); ++k) {
+            pm_engine* part = engine_create(d.parts[k].get(), device);
+            if (!part) { ok = false; break; }
+            e->parts.push_back(part);
+        }
+        if (!ok) { if (g_err.empty()) cuda_fail(cudaGetLastError(), "pm_engine_create"); pm_engine_free(e); return nullptr; }
+        return e;
+    }
     auto up = [&](auto& vec, auto** ptr) -> bool {
         cudaError_t r = upload(vec, ptr, &e->table_bytes);
         if (r != cudaSuccess) { cuda_fail(r, "table upload"); return false; }
@@ -833,6 +952,11 @@ void pm_engine_free(pm_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
+    for (pm_engine* part : e->parts) pm_engine_free(part);
+    if (e->d_glen) cudaFree(e->d_glen);
+    if (e->d_tmp16) cudaFree(e->d_tmp16);
+    if (e->d_out32) cudaFree(e->d_out32);
+    if (e->h_out32) cudaFreeHost(e->h_out32);
     e->pool.reset();
     if (e->rows_tex) cudaDestroyTextureObject(e->rows_tex);
     void* ptrs[] = {e->d_root2, e->d_root1, e->d_rows, e->d_row_best, e->d_cls, e->d_pat_off, e->d_pat_len, e->d_pat_bytes,
@@ -859,7 +983,12 @@ void pm_engine_free(pm_engine* e) {
     delete e;
 }
 
-size_t pm_engine_total_mem(const pm_engine* e) { return e ? e->table_bytes : 0; }
+size_t pm_engine_total_mem(const pm_engine* e) {
+    if (!e) return 0;
+    size_t sum = e->table_bytes;
+    for (const pm_engine* part : e->parts) sum += part->table_bytes;
+    return sum;
+}
 size_t pm_engine_scratch_mem(const pm_engine* e) { return e ? e->scratch_bytes : 0; }
 int pm_engine_host_threads(const pm_engine* e) { return e ? e->opts.host_threads : 0; }
 uint64_t pm_engine_launch_count(const pm_engine* e) { return e ? e->launches : 0; }
@@ -917,9 +1046,23 @@ int pm_engine_scan_device(pm_engine* e, int algo, const uint8_t* d_stream, size_
     return rc;
 }
 
+int pm_engine_scan_device32(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid,
+                            uint32_t* d_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lock(e->mu);
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if (algo == PM_ALGO_AUTO) { e->auto_choice = -1; for (pm_engine* part : e->parts) part->auto_choice = -1; }
+    if (e->scratch_used) CU(cudaStreamWaitEvent(st, e->scratch_free, 0));
+    const int rc = scan_device32_impl(e, algo, d_stream, n, hist_valid, d_out, st);
+    CU(cudaEventRecord(e->scratch_free, st));
+    e->scratch_used = true;
+    return rc;
+}
+
 void pm_engine_reset(pm_engine* e) {
     std::lock_guard<std::mutex> lock(e->mu);
     e->auto_choice = -1;  // a new stream: PM_ALGO_AUTO samples again
+    for (pm_engine* part : e->parts) part->auto_choice = -1;
     e->hist_valid = 0;
     std::fill(e->h_hist.begin(), e->h_hist.end(), uint8_t(0));
 }
@@ -943,6 +1086,7 @@ int pm_engine_scan_host_ids(pm_engine* e, int algo, const uint8_t* stream, size_
 int pm_engine_scan_host_records(pm_engine* e, int algo, const uint8_t* stream, size_t n, uint32_t min_len,
                                 uint64_t* records, size_t cap, uint64_t* n_records) {
     std::lock_guard<std::mutex> lock(e->mu);
+    if (!e->parts.empty()) return fail("this dictionary has more than 65,535 patterns: only pm_engine_scan_device32, pm_engine_scan_host_ids and the plugin calls serve it");
     CU(cudaSetDevice(e->device));
     if (ensure_pipe(e)) return -1;
     if (algo == PM_ALGO_DFA && ensure_dfa(e)) return -1;
@@ -1019,6 +1163,7 @@ int pm_engine_scan_host_records(pm_engine* e, int algo, const uint8_t* stream, s
 
 int pm_engine_summarize(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t pos_base, uint64_t out4[4], void* cuda_stream) {
     std::lock_guard<std::mutex> lock(e->mu);
+    if (!e->parts.empty()) return fail("this dictionary has more than 65,535 patterns: only pm_engine_scan_device32, pm_engine_scan_host_ids and the plugin calls serve it");
     CU(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     cudaError_t ce = pm::summarize_launch(d_out, n, pos_base, e->pt, e->d_acc, e->n_sms, st, &e->launches);
@@ -1032,6 +1177,7 @@ int pm_engine_summarize(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t 
 
 int pm_engine_classify(pm_engine* e, const uint16_t* d_algo, const uint16_t* d_real, size_t n, uint64_t counts4[4], void* cuda_stream) {
     std::lock_guard<std::mutex> lock(e->mu);
+    if (!e->parts.empty()) return fail("this dictionary has more than 65,535 patterns: only pm_engine_scan_device32, pm_engine_scan_host_ids and the plugin calls serve it");
     CU(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     if ((reinterpret_cast<uintptr_t>(d_algo) & 15) || (reinterpret_cast<uintptr_t>(d_real) & 15))
@@ -1048,6 +1194,7 @@ int pm_engine_classify(pm_engine* e, const uint16_t* d_algo, const uint16_t* d_r
 int pm_engine_compact(pm_engine* e, const uint16_t* d_out, size_t n, uint64_t pos_base, int expand_ancestors,
                       uint64_t* d_records, size_t cap, uint64_t* n_records, void* cuda_stream) {
     std::lock_guard<std::mutex> lock(e->mu);
+    if (!e->parts.empty()) return fail("this dictionary has more than 65,535 patterns: only pm_engine_scan_device32, pm_engine_scan_host_ids and the plugin calls serve it");
     CU(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     if (ensure_compact_counts(e, pm::compact_blocks(n) + 1)) return -1;
@@ -1065,6 +1212,7 @@ int pm_engine_scan_device_records(pm_engine* e, int algo, const uint8_t* d_strea
                                   uint64_t pos_base, uint32_t min_len, uint16_t* d_out, uint64_t* d_records, size_t cap,
                                   uint64_t* n_records, void* cuda_stream) {
     std::lock_guard<std::mutex> lock(e->mu);
+    if (!e->parts.empty()) return fail("this dictionary has more than 65,535 patterns: only pm_engine_scan_device32, pm_engine_scan_host_ids and the plugin calls serve it");
     CU(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     if (n == 0) { *n_records = 0; return 0; }
@@ -1115,6 +1263,7 @@ int pm_engine_scan_device_records(pm_engine* e, int algo, const uint8_t* d_strea
 
 int pm_engine_generate(pm_engine* e, int kind, uint64_t off, size_t n, uint8_t* d_dst, void* cuda_stream) {
     std::lock_guard<std::mutex> lock(e->mu);
+    if (!e->parts.empty()) return fail("this dictionary has more than 65,535 patterns: only pm_engine_scan_device32, pm_engine_scan_host_ids and the plugin calls serve it");
     CU(cudaSetDevice(e->device));
     if ((off & 4095) || (n & 4095)) return fail("pm_engine_generate: off and n must be multiples of 4096");
     cudaError_t ce = pm::generate_launch(kind, off, n, d_dst, e->pt, static_cast<cudaStream_t>(cuda_stream), &e->launches);

@@ -44,7 +44,8 @@ class HostPool {
     };
     using Ticket = std::shared_ptr<Job>;
 
-    explicit HostPool(int n_threads) : n_(n_threads < 1 ? 1 : n_threads) {
+    // cpu_first / cpu_count: the slice of the allowed CPUs this pool may pin its workers to (0 / 0 = all of them)
+    explicit HostPool(int n_threads, int cpu_first = 0, int cpu_count = 0) : n_(n_threads < 1 ? 1 : n_threads) {
         // the caller takes part in every job it waits for, so n_ - 1 workers make n_ threads
         for (int i = 0; i + 1 < n_; ++i) workers_.emplace_back([this] { loop(); });
 #if defined(__linux__)
@@ -55,6 +56,10 @@ class HostPool {
         if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
             std::vector<int> cpus;
             for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &allowed)) cpus.push_back(c);
+            if (cpu_count > 0 && size_t(cpu_first) < cpus.size()) {
+                const size_t hi = std::min(cpus.size(), size_t(cpu_first) + size_t(cpu_count));
+                cpus = std::vector<int>(cpus.begin() + cpu_first, cpus.begin() + hi);
+            }
             for (size_t w = 0; w < workers_.size() && !cpus.empty(); ++w) {
                 cpu_set_t one;
                 CPU_ZERO(&one);

@@ -107,6 +107,70 @@ def test_reference_stream_matches_golden(name):
         assert "%016x" % s["hsum_longest"] == gold["hsum_longest"] and "%016x" % s["hsum_all"] == gold["hsum_all"]
 
 
+def test_more_than_65535_patterns():
+    """70,000 unique patterns (the reference's Aho-Corasick takes any number, mpac.c:257-291): the dictionary compiles into
+    two parts, the engine scans once per part and keeps the longer answer.  32-bit device results and the plugin call
+    against the oracle; the 16-bit entry points refuse with a message instead of truncating."""
+    rng = np.random.default_rng(65536)
+    sym = np.frombuffer(b"abcdefgh", np.uint8)
+    pats, seen = [], set()
+    while len(pats) < 70000:
+        L = int(rng.integers(3, 13))
+        p = bytes(rng.choice(sym, L))
+        if p not in seen:
+            seen.add(p); pats.append(p)
+    for p in list(pats[:300]):                       # nested patterns whose parents sit in the other part
+        q = p[-2:]
+        if q not in seen:
+            seen.add(q); pats.append(q)
+    d = pm.Dictionary(); o = Oracle()
+    for i, p in enumerate(pats):
+        d.add_pattern(p, 0, i + 1); o.add_pattern(p, 0, i + 1)
+    d.compile(); o.compile()
+    assert d.n_patterns == len(pats) > 65535
+    eng = pm.Engine(d)
+    stream = rng.choice(sym, 300_000).astype(np.uint8)
+    for k in range(2000):                            # planted occurrences of patterns from both parts
+        p = pats[int(rng.integers(0, len(pats)))]
+        c = int(rng.integers(0, stream.size - 16))
+        stream[c:c + len(p)] = np.frombuffer(p, np.uint8)
+    want = (o.scan(stream) + 1).astype(np.uint32)
+    assert (want > 49152).any() and ((want > 0) & (want <= 49152)).any()
+    torch, dev = torch_dev()
+    d_in = torch.from_numpy(stream).to(dev)
+    for algo in (pm.ALGO_SFX, pm.ALGO_DFA, pm.ALGO_AUTO):
+        d_out = torch.zeros(stream.size, dtype=torch.int32, device=dev)
+        eng.scan_device32(d_in, stream.size, d_out, algo=algo)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint32), want), algo
+    cut = 100_000                                    # a shard with history
+    d_out = torch.zeros(stream.size - cut, dtype=torch.int32, device=dev)
+    eng.scan_device32(d_in.data_ptr() + cut - cut % 16, stream.size - cut + cut % 16, d_out, hist_valid=cut - cut % 16)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint32), want[cut - cut % 16:])
+    with pytest.raises(pm.PmError, match="more than 65,535 patterns"):
+        eng.scan_device(d_in, stream.size, torch.zeros(stream.size, dtype=torch.int16, device=dev))
+    with pytest.raises(pm.PmError, match="more than 65,535 patterns"):
+        eng.scan_host(stream)
+    # a small dictionary through the same 32-bit entry point
+    small = pm.Dictionary().add_bytes(TINY_DICT).compile()
+    so = Oracle(); so.add_dict_bytes(TINY_DICT); so.compile()
+    s2 = np.frombuffer(TINY_STREAM * 50, np.uint8)
+    d2 = torch.zeros(s2.size, dtype=torch.int32, device=dev)
+    pm.Engine(small).scan_device32(torch.from_numpy(s2.copy()).to(dev), s2.size, d2)
+    torch.cuda.synchronize()
+    assert np.array_equal(d2.cpu().numpy().view(np.uint32), (so.scan(s2) + 1).astype(np.uint32))
+    # the plugin surface: 8-byte ids, state carried over ragged calls
+    m = pm.MpsGpu("sfx")
+    for i, p in enumerate(pats):
+        m.add_pattern(p, i + 1)
+    m.compile(); m.reset()
+    got = np.concatenate([m.read_block(stream[a:b].tobytes()) for a, b in ((0, 1), (1, 77), (77, 150_000), (150_000, stream.size))])
+    assert np.array_equal(got.astype(np.uint32), want)
+    assert m.total_mem() > 0
+    m.free()
+
+
 @pytest.mark.parametrize("max_len", [1, 2, 3, 4, 5, 9])
 def test_short_history_with_short_patterns(max_len):
     """1 .. 5 bytes of history in front of a scan whose longest pattern is as short: the history covers every pattern

@@ -98,7 +98,8 @@ def test_tiny_dictionary_shape():
 def test_limits_are_reported_not_silently_truncated():
     """The reference's Aho-Corasick takes any dictionary (mpac.c:257-291).  Here: patterns of any length and any number of
     2-byte continuations compile (the engine serves dictionaries without backward-scan tables with the forward walkers);
-    what dense uint16 results cannot name -- more than 65,535 unique patterns -- is refused with a message."""
+    more than 65,535 unique patterns -- which dense uint16 results cannot name -- compile into parts that an engine scans
+    one after the other (32-bit results; tests/test_gpu_parity.py::test_more_than_65535_patterns)."""
     d = pm.Dictionary()
     d.add_pattern(b"x" * 354, 0, 1)                                      # beyond the round-1 limit of 353 bytes
     d.add_pattern(b"y" * 5000, 0, 2)                                     # beyond what the backward scan's queue items encode
@@ -110,11 +111,13 @@ def test_limits_are_reported_not_silently_truncated():
         d.add_pattern(bytes(rng.integers(0, 256, 4, dtype=np.uint8)), 0, i + 1)
     d.compile()
     assert d.n_patterns + d.info.n_hot2_cont > 65535
-    d = pm.Dictionary()                                                  # more patterns than dense uint16 results can name
-    for i in range(66000):
+    d = pm.Dictionary()                                                  # more patterns than dense uint16 results can name:
+    for i in range(66000):                                               # compiled into parts (32-bit results, dict.hpp)
         d.add_pattern(b"%07d" % i, 0, i + 1)
-    with pytest.raises(pm.PmError, match="more than 65,535 unique patterns"):
-        d.compile()
+    d.add_pattern(b"0001", 0, 70001)                                     # a suffix of b"0000001" and of nothing else
+    d.compile()
+    assert d.n_patterns == 66001 and d.max_pat_len == 7
+    assert d.pattern(2)[3] == 66001 and d.pattern(66001)[3] == 0        # the PatternsTree relation spans the parts
 
 
 def test_compiled_dictionary_cache_round_trip(tmp_path, dict_merged):
