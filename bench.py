@@ -429,7 +429,9 @@ def main():
     regimes = {k: round(v, 3) for k, v in regimes.items()}
     regimes["records_per_step"] = int(n_rec[0])
     regimes["note"] = ("aggregate GB/s of stream over all ranks; read_block writes 8-byte pattern ids (the reference's read_char contract, "
-                       "mps.h:41-42): bound by the host's memory system; scan_host_u16 returns dense uint16 pids: bound by PCIe (2 B per position)")
+                       "mps.h:41-42): bound by the host threads' store rate (scripts/microbench/host_mem.cpp: 107-131 GB/s of ids = "
+                       "13-16 GB/s of stream with 8-16 threads on the 16-vCPU box); scan_host_u16 returns dense uint16 pids: bound by PCIe "
+                       "(2 B per position)")
 
     # what the host link gives a plain pinned copy while EVERY rank copies at once (the regime of the e2e numbers above)
     link = None
@@ -487,7 +489,8 @@ def main():
         "roofline": roofline_entry(args.algo, n, ms_step, main_ms, scan_ms, n_prof, peak, peak_src),
         "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": ne, "d2h_bytes_per_step": 2 * ne,
                 "call": "gpu_read_block (MpsElem plugin surface, mps_gpu_shim.c): page-locked stream in, 8-byte pattern ids out "
-                        f"({8 * ne} bytes written on the host per step), one call per {ne >> 20} MiB",
+                        f"({8 * ne} bytes written on the host per step by {eng.host_threads} host threads from the 2-byte pids "
+                        f"that cross PCIe), one call per {ne >> 20} MiB",
                 "steps": e2e_steps, "matches_device_result": e2e_ok, "host_threads": eng.host_threads, "regimes": regimes,
                 "host_link": link},
         "sparse": sparse,
@@ -572,6 +575,34 @@ def config_block(pm, torch, np, eng, d, buf, out, lead, n16, ref, peak, args):
 
     def same(a, b):
         return all(int(a[k]) == int(b[k]) for k in ("positions", "matches", "hsum_longest", "hsum_all"))
+
+    # C1: snort.dict on the reference's own 10 KB stream, through the plugin call (BASELINE configs[0]); the results must carry
+    # the digests of the reference's AC (tests/golden/ref_snort.json, generated from the unmodified reference), and the
+    # PM_ALGO_MPBG mode must reproduce the reference MPBG's success counts (results.csv row of MPBG on this config)
+    try:
+        gold = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_snort.json")))
+        s1 = np.fromfile(os.path.join(DATA, gold["stream"]), dtype=np.uint8)
+        d1 = pm.Dictionary().add_file(DICTS[0]).compile()
+        e1 = pm.Engine(d1, device=dev.index or 0)
+        t_small = []
+        for _ in range(20):
+            e1.reset(); t0 = time.perf_counter(); got = e1.scan_host(s1, algo=pm.ALGO_AUTO); t_small.append(time.perf_counter() - t0)
+        d_got = torch.from_numpy(got.view(np.int16).copy()).to(dev)
+        sg = e1.summarize(d_got, s1.size)
+        e1.reset(); mp = e1.scan_host(s1, algo=pm.ALGO_MPBG)
+        c = e1.classify(torch.from_numpy(mp.view(np.int16).copy()).to(dev), d_got, s1.size)
+        res["C1_snort_reference_stream"] = {
+            "bytes": int(s1.size), "ms": sorted(t_small)[len(t_small) // 2] * 1e3, "value": s1.size / sorted(t_small)[len(t_small) // 2] / 1e9, "unit": "GB/s",
+            "kernel": "sfx_edge_kernel (one launch: calls of <= 256 KiB are launch-latency bound)", "call": "pm_engine_scan_host, host buffers",
+            "matches_reference": bool(sg["positions"] == gold["positions"] and sg["matches"] == gold["matches"] and
+                                      "%016x" % sg["hsum_longest"] == gold["hsum_longest"] and "%016x" % sg["hsum_all"] == gold["hsum_all"]),
+            "reference_ac_seconds_same_config_survey_8c": 0.002133,
+            "mpbg_mode_counts_vs_exact": [c["success"], c["partial"], c["false_neg"], c["false_pos"]],
+            "reference_mpbg_counts_vs_its_ac": gold["mpbg_vs_ac_counts"],
+            "mpbg_mode_matches_reference": [c["success"], c["partial"], c["false_neg"], c["false_pos"]] == gold["mpbg_vs_ac_counts"]}
+        del e1
+    except Exception as ex:
+        res["C1_snort_reference_stream"] = {"error": str(ex)[:200]}
 
     choice_name = {0: "sfx_scan_kernel (backward suffix-trie scan)", 1: "dfa_small_kernel / dfa_hot_kernel (forward DFA in shared memory)",
                    4: "deep_scan_kernel (compact goto+failure records)", -1: "undecided"}

@@ -73,7 +73,7 @@ def to_bytes(name):
 if nbytes:
     rd, wr = to_bytes("dram__bytes_read.sum"), to_bytes("dram__bytes_write.sum")
     rnd = re.search(r"r(\d+)", tag).group(1)
-    json.dump({"kernel": get("Kernel Name"), "stream_bytes": nbytes, "dram_bytes_read": rd, "dram_bytes_write": wr,
+    json.dump({"algo": "sfx", "kernel": get("Kernel Name"), "stream_bytes": nbytes, "dram_bytes_read": rd, "dram_bytes_write": wr,
                "dram_bytes_per_stream_byte": (rd + wr) / nbytes, "algorithmic_bytes_per_stream_byte": 3,
                "source": os.path.basename(rep)}, open(os.path.join(ROOT, "profiles", f"traffic_r{rnd}.json"), "w"), indent=1)
 print(open(os.path.join(ROOT, "profiles", f"{tag}_launches.md")).read())
