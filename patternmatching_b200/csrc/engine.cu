@@ -1067,6 +1067,12 @@ void pm_engine_reset(pm_engine* e) {
     std::fill(e->h_hist.begin(), e->h_hist.end(), uint8_t(0));
 }
 
+int pm_engine_prepare_host(pm_engine* e) {
+    std::lock_guard<std::mutex> lock(e->mu);
+    CU(cudaSetDevice(e->device));
+    return ensure_pipe(e);
+}
+
 int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n, uint16_t* out) {
     std::lock_guard<std::mutex> lock(e->mu);
     HostSink sink;

