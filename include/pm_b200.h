@@ -122,7 +122,7 @@ size_t pm_engine_total_mem(const pm_engine* e);
 /* device scratch that is not a table: deferred-walk queues (at most 2 MiB per SM and pipeline slot), the host
  * pipeline's device buffers, compaction counters.  Grows on demand, never shrinks. */
 size_t pm_engine_scratch_mem(const pm_engine* e);
-/* host threads used to stage pageable buffers and to translate pids (PM_HOST_THREADS; default = half the cores, at most 16) */
+/* host threads used to stage pageable buffers and to translate pids (PM_HOST_THREADS; default = three quarters of this rank's share of the cores, at most 16) */
 int pm_engine_host_threads(const pm_engine* e);
 /* KR variant parameters: r is drawn from `seed` (the reference draws it from rand(), bgps.c:469-475) */
 int pm_engine_set_kr_seed(pm_engine* e, uint64_t seed);

@@ -62,10 +62,10 @@ constexpr size_t kQueueMaxPerCta = size_t(256) << 10;  // deferred-walk slots pe
 
 // Diagnostic / A-B switches, read ONCE when an engine is created.
 struct EngineOpts {
-    bool sfx_no_tex = false, sfx_no_l3 = false, dfa_no_fb = false, dfa_flat = false, dfa_deep = false, dfa_no_fused = false;
+    bool sfx_no_tex = false, sfx_no_l3 = false, dfa_no_fb = false, dfa_flat = false, dfa_deep = false, dfa_no_fused = false, kr_no_bulk = false;
     uint32_t l3_min = 4, l3_min_b = 4;
     size_t host_chunk = size_t(16) << 20;  // bytes per pipeline slot for pinned buffers (PM_HOST_CHUNK_MIB)
-    int host_threads = 0;                  // staging threads (PM_HOST_THREADS; default: half of this rank's share of the host's cores, at most 16)
+    int host_threads = 0;                  // staging threads (PM_HOST_THREADS; default: 3/4 of this rank's share of the host's cores, at most 16)
     int cpu_first = 0, cpu_count = 0;      // this rank's share of the CPUs (the workers are pinned inside it)
     // PM_HOST_IDS=device|host|<N>: where pids become 8-byte ids when the result buffer is page-locked: every piece on the
     // device (1), every piece by the host threads (0), or every N-th piece on the device and the rest by the host threads
@@ -79,14 +79,16 @@ struct EngineOpts {
         o.dfa_flat = getenv("PM_DFA_FLAT") != nullptr;
         o.dfa_deep = getenv("PM_DFA_DEEP") != nullptr;
         o.dfa_no_fused = getenv("PM_DFA_NO_FUSED") != nullptr;
+        o.kr_no_bulk = getenv("PM_KR_NO_BULK") != nullptr;
         if (const char* v = getenv("PM_SFX_L3_MIN")) o.l3_min = o.l3_min_b = uint32_t(atoi(v));
         if (const char* v = getenv("PM_SFX_L3_MIN_B")) o.l3_min_b = uint32_t(atoi(v));
         if (const char* v = getenv("PM_HOST_CHUNK_MIB")) { const long m = atol(v); if (m >= 1 && m <= 1024) o.host_chunk = size_t(m) << 20; }
         // One process per GPU (torchrun sets LOCAL_WORLD_SIZE / LOCAL_RANK): the ranks of a box split its cores, and each
         // pins its workers inside its own share -- eight ranks that all take "half the cores" and pin them to the same
-        // CPUs starve each other.  Within the share: half of the cores (at most 16): on the 16-vCPU B200 box 8 threads
-        // gave the best host-path numbers, 16 (one per core, competing with the CUDA driver's own threads and the
-        // caller) were slower.
+        // CPUs starve each other.  Within the share: three quarters of the cores (at most 16): on the 16-vCPU B200 box
+        // 12 threads gave the best host-path numbers in same-box comparisons (8: 10.8-11.1, 12: 12.2-12.3, 16: 12.6 GB/s
+        // for page-locked 1 GiB gpu_read_block calls, but 16 lost on 16 MiB calls: one per core competes with the CUDA
+        // driver's own threads and the caller).
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         unsigned lws = 1, lrank = 0;
         if (const char* v = getenv("LOCAL_WORLD_SIZE")) lws = unsigned(std::max(1, atoi(v)));
@@ -94,7 +96,7 @@ struct EngineOpts {
         const unsigned share = std::max(1u, hw / lws);
         o.cpu_first = int((lrank % lws) * share);
         o.cpu_count = int(share);
-        o.host_threads = int(std::max(1u, std::min<unsigned>(share >= 4 ? share / 2 : share, 16)));
+        o.host_threads = int(std::max(1u, std::min<unsigned>(share >= 4 ? share * 3 / 4 : share, 16)));
         if (const char* v = getenv("PM_HOST_THREADS")) { const int t = atoi(v); if (t >= 1 && t <= 256) o.host_threads = t; }
         if (const char* v = getenv("PM_HOST_IDS")) o.ids_device_every = v[0] == 'd' ? 1 : v[0] == 'h' ? 0 : std::max(0, atoi(v));
         return o;
@@ -410,7 +412,7 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
             cudaError_t ce = pm::deep_scan_launch(p, e->n_sms, st, &e->launches);
             if (ce != cudaSuccess) return cuda_fail(ce, "deep_scan_launch");
             if (kr_after) {
-                ce = pm::kr_scan_launch(e->kr, d_stream, n, hist_valid, d_out, e->pt, e->n_sms, st, &e->launches);
+                ce = pm::kr_scan_launch(e->kr, d_stream, n, hist_valid, d_out, e->pt, e->n_sms, st, &e->launches, !e->opts.kr_no_bulk);
                 if (ce != cudaSuccess) return cuda_fail(ce, "kr_scan_launch");
             }
             return 0;
@@ -430,7 +432,7 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
         cudaError_t ce = pm::dfa_scan_launch(p, d.sfx.cls_identity, force_flat || e->opts.dfa_flat, e->n_sms, st, &e->launches);
         if (ce != cudaSuccess) return cuda_fail(ce, "dfa_scan_launch");
         if (kr_after) {
-            ce = pm::kr_scan_launch(e->kr, d_stream, n, hist_valid, d_out, e->pt, e->n_sms, st, &e->launches);
+            ce = pm::kr_scan_launch(e->kr, d_stream, n, hist_valid, d_out, e->pt, e->n_sms, st, &e->launches, !e->opts.kr_no_bulk);
             if (ce != cudaSuccess) return cuda_fail(ce, "kr_scan_launch");
         }
         return 0;
@@ -446,7 +448,7 @@ int scan_device_impl(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, 
         if (fill_sfx_params(e, &p, n, slot)) return -1;
         cudaError_t ce = pm::sfx_scan_launch(p, d.sfx.cls_identity, e->n_sms, d.max_len, st, &e->launches);
         if (ce != cudaSuccess) return cuda_fail(ce, "sfx_scan_launch");
-        ce = pm::kr_scan_launch(e->kr, d_stream, n, hist_valid, d_out, e->pt, e->n_sms, st, &e->launches);
+        ce = pm::kr_scan_launch(e->kr, d_stream, n, hist_valid, d_out, e->pt, e->n_sms, st, &e->launches, !e->opts.kr_no_bulk);
         if (ce != cudaSuccess) return cuda_fail(ce, "kr_scan_launch");
         return 0;
     }

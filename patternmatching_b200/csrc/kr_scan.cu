@@ -43,7 +43,7 @@ constexpr int kOffBloom = 0;                                  // 65536
 constexpr int kOffRpow = kOffBloom + kBloomWords * 4;
 constexpr int kOffRinv = kOffRpow + kPowBytes;
 constexpr int kOffWarp = kOffRinv + kPowBytes;                // per warp: phi[(kSpan + 1)] u32, then the staged bytes
-constexpr int kWarpBytes = kPowBytes + kSpan;
+constexpr int kWarpBytes = kPowBytes + kSpan + 16;             // + the warp's mbarrier (bulk-copy staging)
 constexpr int kSmem = kOffWarp + kWarps * kWarpBytes;
 static_assert(kWarpBytes % 16 == 0 && kSmem <= 227 * 1024, "shared memory budget");
 
@@ -54,6 +54,7 @@ struct KrParams {
     uint16_t* out;
     const uint32_t* pat_len;  // by canonical index
     uint32_t n_tiles;
+    uint32_t bulk;            // stage full tiles with one bulk async copy (TMA engine) per tile
 };
 
 // A position whose 8-byte fingerprint passed the Bloom test: probe the table of 8-byte-suffix fingerprints and
@@ -101,6 +102,9 @@ __global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint32_t* s_phi = reinterpret_cast<uint32_t*>(smem + kOffWarp + wid * kWarpBytes);
     uint8_t* s_bytes = reinterpret_cast<uint8_t*>(s_phi) + kPowBytes;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bytes + kSpan);     // this warp's mbarrier
+    uint32_t bar_parity = 0;
+    if (lane == 0) { mbar_init(s_bar, 1); fence_mbar_init(); }
 
     for (int i = tid; i < kBloomWords; i += kThreads) s_bloom[i] = __ldg(p.t.bloom + i);
     for (int i = tid; i <= kSpan; i += kThreads) { s_rpow[i] = __ldg(p.t.rpow + i); s_rinv[i] = __ldg(p.t.rinvpow + i); }
@@ -112,8 +116,22 @@ __global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) 
         const uint32_t len = uint32_t(min(uint64_t(kWT), p.n - s0));
         // ---- stage [s0 - kLead, s0 + kWT): 16-byte pieces, zeros where the stream has no byte ----
         const int64_t lo = -int64_t(p.hist_valid), hi = int64_t(p.n);   // readable range, relative to p.stream
+        // A tile that is readable as a whole (all but the first and the last of a scan) is staged by ONE bulk async copy:
+        // lane 0 arms the warp's mbarrier with the byte count and hands the 544-byte copy to the TMA engine
+        // (cp.async.bulk, SASS UBLKCP); the warp waits on the barrier's phase.  The fence orders the previous tile's
+        // generic-proxy reads of the buffer before the async-proxy write.
+        const bool whole = p.bulk && int64_t(s0) - kLead >= lo && int64_t(s0) + kWT <= hi;
+        if (whole) {
+            if (lane == 0) {
+                fence_proxy_async();
+                mbar_arrive_expect_tx(s_bar, kSpan);
+                bulk_g2s(s_bytes, p.stream + (int64_t(s0) - kLead), kSpan, s_bar);
+            }
+            mbar_wait(s_bar, bar_parity);
+            bar_parity ^= 1u;
+        }
 #pragma unroll
-        for (int k = 0; k < (kSpan / 16 + 31) / 32; ++k) {
+        for (int k = 0; !whole && k < (kSpan / 16 + 31) / 32; ++k) {
             const int j = k * 32 + lane;
             if (j < kSpan / 16) {
                 const int64_t g = int64_t(s0) - kLead + 16 * j;
@@ -265,11 +283,12 @@ void kr_free_tables(KrDevTables* t) {
 }
 
 cudaError_t kr_scan_launch(const KrDevTables& t, const uint8_t* stream, uint64_t n, uint64_t hist_valid, uint16_t* out,
-                           const PatTables& pt, int n_sms, cudaStream_t st, uint64_t* launches) {
+                           const PatTables& pt, int n_sms, cudaStream_t st, uint64_t* launches, bool bulk) {
     if (n == 0) return cudaSuccess;
     KrParams p{};
     p.t = t; p.stream = stream; p.n = n; p.hist_valid = hist_valid; p.out = out; p.pat_len = pt.len;
     p.n_tiles = uint32_t((n + kKrTile - 1) / kKrTile);
+    p.bulk = (bulk && (reinterpret_cast<uintptr_t>(stream) & 15) == 0) ? 1u : 0u;
     cudaError_t e = cudaFuncSetAttribute(kr_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return e;
     const uint32_t ctas = (p.n_tiles + kWarps - 1) / kWarps;

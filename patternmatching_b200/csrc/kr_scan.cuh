@@ -26,7 +26,7 @@ void kr_free_tables(KrDevTables* t);
 // d_out holds the exact dense result on entry (used ONLY through short_of[], i.e. for the patterns
 // of <= 8 bytes that the variant matches exactly) and the variant's result on exit.
 cudaError_t kr_scan_launch(const KrDevTables& t, const uint8_t* stream, uint64_t n, uint64_t hist_valid, uint16_t* out,
-                           const PatTables& pt, int n_sms, cudaStream_t st, uint64_t* launches);
+                           const PatTables& pt, int n_sms, cudaStream_t st, uint64_t* launches, bool bulk = true);
 
 // out[i] = short_of[out[i]] in place: the observable behaviour of the reference's MPBG (only patterns of <= 8 bytes are
 // ever reported, Core/src/mpbg.c:132-145 + SURVEY Q5); `out` holds the exact dense result on entry, 16-byte aligned.

@@ -14,7 +14,7 @@ __host__ __device__ __forceinline__ uint64_t splitmix64_d(uint64_t x) {
     return z ^ (z >> 31);
 }
 
-// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) ----
+// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP): the staging of kr_scan_kernel's tiles ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -45,22 +45,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// shared -> global bulk store (bulk async-group completion)
-__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-template <int N>
-__device__ __forceinline__ void bulk_wait() {
-    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
-}
-
 // ---- GF(2^31-1) arithmetic (Core/src/field.h:61-80 restated for a Mersenne prime) ----
 __host__ __device__ __forceinline__ uint32_t kr_reduce(uint64_t x) {  // x < 2^62
     uint32_t lo = uint32_t(x & 0x7FFFFFFFu), hi = uint32_t(x >> 31);
