@@ -163,9 +163,10 @@ int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n,
 /* Same pipeline; out[i] = id_of_pid[pid of the longest pattern ending at i] -- 8 bytes per position, what the
  * reference's read_char returns (pattern_id_t is a pointer, Core/src/PatternsTree.h:104; Core/src/mps.h:41-42).
  * id_of_pid has n_ids >= P + 1 entries, entry 0 = the "no pattern" id.  The translation runs on the engine's host
- * threads piece by piece while later pieces are still on the GPU; when `out` is page-locked (and 16-byte aligned) the
- * translation happens on the device instead and the ids arrive by DMA (8 B per position over PCIe, no host thread
- * involved).  This is what gpu_read_block calls. */
+ * threads piece by piece while later pieces are still on the GPU (2 B per position cross PCIe; 13-16 GB/s of stream on
+ * the B200 box's host).  With PM_HOST_IDS=device -- or when the engine has a single host thread -- and a page-locked,
+ * 16-byte aligned `out`, the translation happens on the device instead and the ids arrive by DMA (8 B per position
+ * over PCIe: 6-7 GB/s at best, but no host thread works).  This is what gpu_read_block calls. */
 int pm_engine_scan_host_ids(pm_engine* e, int algo, const uint8_t* stream, size_t n, const uint64_t* id_of_pid,
                             size_t n_ids, uint64_t* out);
 /* Same pipeline, sparse result: only the positions whose longest match is a pattern of at least min_len bytes

@@ -606,15 +606,17 @@ int scan_host_impl(pm_engine* e, int algo, const uint8_t* stream, size_t n, cons
     const bool direct_out = sink.out16 && is_pinned(sink.out16);   // the D2H copy lands in the caller's buffer
     // 8-byte ids: translated by the host threads from the 2-byte pids (2 B per position over PCIe; the box's host writes
     // 107-131 GB/s of ids with 8-16 threads, scripts/microbench/host_mem.cpp), or -- into a page-locked buffer, when the
-    // engine has fewer than four host threads (or PM_HOST_IDS=device) -- translated on the device and sent by DMA (8 B per
+    // engine has a single host thread (or PM_HOST_IDS=device) -- translated on the device and sent by DMA (8 B per
     // position over PCIe: 6-7 GB/s of stream at most)
     const bool ids_pinned = sink.out64 && is_pinned(sink.out64) && (reinterpret_cast<uintptr_t>(sink.out64) & 15) == 0;
-    // every dev_every-th piece is translated on the device (0 = none, 1 = all).  Default: none with >= 4 host threads.
+    // every dev_every-th piece is translated on the device (0 = none, 1 = all).  Default: none unless the engine has a
+    // single host thread (eight ranks with 3 threads each on a 32-vCPU box: host 12.3 GB/s aggregate, device 6.4, every
+    // 2nd / 3rd piece on the device 8.8 / 10.0 -- scripts/e2e_ranks.py).
     // Mixing the two was measured on the B200 box (1 GiB, page-locked buffers, 8 / 12 threads): host only 10.8 / 12.2 GB/s,
     // every 5th piece on the device 11.2 / 10.4, every 3rd 9.5 / 9.5, device only 6.3 / 6.3 -- the DMA writes of 8-byte
     // ids compete with the host threads for the same memory system, so the mix gains nothing.
     const size_t dev_every = !ids_pinned ? 0 : e->opts.ids_device_every >= 0 ? size_t(e->opts.ids_device_every)
-                                             : (e->opts.host_threads < 4 ? 1 : 0);
+                                             : (e->opts.host_threads < 2 ? 1 : 0);
     const bool device_ids = dev_every == 1;
     auto dev_piece = [&](size_t k) { return dev_every != 0 && k % dev_every == dev_every - 1; };
     if (dev_every != 0) {
