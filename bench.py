@@ -322,15 +322,16 @@ def main():
             dist.all_reduce(cnts)
             all_cap = int(cnts.item()) + 16
             allrec = torch.empty(all_cap if rank == 0 else 1, dtype=torch.int64, device=dev)
-            comm.gather_records(rec, min(cnt, cap), allrec, all_cap, root=0, cuda_stream=st)      # warm-up (connections)
+            for _ in range(2):                                                                     # warm-up (connections, channel buffers)
+                comm.gather_records(rec, min(cnt, cap), allrec, all_cap, root=0, cuda_stream=st)
             barrier()
             g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
             g0.record()
-            for _ in range(3):
+            for _ in range(5):
                 counts, tot = comm.gather_records(rec, min(cnt, cap), allrec, all_cap, root=0, cuda_stream=st)
             g1.record()
             barrier()
-            g_ms = reduce_max(g0.elapsed_time(g1)) / 3
+            g_ms = reduce_max(g0.elapsed_time(g1)) / 5
             recv_bytes = 8 * (tot - counts[0])
             sparse["gather"] = {"ms": g_ms, "records_total": int(tot), "bytes_into_rank0": int(recv_bytes),
                                 "effective_GBps_into_rank0": recv_bytes / (g_ms * 1e-3) / 1e9 if g_ms else None,
