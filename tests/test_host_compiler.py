@@ -246,3 +246,16 @@ def test_deep_automaton_records_walk_like_the_oracle(dict_merged, oracle_merged)
     stream = rng.choice(np.frombuffer(b"aaabbc", np.uint8), 50000)
     got, _, _ = emulate_deep_walk(d, stream)
     assert np.array_equal(got, (o.scan(stream) + 1).astype(np.uint16))
+
+
+def test_host_thread_pool_stress(tmp_path):
+    """The staging pool of the host pipeline (host_pool.hpp: asynchronous jobs, caller participation, polling workers) is
+    plain C++ without CUDA: built here with g++ and driven with random job mixes -- several jobs in flight, waited out of
+    order, empty jobs, workers that fell asleep -- plus the pid -> id translation loop against a scalar loop."""
+    import subprocess
+    exe = str(tmp_path / "pool_stress")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "patternmatching_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "host_pool_stress.cpp"), "-o", exe])
+    for threads in ("1", "3", "8"):
+        out = subprocess.run([exe, threads], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
