@@ -94,28 +94,33 @@ __global__ void __launch_bounds__(kSumThreads, 1) summarize_kernel(const uint16_
     uint64_t* s_anc = s_own + t.n_hot;
     uint16_t* s_map = reinterpret_cast<uint16_t*>(s_anc + t.n_hot);
     for (uint32_t i = threadIdx.x; i < t.n_hot; i += kSumThreads) { s_own[i] = __ldg(t.hot_own + i); s_anc[i] = __ldg(t.hot_anc + i); }
-    for (uint32_t i = threadIdx.x; i <= t.n_patterns; i += kSumThreads) s_map[i] = __ldg(t.hot_map + i);
+    for (uint32_t i = threadIdx.x; i <= t.n_patterns; i += kSumThreads) s_map[i] = i ? __ldg(t.hot_map + i) : uint16_t(0x4000u);   // 0x4000: no pattern (slot 0 is read, its digest masked out)
     __syncthreads();
-    uint64_t positions = 0, matches = 0, h0 = 0, h1 = 0;
-    auto one = [&](uint32_t pid, uint64_t pos) {
-        if (!pid) return;
-        ++positions;
-        const uint32_t m = s_map[pid];
-        if (m != 0xFFFFu) {
-            const uint64_t own = splitmix64_d(pos ^ s_own[m & 0x7FFFu]);
-            h0 += own; h1 += own; ++matches;
-            if (m & 0x8000u) { h1 += splitmix64_d(pos ^ s_anc[m & 0x7FFFu]); ++matches; }
-            return;
-        }
-        const uint64_t own = splitmix64_d(pos ^ __ldg(t.pidhash + pid));
-        h0 += own;
-        h1 += own;                                      // the range starts with pid itself
+    // Accumulators: h0 = digest sum of the longest matches; hx = digest sum of the ANCESTORS only (h_all = h0 + hx);
+    // positions; extra = ancestor count (matches = positions + extra).
+    uint64_t h0 = 0, hx = 0;
+    uint32_t positions = 0, extra = 0;
+    // the general path: a pattern outside the shared-memory table (0.1 % of the matches of binary traffic)
+    auto slow = [&](uint32_t pid, uint64_t pos) {
+        h0 += splitmix64_d(pos ^ __ldg(t.pidhash + pid));
         const uint32_t nanc = __ldg(t.chain + pid);
-        matches += 1 + nanc;
+        extra += nanc;
         if (nanc) {
             const uint32_t b = __ldg(t.anc_off + pid) + 1;
-            for (uint32_t k = b; k < b + nanc; ++k) h1 += splitmix64_d(pos ^ __ldg(t.pidhash + __ldg(t.anc_list + k)));
+            for (uint32_t k = b; k < b + nanc; ++k) hx += splitmix64_d(pos ^ __ldg(t.pidhash + __ldg(t.anc_list + k)));
         }
+    };
+    // One position, straight-line for the common cases: s_map[0] is the "no pattern" code 0x4000, so a
+    // position without a match runs the same instructions with its digest masked out -- the 29 % of such positions cost
+    // less than the divergence of a branch around two 64-bit mixes did (18 of 32 lanes active, 72 instructions per position).
+    auto one = [&](uint32_t pid, uint64_t pos) {
+        const uint32_t m = s_map[pid];
+        if (m == 0xFFFFu) { ++positions; slow(pid, pos); return; }
+        const uint64_t own = splitmix64_d(pos ^ s_own[m & 0x3FFFu]);
+        const bool hit = !(m & 0x4000u);
+        h0 += hit ? own : 0ull;
+        positions += hit ? 1u : 0u;
+        if (m & 0x8000u) { hx += splitmix64_d(pos ^ s_anc[m & 0x3FFFu]); ++extra; }
     };
     // 8 positions (one 16-byte load) per thread and step; `out` is 16-byte aligned
     const uint64_t n8 = n / 8;
@@ -124,13 +129,14 @@ __global__ void __launch_bounds__(kSumThreads, 1) summarize_kernel(const uint16_
         const uint4 v = __ldcs(out8 + i);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
         if ((v.x | v.y | v.z | v.w) == 0) continue;
+        const uint64_t pos0 = pos_base + i * 8;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) one((w[k >> 1] >> (16 * (k & 1))) & 0xFFFF, pos_base + i * 8 + k);
+        for (int k = 0; k < 8; ++k) one((w[k >> 1] >> (16 * (k & 1))) & 0xFFFF, pos0 + k);
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 7)) one(out[n8 * 8 + threadIdx.x], pos_base + n8 * 8 + threadIdx.x);
     __shared__ uint64_t sh[4][kSumThreads / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint64_t v[4] = {warp_sum(positions), warp_sum(matches), warp_sum(h0), warp_sum(h1)};
+    uint64_t v[4] = {warp_sum(uint64_t(positions)), warp_sum(uint64_t(positions) + extra), warp_sum(h0), warp_sum(h0 + hx)};
     if (lane == 0) for (int k = 0; k < 4; ++k) sh[k][wid] = v[k];
     __syncthreads();
     if (threadIdx.x < 4) {
