@@ -152,11 +152,11 @@ int pm_engine_scan_device(pm_engine* e, int algo, const uint8_t* d_stream, size_
 int pm_engine_scan_device32(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid,
                             uint32_t* d_out, void* cuda_stream);
 
-/* Scan a HOST buffer: pinned double-buffered H2D copy, scan, D2H of the dense uint16 result,
- * synchronous.  State is carried across calls exactly like consecutive read_char calls until
- * pm_engine_reset().  replaces: the chunk loop of measure_single_instance_stats (measure.c:281-304).
- * Page-locked buffers (pm_host_alloc) are used in place; pageable ones are staged through the engine's pinned
- * buffers by its host threads in 4 MiB pieces that overlap the transfers.  Calls of <= 256 KiB (the reference's
+/* Scan a HOST buffer: the call is cut into pieces that move through a four-slot pipeline (H2D copy, scan, D2H of the
+ * dense uint16 result, each piece on its own CUDA stream); synchronous.  State is carried across calls exactly like
+ * consecutive read_char calls until pm_engine_reset().  replaces: the chunk loop of measure_single_instance_stats
+ * (measure.c:281-304).  Page-locked buffers (pm_host_alloc) are used in place; pageable ones are staged through the
+ * engine's pinned buffers by its host threads (asynchronous jobs, 512 KiB .. 4 MiB pieces) while the transfers run.  Calls of <= 256 KiB (the reference's
  * 100 KiB chunks, measure.c:77; read_char) take a latency path: one H2D copy, one kernel launch writing into mapped
  * pinned memory, one synchronise. */
 int pm_engine_scan_host(pm_engine* e, int algo, const uint8_t* stream, size_t n, uint16_t* out);
