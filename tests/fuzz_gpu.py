@@ -79,6 +79,26 @@ def main():
                 bad += 1
                 w = np.nonzero(got != want)[0]
                 print(f"MISMATCH case {case} algo {name}: {len(pats)} patterns, n={body.size}, hist={hist}, first diff at {w[:5]} got {got[w[:5]]} want {want[w[:5]]}", flush=True)
+        # 32-bit results and the reference MPBG's behaviour (longest pattern of <= 8 bytes on the answer's PatternsTree chain)
+        d_out32 = torch.zeros(max(body.size, 8), dtype=torch.int32, device=dev)
+        eng.scan_device32(d_in.data_ptr() + pad + hist, body.size, d_out32, hist_valid=hist, algo=pm.ALGO_AUTO)
+        torch.cuda.synchronize()
+        if not np.array_equal(d_out32.cpu().numpy().view(np.uint32)[:body.size], want.astype(np.uint32)):
+            bad += 1
+            print(f"MISMATCH case {case} scan_device32", flush=True)
+        lens, par = o.lengths(), o.parents()
+        short_of = np.arange(len(pats) + 1, dtype=np.int64)
+        for q in range(1, len(pats) + 1):
+            r = q - 1
+            while r >= 0 and lens[r] > 8:
+                r = int(par[r])
+            short_of[q] = r + 1
+        d_out = torch.zeros(max(body.size, 8), dtype=torch.int16, device=dev)
+        eng.scan_device(d_in.data_ptr() + pad + hist, body.size, d_out, hist_valid=hist, algo=pm.ALGO_MPBG)
+        torch.cuda.synchronize()
+        if not np.array_equal(d_out.cpu().numpy().view(np.uint16)[:body.size], short_of[want].astype(np.uint16)):
+            bad += 1
+            print(f"MISMATCH case {case} mpbg mode", flush=True)
         # the randomized variant against the oracle's restatement of it (whole stream, no history)
         seed = 0xF1A90000 + case
         eng.set_kr_seed(seed)
