@@ -204,24 +204,26 @@ template <bool kIdentCls>
 __global__ void __launch_bounds__(kHotThreads, 1) dfa_small_kernel(const DfaParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem);
-    uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_tab + (size_t((p.n_states + 7) & ~7u) << p.log2_ncp));
-    // Bank swizzle, free at run time.  With few byte classes the bank of an entry is a few low bits of the state id, and
-    // the states an adversarial stream dwells in collide there: breadth-first ids of a^k are 2^k - 1, all = 7 mod 8 --
-    // 11 wavefronts per gather on C5a (ncu: 81 % of the shared-memory wavefronts were conflict replays).  The low three
-    // bits of every state id are XORed with a fold of its higher bits -- a bijection that keeps the table size (rounded up
-    // to 8 states) -- and the table stores SWIZZLED targets, so the walk itself never computes the swizzle.
-    auto swz = [](uint32_t s) { return s ^ (((s >> 3) ^ (s >> 6) ^ (s >> 9) ^ (s >> 12) ^ (s >> 15)) & 7u); };
+    const uint32_t n_pad = (p.n_states + 31) & ~31u;          // states per class plane
+    uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_tab + (size_t(n_pad) << p.log2_ncp));
+    // Layout and bank swizzle, both free at run time.  The table is stored class-major, [class][state]: with few byte
+    // classes a state-major entry's bank is (state & 7, class), and a two-letter stream uses 2 of the 4 class slots --
+    // half of the banks never.  Class-major, the bank is the low five bits of the state id alone; those are XORed with a
+    // fold of the higher bits, because the states an adversarial stream dwells in collide there: breadth-first ids of
+    // a^k are 2^k - 1, all = 31 mod 32 (ncu on the plain layout: 11 wavefronts per gather, 81 % of the shared-memory
+    // wavefronts conflict replays; state-major with a 3-bit swizzle: 7).  The swizzle is a bijection that keeps the
+    // table size (rounded up to 32 states), and the table stores SWIZZLED targets: the walk never computes it.
+    auto swz = [](uint32_t s) { return s ^ (((s >> 5) ^ (s >> 10) ^ (s >> 15)) & 31u); };
     const uint32_t ncp = 1u << p.log2_ncp;
     for (uint32_t i = threadIdx.x; i < (p.n_states << p.log2_ncp); i += kHotThreads) {
         const uint32_t nx = __ldg(p.delta + i);
-        s_tab[(swz(i >> p.log2_ncp) << p.log2_ncp) | (i & (ncp - 1))] = swz(nx) | (uint32_t(__ldg(p.longest + nx)) << 16);
+        s_tab[(i & (ncp - 1)) * n_pad + swz(i >> p.log2_ncp)] = swz(nx) | (uint32_t(__ldg(p.longest + nx)) << 16);
     }
     if (threadIdx.x < 256) s_cls[threadIdx.x] = p.cls[threadIdx.x];
     __syncthreads();
-    const uint32_t l2 = p.log2_ncp;
     auto step = [&](uint32_t e, uint32_t c) -> uint32_t {
         if constexpr (!kIdentCls) c = s_cls[c];
-        return s_tab[((e & 0xFFFFu) << l2) | c];
+        return s_tab[c * n_pad + (e & 0xFFFFu)];
     };
     const uint64_t n_seg = (p.n + p.seg - 1) / p.seg;
     for (uint64_t seg = uint64_t(blockIdx.x) * kHotThreads + threadIdx.x; seg < n_seg; seg += uint64_t(gridDim.x) * kHotThreads) {
@@ -310,7 +312,7 @@ cudaError_t dfa_scan_launch(const DfaParams& p_in, bool ident_cls, bool flat, in
     while (seg < 16384 && p.n / (uint64_t(seg) * 2) >= uint64_t(n_sms) * kHotThreads * 2) seg *= 2;
     p.seg = seg;
     // the whole automaton is hot and its fused u32 table fits: one gather per byte
-    const size_t small_smem = (size_t((p.n_states + 7) & ~7u) << p.log2_ncp) * 4 + 256;
+    const size_t small_smem = (size_t((p.n_states + 31) & ~31u) << p.log2_ncp) * 4 + 256;
     if (p.hot_rows == p.n_states && p.n_states <= 65535 && small_smem <= 200 * 1024 && !p.no_fused) {
         auto kern = ident_cls ? dfa_small_kernel<true> : dfa_small_kernel<false>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_smem));
