@@ -217,6 +217,10 @@ int pm_engine_scan_device_records(pm_engine* e, int algo, const uint8_t* d_strea
  * writes bytes [off, off+n) of stream `kind` to d_dst.  off and n multiples of 4096. */
 int pm_engine_generate(pm_engine* e, int kind, uint64_t off, size_t n, uint8_t* d_dst, void* cuda_stream);
 
+/* Same streams into a HOST buffer (generated on the device piece by piece and copied out): what a tool that writes
+ * .stream files needs (pm_driver -g; the reference's Streams/write_first_lines.py:48-61 is unseeded Python 2). */
+int pm_engine_generate_host(pm_engine* e, int kind, uint64_t off, size_t n, uint8_t* dst);
+
 /* Timing helper used by bench.py: runs pm_engine_scan_device `iters` times on `cuda_stream`
  * bracketed by CUDA events recorded ON THAT STREAM and returns the mean milliseconds per scan. */
 int pm_engine_time_scan(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid,

@@ -86,6 +86,7 @@ def lib():
         "pm_engine_scan_device": (C.c_int, [vp, C.c_int, vp, sz, sz, vp, vp]),
         "pm_engine_scan_device32": (C.c_int, [vp, C.c_int, vp, sz, sz, vp, vp]),
         "pm_engine_prepare_host": (C.c_int, [vp]),
+        "pm_engine_generate_host": (C.c_int, [vp, C.c_int, u64, sz, vp]),
         "pm_engine_scan_host": (C.c_int, [vp, C.c_int, vp, sz, vp]),
         "pm_engine_scan_device_records": (C.c_int, [vp, C.c_int, vp, sz, sz, u64, u32, vp, vp, sz, C.POINTER(u64), vp]),
         "pm_engine_scan_host_ids": (C.c_int, [vp, C.c_int, vp, sz, vp, sz, vp]),

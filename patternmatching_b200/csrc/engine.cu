@@ -1281,6 +1281,23 @@ int pm_engine_generate(pm_engine* e, int kind, uint64_t off, size_t n, uint8_t* 
     return 0;
 }
 
+int pm_engine_generate_host(pm_engine* e, int kind, uint64_t off, size_t n, uint8_t* dst) {
+    std::lock_guard<std::mutex> lock(e->mu);
+    if (!e->parts.empty()) return fail("this dictionary has more than 65,535 patterns: only pm_engine_scan_device32, pm_engine_scan_host_ids and the plugin calls serve it");
+    CU(cudaSetDevice(e->device));
+    if ((off & 4095) || (n & 4095)) return fail("pm_engine_generate_host: off and n must be multiples of 4096");
+    if (ensure_pipe(e)) return -1;
+    const size_t chunk = e->opts.host_chunk & ~size_t(4095);
+    for (size_t o = 0; o < n; o += chunk) {   // piece by piece through the pipeline's first device buffer
+        const size_t len = std::min(chunk, n - o);
+        cudaError_t ce = pm::generate_launch(kind, off + o, len, e->d_in[0], e->pt, e->st[0], &e->launches);
+        if (ce != cudaSuccess) return cuda_fail(ce, "generate_launch");
+        CU(cudaMemcpyAsync(dst + o, e->d_in[0], len, cudaMemcpyDeviceToHost, e->st[0]));
+        CU(cudaStreamSynchronize(e->st[0]));
+    }
+    return 0;
+}
+
 int pm_engine_time_scan(pm_engine* e, int algo, const uint8_t* d_stream, size_t n, size_t hist_valid, uint16_t* d_out,
                         int iters, float* ms_per_scan, void* cuda_stream) {
     std::lock_guard<std::mutex> lock(e->mu);

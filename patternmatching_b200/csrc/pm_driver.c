@@ -50,6 +50,8 @@ static void usage(void) {
     fprintf(stderr, "  -p LIB.so             also measure every algorithm of LIB.so's mps_table (MpsElem plugins)\n");
     fprintf(stderr, "  -b BYTES              stream bytes per chunk (default 16777216)\n");
     fprintf(stderr, "  -r gpu|plugin         which instance is the reliable one\n");
+    fprintf(stderr, "  -g KIND:BYTES:FILE    write the seeded synthetic stream KIND (uniform, planted, almost, ab, ascii) of BYTES\n");
+    fprintf(stderr, "                        bytes (a multiple of 4096) to FILE and exit; planted / almost use the -d dictionaries\n");
 }
 static void fatal(const char* what) {
     fprintf(stderr, "%s: %s\n", what, pm_last_error());
@@ -204,7 +206,9 @@ int main(int argc, char* argv[]) {
     const char* reliable_kind = NULL;
     size_t chunk = (size_t)16 << 20;
     opterr = 0;
-    while ((opt = getopt(argc, argv, "d:s:o:vp:b:r:")) != -1) {
+    const char* gen_spec = NULL;
+    while ((opt = getopt(argc, argv, "d:s:o:vp:b:r:g:")) != -1) {
+        if (opt == 'g') { gen_spec = optarg; continue; }
         if (opt == 'd') ++n_dict;
         else if (opt == 's') ++n_stream;
         else if (opt == 'o') ++n_out;
@@ -213,12 +217,45 @@ int main(int argc, char* argv[]) {
         else if (opt == 'b') chunk = (size_t)strtoull(optarg, NULL, 10);
         else if (opt == 'r') reliable_kind = optarg;
         else {
-            if (optopt == 'd' || optopt == 's' || optopt == 'o' || optopt == 'p' || optopt == 'b' || optopt == 'r')
+            if (optopt == 'd' || optopt == 's' || optopt == 'o' || optopt == 'p' || optopt == 'b' || optopt == 'r' || optopt == 'g')
                 fprintf(stderr, "Option -%c must have argument.\n\n", optopt);
             else fprintf(stderr, "Unknown option -%c.\n\n", optopt);
             usage();
             return EXIT_FAILURE;
         }
+    }
+    if (gen_spec) {
+        /* stream generator mode: the engine's seeded generators, written to a file */
+        static const char* kinds[] = {"uniform", "planted", "almost", "ab", "ascii"};
+        char kind_name[16] = {0};
+        unsigned long long bytes = 0;
+        char path[4096] = {0};
+        if (sscanf(gen_spec, "%15[^:]:%llu:%4095s", kind_name, &bytes, path) != 3 || bytes == 0 || (bytes & 4095)) { usage(); return EXIT_FAILURE; }
+        int kind = -1;
+        for (int k = 0; k < 5; ++k) if (strcmp(kind_name, kinds[k]) == 0) kind = k;
+        if (kind < 0 || ((kind == 1 || kind == 2) && n_dict == 0)) { usage(); return EXIT_FAILURE; }
+        pm_dict* gd = pm_dict_create();
+        optind = 1;
+        while ((opt = getopt(argc, argv, "d:s:o:vp:b:r:g:")) != -1)
+            if (opt == 'd' && pm_dict_add_file(gd, optarg)) fatal("pm_dict_add_file");
+        if (n_dict == 0) pm_dict_add_pattern(gd, (const uint8_t*)"a", 1, 0, 1, 0);   /* the generators need a compiled dictionary */
+        if (pm_dict_compile(gd)) fatal("pm_dict_compile");
+        const char* dev = getenv("PM_B200_DEVICE");
+        pm_engine* ge = pm_engine_create(gd, dev ? atoi(dev) : 0);
+        if (!ge) fatal("pm_engine_create");
+        const size_t piece = (size_t)64 << 20;
+        uint8_t* buf = (uint8_t*)pm_host_alloc(piece);
+        FILE* f = fopen(path, "wb");
+        if (!buf || !f) { fprintf(stderr, "can't write %s\n", path); return EXIT_FAILURE; }
+        for (unsigned long long o = 0; o < bytes; o += piece) {
+            const size_t len = (size_t)(bytes - o < piece ? bytes - o : piece);
+            if (pm_engine_generate_host(ge, kind, o, len, buf)) fatal("pm_engine_generate_host");
+            if (fwrite(buf, 1, len, f) != len) { fprintf(stderr, "short write to %s\n", path); return EXIT_FAILURE; }
+        }
+        fclose(f);
+        if (verbose) printf("wrote %llu bytes of the %s stream to %s\n", bytes, kind_name, path);
+        pm_host_free(buf); pm_engine_free(ge); pm_dict_free(gd);
+        return EXIT_SUCCESS;
     }
     if (n_out != 1 || n_dict == 0 || n_stream == 0 || chunk == 0) {
         if (n_out > 1) fprintf(stderr, "Error: have more than one output file\n\n");
@@ -230,7 +267,7 @@ int main(int argc, char* argv[]) {
     char* out_name = NULL;
     int di = 0, si = 0;
     optind = 1;
-    while ((opt = getopt(argc, argv, "d:s:o:vp:b:r:")) != -1) {
+    while ((opt = getopt(argc, argv, "d:s:o:vp:b:r:g:")) != -1) {
         if (opt == 'd') dicts[di++] = optarg;
         else if (opt == 's') streams[si++] = optarg;
         else if (opt == 'o') out_name = optarg;
@@ -253,11 +290,12 @@ int main(int argc, char* argv[]) {
         }
         setup();
         n_plugin = count();
-        for (int i = 0; i < n_plugin && n_rows < MAX_ROWS - 4; ++i) rows[n_rows++].elem = table[i];
+        for (int i = 0; i < n_plugin && n_rows < MAX_ROWS - 5; ++i) rows[n_rows++].elem = table[i];
     }
     mps_gpu_register_into(&rows[n_rows].elem);     rows[n_rows++].read_block = gpu_read_block;
     mps_gpu_dfa_register_into(&rows[n_rows].elem); rows[n_rows++].read_block = gpu_read_block;
     mps_gpu_kr_register_into(&rows[n_rows].elem);  rows[n_rows++].read_block = gpu_read_block;
+    mps_gpu_mpbg_register_into(&rows[n_rows].elem); rows[n_rows++].read_block = gpu_read_block;   /* the reference MPBG's behaviour */
     Row reliable;
     memset(&reliable, 0, sizeof(reliable));
     const int reliable_plugin = reliable_kind ? strcmp(reliable_kind, "plugin") == 0 : n_plugin > 0;

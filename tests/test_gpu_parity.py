@@ -409,13 +409,26 @@ def test_driver_binary_csv(tmp_path):
     rows = [l.split(",") for l in open(out).read().splitlines()]
     assert rows[0][:6] == ["Algorithm", "Time (in secs)", "Total Memory Used", "False Positive Rate", "False Negative Rate",
                            "Partial Success Rate"]
-    assert len(rows) == 4
+    assert len(rows) == 5
     for row in rows[1:3]:
         assert [float(x) for x in row[3:6]] == [0.0, 0.0, 0.0] and int(row[2]) > 0 and int(row[6]) == 10240
     kr = [float(x) for x in rows[3][3:6]]
     assert kr[0] <= 1e-3 and kr[1] == 0.0          # randomized row: no false negatives, (almost) no false positives
+    # the PM_ALGO_MPBG row on the merged dictionary: the reference MPBG's own rates, results.csv:4 (3 FN + 233 partial of 10240)
+    assert rows[4][0] == "B200 MPBG (as shipped)" and [float(x) for x in rows[4][3:6]] == [0.0, 0.000293, 0.022754]
     # missing output file -> usage + failure, like the reference's parse_arguments
     assert subprocess.run([exe, "-d", "x"], capture_output=True).returncode != 0
+    # -g: the seeded generators written to a .stream file, identical to the oracle's generator
+    sf = tmp_path / "planted.stream"
+    args = [exe, "-g", f"planted:{1 << 20}:{sf}"]
+    for p in dict_paths("merged"):
+        args += ["-d", p]
+    assert subprocess.run(args, capture_output=True, timeout=300).returncode == 0
+    o = Oracle()
+    for p in dict_paths("merged"):
+        o.add_dict_file(p)
+    o.compile()
+    assert np.array_equal(np.fromfile(sf, dtype=np.uint8), o.gen("planted", 0, 1 << 20))
 
 
 def test_auto_picks_the_kernel_from_a_sample(oracle_merged, engine_merged):

@@ -69,23 +69,24 @@ def test_driver_hosts_reference_cpu_algorithms_beside_gpu_rows(tmp_path):
     r = subprocess.run(args, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     head, rows = read_csv(out)
-    assert len(rows) == 6
+    assert len(rows) == 7
     gpu_rows = [v for k, v in rows.items() if k.startswith("B200")]
     cpu_rows = [v for k, v in rows.items() if not k.startswith("B200")]
-    assert len(gpu_rows) == 3 and len(cpu_rows) == 3
+    assert len(gpu_rows) == 4 and len(cpu_rows) == 3
     for v in gpu_rows[:2]:
         assert rates(v) == [0.0, 0.0, 0.0] and int(v[6]) == 10240
     exact_cpu = [v for v in cpu_rows if rates(v) == [0.0, 0.0, 0.0]]
     assert len(exact_cpu) == 2 and 511307 * 2072 + 24 in [int(v[2]) for v in exact_cpu]      # AC and LMAC; 511,307 states
     mpbg = [v for v in cpu_rows if rates(v) != [0.0, 0.0, 0.0]][0]
     assert rates(mpbg) == [0.0, 0.000391, 0.018262]            # snort only: 4 FN + 187 partial of 10240
+    assert rates(rows["B200 MPBG (as shipped)"]) == rates(mpbg)  # PM_ALGO_MPBG: the same rates as the reference's MPBG row
     # -r gpu: the same run classified against the B200 DFA instead; needs no plugin
     out2 = tmp_path / "r2.csv"
     r = subprocess.run([exe, "-o", str(out2), "-r", "gpu", "-b", "102400", "-s", os.path.join(DATA, "dictionaries_generated.stream"),
                         "-d", dict_paths("snort")[0]], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     _, rows2 = read_csv(out2)
-    assert len(rows2) == 3 and all(rates(v)[1] == 0.0 for v in rows2.values())
+    assert len(rows2) == 4 and all(rates(v)[1] == 0.0 for k, v in rows2.items() if "MPBG" not in k)
 
 
 @pytest.fixture(scope="module")
