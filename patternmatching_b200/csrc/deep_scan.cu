@@ -199,10 +199,11 @@ cudaError_t deep_scan_launch(const DeepParams& p_in, int n_sms, cudaStream_t st,
     if (p.n == 0) return cudaSuccess;
     const size_t smem = deep_smem_bytes(p.n_hot, p.n_small);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    // segments: about 4 KiB each (the warm-up is max_pat_len-1 bytes), cut so that the persistent grid's lanes get the
-    // same number of them; multiples of 16 bytes (8-byte loads, 16-byte result stores)
+    // segments: up to 16 KiB each (every segment pays a warm-up of max_pat_len-1 bytes: 346 of 4 KiB were 8 % of the
+    // walk), cut so that the persistent grid's lanes get the same number of them; multiples of 16 bytes (8-byte loads,
+    // 16-byte result stores)
     const uint64_t lanes = uint64_t(n_sms) * kThreads;
-    uint64_t per_lane = (p.n + lanes * 4096 - 1) / (lanes * 4096);
+    uint64_t per_lane = (p.n + lanes * 16384 - 1) / (lanes * 16384);
     if (per_lane == 0) per_lane = 1;
     uint64_t seg = (p.n + lanes * per_lane - 1) / (lanes * per_lane);
     seg = (seg + 15) / 16 * 16;

@@ -308,8 +308,16 @@ cudaError_t dfa_scan_launch(const DfaParams& p_in, bool ident_cls, bool flat, in
         return cudaGetLastError();
     }
     // segment length: long enough to amortise the warm-up, short enough to give every SM work
-    uint32_t seg = 4096;
-    while (seg < 16384 && p.n / (uint64_t(seg) * 2) >= uint64_t(n_sms) * kHotThreads * 2) seg *= 2;
+    // up to 16 KiB, cut so that every lane of the persistent grid gets the same number of segments (262,144 segments
+    // of 4 KiB on 151,552 lanes leave the second pass 73 % full) and the warm-up of max_pat_len-1 bytes per segment stays
+    // small; multiples of 32 bytes (256-bit loads and stores)
+    const uint64_t lanes = uint64_t(n_sms) * kHotThreads;
+    uint64_t per_lane = (p.n + lanes * 16384 - 1) / (lanes * 16384);
+    if (per_lane == 0) per_lane = 1;
+    uint64_t seg64 = (p.n + lanes * per_lane - 1) / (lanes * per_lane);
+    seg64 = (seg64 + 31) / 32 * 32;
+    if (seg64 < 1024) seg64 = 1024;
+    const uint32_t seg = uint32_t(seg64);
     p.seg = seg;
     // the whole automaton is hot and its fused u32 table fits: one gather per byte
     const size_t small_smem = (size_t((p.n_states + 31) & ~31u) << p.log2_ncp) * 4 + 256;
