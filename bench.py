@@ -180,7 +180,19 @@ def roofline_entry(algo_name, n, step_ms, main_ms, scan_ms, n_prof, peak, peak_s
                 tsrc = f"ncu --set full capture of this command ({tr.get('source')}), dram__bytes_read+write per launch scaled by stream bytes"
         except Exception:
             traffic = None
-    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    # SURVEY 8d's second candidate: the dependent-lookup rate.  One root2 gather per position costs the LSU data pipe
+    # 3.53 wavefronts per 32 positions (the expected maximum bank load of 32 random indices; scripts/microbench/lds_gather.cu,
+    # profiles/r02_kernel.md), one wavefront per clock and SM: that alone allows n_sms * clock * 32 / 3.53 bytes of stream per
+    # second.  The LOWER of the two stream ceilings is the binding roofline (HBM: peak / 3).
+    lookup = None
+    if algo_name == "sfx":
+        sm_hz = 1.965e9
+        ceiling = 148 * sm_hz * 32 / 3.53 / 1e9
+        lookup = {"bound": "shared-memory gather (LSU data pipe)", "stream_ceiling_GBps": ceiling, "hbm_stream_ceiling_GBps": peak / 3.0,
+                  "binding": "hbm" if peak / 3.0 < ceiling else "lookup", "achieved_stream_GBps": n / (kernel_ms * 1e-3) / 1e9,
+                  "frac_of_lookup_ceiling": n / (kernel_ms * 1e-3) / 1e9 / ceiling,
+                  "note": "148 SMs x 1.965 GHz x 32 positions / 3.53 wavefronts per gather; ncu: l1tex data pipe 88.6 % busy with ALL of the kernel's wavefronts"}
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "lookup_roofline": lookup,
             "traffic_source": tsrc, "kernel": kernel, "algorithmic_bytes_per_stream_byte": 3, "kernel_ms": kernel_ms,
             "kernel_share_of_step": share, "kernel_timing": how, "peak_source": peak_src}
 

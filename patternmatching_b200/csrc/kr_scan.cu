@@ -42,7 +42,9 @@ constexpr int kPowBytes = ((kSpan + 1) * 4 + 15) / 16 * 16;   // one power table
 constexpr int kOffBloom = 0;                                  // 65536
 constexpr int kOffRpow = kOffBloom + kBloomWords * 4;
 constexpr int kOffRinv = kOffRpow + kPowBytes;
-constexpr int kOffWarp = kOffRinv + kPowBytes;                // per warp: phi[(kSpan + 1)] u32, then the staged bytes
+constexpr int kOffLong = kOffRinv + kPowBytes;                // one bit per pid: the pattern has more than 8 bytes (8 KiB for 65,536 pids)
+constexpr int kLongWords = 65536 / 32;
+constexpr int kOffWarp = kOffLong + kLongWords * 4;           // per warp: phi[(kSpan + 1)] u32, then the staged bytes
 constexpr int kWarpBytes = kPowBytes + kSpan + 16;             // + the warp's mbarrier (bulk-copy staging)
 constexpr int kSmem = kOffWarp + kWarps * kWarpBytes;
 static_assert(kWarpBytes % 16 == 0 && kSmem <= 227 * 1024, "shared memory budget");
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) 
     uint32_t* s_bloom = reinterpret_cast<uint32_t*>(smem + kOffBloom);
     uint32_t* s_rpow = reinterpret_cast<uint32_t*>(smem + kOffRpow);
     uint32_t* s_rinv = reinterpret_cast<uint32_t*>(smem + kOffRinv);
+    uint32_t* s_longbits = reinterpret_cast<uint32_t*>(smem + kOffLong);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint32_t* s_phi = reinterpret_cast<uint32_t*>(smem + kOffWarp + wid * kWarpBytes);
     uint8_t* s_bytes = reinterpret_cast<uint8_t*>(s_phi) + kPowBytes;
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) 
 
     for (int i = tid; i < kBloomWords; i += kThreads) s_bloom[i] = __ldg(p.t.bloom + i);
     for (int i = tid; i <= kSpan; i += kThreads) { s_rpow[i] = __ldg(p.t.rpow + i); s_rinv[i] = __ldg(p.t.rinvpow + i); }
+    for (int i = tid; i < kLongWords; i += kThreads) s_longbits[i] = __ldg(p.t.long_bits + i);
     __syncthreads();  // the only CTA-wide barrier
 
     const uint64_t gw = uint64_t(blockIdx.x) * kWarps + wid, G = uint64_t(gridDim.x) * kWarps;
@@ -182,8 +186,12 @@ __global__ void __launch_bounds__(kThreads, 1) kr_scan_kernel(const KrParams p) 
                 const uint32_t q = uint32_t(kb + k) * 32 + lane;
                 sp[k] = q < len ? uint32_t(p.out[s0 + q]) : 0u;
             }
+            // short_of[] is the identity for patterns of <= 8 bytes -- 99.9 % of the matches of binary traffic; only the
+            // others pay for the gather from the 111 KB table (as a gather for every position it was 0.8 L1 sectors
+            // per stream byte, most of this kernel's global-load traffic)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) sp[k] = __ldg(p.t.short_of + sp[k]);
+            for (int k = 0; k < 4; ++k)
+                if ((s_longbits[sp[k] >> 5] >> (sp[k] & 31u)) & 1u) sp[k] = __ldg(p.t.short_of + sp[k]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t q = uint32_t(kb + k) * 32 + lane;
@@ -270,14 +278,17 @@ cudaError_t kr_upload_tables(const Dict& d, const KrTables& k, KrDevTables* t, s
     if ((e = up(vec.data(), vec.size() * sizeof(vec[0]), reinterpret_cast<void**>(&t->field))) != cudaSuccess) return e;
     UP(k.slot_fp, slot_fp) UP(k.slot_begin, slot_begin) UP(k.slot_count, slot_count) UP(k.cand_pid, cand_pid)
     UP(k.cand_len, cand_len) UP(k.cand_stage_off, cand_stage_off) UP(k.stage_fp, stage_fp) UP(k.bloom, bloom)
-    UP(rpow, rpow) UP(rinvpow, rinvpow) UP(short_of, short_of)
+    std::vector<uint32_t> long_bits(65536 / 32, 0);
+    for (size_t i = 0; i < d.pats.size() && i + 1 < 65536; ++i)
+        if (d.pats[i].len > 8) long_bits[(i + 1) >> 5] |= 1u << ((i + 1) & 31);
+    UP(rpow, rpow) UP(rinvpow, rinvpow) UP(short_of, short_of) UP(long_bits, long_bits)
 #undef UP
     return cudaSuccess;
 }
 
 void kr_free_tables(KrDevTables* t) {
     void* ptrs[] = {t->slot_fp, t->slot_begin, t->slot_count, t->cand_pid, t->cand_len, t->cand_stage_off,
-                    t->stage_fp, t->bloom, t->rpow, t->rinvpow, t->short_of};
+                    t->stage_fp, t->bloom, t->rpow, t->rinvpow, t->short_of, t->long_bits};
     for (void* p : ptrs) if (p) cudaFree(p);
     *t = KrDevTables();
 }

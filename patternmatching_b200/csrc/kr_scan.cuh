@@ -19,6 +19,7 @@ struct KrDevTables {
     uint32_t* rpow = nullptr;      // r^k,  k < kHalo + kKrTile
     uint32_t* rinvpow = nullptr;   // r^-k
     uint16_t* short_of = nullptr;  // pid -> longest ancestor-or-self of <= 8 bytes (0 = none)
+    uint32_t* long_bits = nullptr; // bit pid: the pattern has more than 8 bytes (short_of[pid] != pid); 2048 words
 };
 
 cudaError_t kr_upload_tables(const Dict& d, const KrTables& k, KrDevTables* t, size_t* bytes);
