@@ -412,18 +412,6 @@ __global__ void __launch_bounds__(kThreads, 1) sfx_scan_kernel(const SfxParams p
     if (tid == 0) { p.qcount[2 * blockIdx.x] = s_qcnt[2]; p.qcount[2 * blockIdx.x + 1] = s_qcnt[1]; }
 }
 
-// Deferred walks (levels >= 5).  An item is a chain of dependent memory round trips (~900 cycles each: the stream
-// bytes come from DRAM, rows / pattern text from L2) whose length differs wildly between items (one lookup ...
-// hundreds for a long repetitive pattern), and nothing hides a round trip but other, independent, round trips.
-// So every lane runs kSlots independent state machines; one loop iteration first ISSUES the next load of every
-// slot (whatever its state) and only then CONSUMES them: one wait per iteration for all slots of all lanes, and a
-// slot pulls its next item the moment its current one ends.  One CTA drains the strip of one scan CTA in two phases:
-//   phase A, "continue at row" items (front of the strip; payload = row): row lookups, the stream bytes coming
-//            from an 8-byte history word; a walk that reaches a tail entry is appended to the tail items;
-//   phase B, "tail of pattern" items (back of the strip; payload = pid | depth << 16): 8-byte compares of the
-//            stream against the pattern text, then (rarely) a few steps up the PatternsTree chain.
-constexpr int kSlots = 2;
-
 // raw halves of load8_ending_at, so that issue and use can be separated
 __device__ __forceinline__ void load8_issue(const uint8_t* a, const uint8_t* floor, uint64_t& hi, uint64_t& lo) {
     const uintptr_t ua = reinterpret_cast<uintptr_t>(a);
@@ -437,6 +425,20 @@ __device__ __forceinline__ uint64_t load8_merge(const uint8_t* a, uint64_t hi, u
     return sh == 56 ? hi : ((hi << (56 - sh)) | (lo >> (sh + 8)));
 }
 
+// Deferred walks (levels >= 5).  An item is a chain of dependent memory round trips (~900 cycles each: the stream
+// bytes come from DRAM, rows / pattern text from L2), and nothing hides a round trip but other, independent, round trips.
+// One CTA drains the strip of one scan CTA in two phases:
+//   phase A, "continue at row" items (front of the strip; payload = row): 8 history bytes, then one row lookup per
+//            byte; a walk that reaches a tail entry is appended to the tail items.  Walk lengths differ wildly, so
+//            every lane keeps its own walks going and claims a new item whenever one ends;
+//   phase B, "tail of pattern" items (back of the strip; payload = pid | depth << 16): the tail record, then 8-byte
+//            compares of the stream against the pattern text, then (rarely) a few steps up the PatternsTree chain.
+//            These are alike, so a WARP takes 2 x 32 consecutive items at a time and moves them through the same
+//            steps together: all loads of a step are in flight at once, a finished lane is masked until the batch ends.
+// The first generations gave every lane its own state machines (two per lane, items claimed one by one): no lane waited
+// for another, but the lanes of a warp sat in different states and the hardware ran the states one after the other --
+// ncu: 11.4 of 32 lanes active per issued instruction, 40 warp instructions per item.  Batches wait for their slowest
+// item, yet issue a tenth of the instructions; items of a strip are neighbours in the stream, so their lengths are alike.
 template <bool kIdentCls, bool kFlags>
 __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
     __shared__ uint32_t s_tails, s_next_a, s_next_b;   // tail items so far; next unclaimed item of each phase
@@ -446,69 +448,85 @@ __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
     const uint8_t* const floor_s = p.stream - p.hist_valid;  // first readable stream byte
     if (threadIdx.x == 0) { s_tails = p.qcount[2 * blockIdx.x + 1]; s_next_a = 0; s_next_b = 0; }
     __syncthreads();
-    enum : uint32_t { kIdle, kItem, kHist, kRow, kRec, kCmp, kChain, kEnd };
+    const uint32_t lane = threadIdx.x & 31u;
+    constexpr uint32_t kFull = 0xFFFFFFFFu;
 
     // ---- phase A ----
+    // Row walks differ too much in length for batches (3.7 lookups on average, 16 for the longest of 32: a batch ran
+    // with 7 of 32 lanes active): every lane keeps kA walks going and takes a new item the moment one ends.  One
+    // iteration ISSUES the next load of every walk -- the item itself, 8 bytes of history, or a row entry -- and only
+    // then CONSUMES them: one wait per iteration for all of them.  Items are claimed with one shared-memory atomic per
+    // warp and iteration.
     {
-        uint32_t st[kSlots], v[kSlots], hist_left[kSlots], ld32[kSlots];
-        uint64_t pos[kSlots], k[kSlots], hist[kSlots], ld_hi[kSlots], ld_lo[kSlots];
+        constexpr int kA = 2;
+        enum : uint32_t { kNeedItem, kNeedHist, kLookup, kEnd };
+        uint32_t st[kA], v[kA], left[kA], idx[kA], ld_c[kA];
+        uint64_t pos[kA], k[kA], hist[kA], ld_a[kA], ld_b[kA];
 #pragma unroll
-        for (int s = 0; s < kSlots; ++s) { st[s] = kIdle; v[s] = 0; hist_left[s] = 0; ld32[s] = 0; pos[s] = 0; k[s] = 0; hist[s] = 0; ld_hi[s] = 0; ld_lo[s] = 0; }
+        for (int u = 0; u < kA; ++u) { st[u] = kNeedItem; v[u] = left[u] = idx[u] = ld_c[u] = 0; pos[u] = k[u] = hist[u] = ld_a[u] = ld_b[u] = 0; }
         for (;;) {
-            // issue
+            bool alive = false;
 #pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
-                if (st[s] == kIdle) {
-                    // items are claimed one at a time: their cost differs by two orders of magnitude, and a fixed
-                    // share per lane left 2/3 of the lanes idle behind the stragglers
-                    const uint32_t q = n_rows ? atomicAdd(&s_next_a, 1u) : 0u;
-                    if (q < n_rows) { ld_hi[s] = q_strip[q]; st[s] = kItem; }
-                    else st[s] = kEnd;
-                } else if (st[s] == kHist) {
-                    load8_issue(p.stream + pos[s] - k[s], floor_s, ld_hi[s], ld_lo[s]);
-                } else if (st[s] == kRow) {
-                    uint32_t c = uint32_t(hist[s] >> 56);
-                    hist[s] <<= 8; --hist_left[s];
+            for (int u = 0; u < kA; ++u) {
+                const uint32_t need = __ballot_sync(kFull, st[u] == kNeedItem);
+                if (need) {
+                    const uint32_t leader = uint32_t(__ffs(int(need))) - 1u;
+                    uint32_t first = 0;
+                    if (lane == leader) first = atomicAdd(&s_next_a, uint32_t(__popc(need)));
+                    first = __shfl_sync(kFull, first, int(leader));
+                    if (st[u] == kNeedItem) {
+                        idx[u] = first + uint32_t(__popc(need & ((1u << lane) - 1u)));
+                        if (idx[u] >= n_rows) st[u] = kEnd;
+                    }
+                }
+                alive = alive || st[u] != kEnd;
+            }
+            if (!__any_sync(kFull, alive)) break;
+            // ---- issue ----
+#pragma unroll
+            for (int u = 0; u < kA; ++u) {
+                if (st[u] == kNeedItem) {
+                    ld_a[u] = q_strip[idx[u]];
+                } else if (st[u] == kNeedHist) {
+                    load8_issue(p.stream + pos[u] - k[u], floor_s, ld_a[u], ld_b[u]);
+                } else if (st[u] == kLookup) {
+                    uint32_t c = uint32_t(hist[u] >> 56);
+                    hist[u] <<= 8; --left[u];
                     if constexpr (!kIdentCls) c = __ldg(p.cls + c);
-                    ld32[s] = __ldg(p.rows + ((size_t(v[s] & 0xFFFFFFu) << p.log2_ncp) | c));
+                    ld_c[u] = __ldg(p.rows + ((size_t(v[u] & 0xFFFFFFu) << p.log2_ncp) | c));
                 }
             }
-            bool all_end = true;
+            // ---- consume ----
 #pragma unroll
-            for (int s = 0; s < kSlots; ++s) all_end = all_end && st[s] == kEnd;
-            if (all_end) break;
-            // consume
-#pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
-                if (st[s] == kItem) pos[s] = ld_hi[s] >> 25;
-                const uint64_t avail = pos[s] + p.hist_valid + 1;
-                if (st[s] == kItem) {
-                    v[s] = kCont | uint32_t(ld_hi[s] & 0xFFFFFFu);
-                    k[s] = 4;
-                    st[s] = kHist;
-                } else if (st[s] == kHist) {
-                    hist[s] = load8_merge(p.stream + pos[s] - k[s], ld_hi[s], ld_lo[s]);
-                    hist_left[s] = 8;
-                    st[s] = kRow;
-                } else if (st[s] == kRow) {
-                    v[s] = ld32[s];
-                    ++k[s];
-                    if (v[s] & kTail) {  // hand over to phase B
+            for (int u = 0; u < kA; ++u) {
+                if (st[u] == kNeedItem) {
+                    pos[u] = ld_a[u] >> 25;
+                    v[u] = kCont | uint32_t(ld_a[u] & 0xFFFFFFu);
+                    k[u] = 4;
+                    st[u] = kNeedHist;
+                } else if (st[u] == kNeedHist) {
+                    hist[u] = load8_merge(p.stream + pos[u] - k[u], ld_a[u], ld_b[u]);   // c[pos-k] in the top byte
+                    left[u] = 8;
+                    st[u] = kLookup;
+                } else if (st[u] == kLookup) {
+                    v[u] = ld_c[u];
+                    ++k[u];
+                    if (v[u] & kTail) {  // hand over to phase B
                         const uint32_t t = atomicAdd(&s_tails, 1u);
-                        if (t < cap_tails) q_strip[p.q_per_cta - 1 - t] = (pos[s] << 25) | (uint32_t(k[s]) << 16) | (v[s] & 0xFFFFu);
-                        else put_result<kFlags>(p, pos[s], sfx_finish(p, v[s], k[s], p.stream + pos[s], avail));  // strip full
-                        st[s] = kIdle;
-                    } else if (!(v[s] & kCont)) {
-                        put_result<kFlags>(p, pos[s], v[s]);
-                        st[s] = kIdle;
-                    } else if (hist_left[s] == 0) {
-                        st[s] = kHist;
+                        if (t < cap_tails) q_strip[p.q_per_cta - 1 - t] = (pos[u] << 25) | (uint32_t(k[u]) << 16) | (v[u] & 0xFFFFu);
+                        else put_result<kFlags>(p, pos[u], sfx_finish(p, v[u], k[u], p.stream + pos[u], pos[u] + p.hist_valid + 1));  // strip full
+                        st[u] = kNeedItem;
+                    } else if (!(v[u] & kCont)) {
+                        put_result<kFlags>(p, pos[u], v[u]);
+                        st[u] = kNeedItem;
+                    } else if (left[u] == 0) {
+                        st[u] = kNeedHist;
                     }
                 }
                 // the walk needs a byte that does not exist (start of the stream): the row's own best pattern
-                if ((st[s] == kHist || st[s] == kRow) && k[s] >= avail) {
-                    put_result<kFlags>(p, pos[s], __ldg(p.row_best + (v[s] & 0xFFFFFFu)));
-                    st[s] = kIdle;
+                if ((st[u] == kNeedHist || st[u] == kLookup) && k[u] >= pos[u] + p.hist_valid + 1) {
+                    put_result<kFlags>(p, pos[u], __ldg(p.row_best + (v[u] & 0xFFFFFFu)));
+                    st[u] = kNeedItem;
                 }
             }
         }
@@ -516,80 +534,76 @@ __global__ void __launch_bounds__(1024) sfx_deep_kernel(const SfxParams p) {
     __syncthreads();
 
     // ---- phase B ----
-    {
-        const uint32_t n_tails = min(s_tails, cap_tails);
-        const uint64_t* q_back = q_strip + (p.q_per_cta - 1);  // item j sits at q_back[-j]
-        uint32_t st[kSlots], pid[kSlots], len[kSlots], next_term[kSlots], best_start[kSlots], text_off[kSlots], k[kSlots], lim[kSlots];
-        uint32_t ld_len[kSlots], ld_par[kSlots];
-        uint64_t pos[kSlots], a_hi[kSlots], a_lo[kSlots], b_hi[kSlots], b_lo[kSlots];
-        uint4 rec[kSlots];
+    // kB batches of 32 items per warp at a time: the steps of the batches are independent, so their loads are in flight
+    // together (the kernel is bound by the latency of its dependent round trips, not by instruction issue)
+    constexpr int kB = 2;
+    const uint32_t n_tails = min(s_tails, cap_tails);
+    const uint64_t* q_back = q_strip + (p.q_per_cta - 1);  // item j sits at q_back[-j]
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&s_next_b, 32u * kB);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= n_tails) break;
+        bool active[kB], cmp_done[kB];
+        uint64_t pos[kB], avail[kB];
+        uint32_t pid[kB], k[kB], lim[kB];
+        uint4 rec[kB];
 #pragma unroll
-        for (int s = 0; s < kSlots; ++s) {
-            st[s] = kIdle; pid[s] = len[s] = next_term[s] = best_start[s] = text_off[s] = k[s] = lim[s] = ld_len[s] = ld_par[s] = 0;
-            pos[s] = a_hi[s] = a_lo[s] = b_hi[s] = b_lo[s] = 0; rec[s] = make_uint4(0, 0, 0, 0);
+        for (int u = 0; u < kB; ++u) {
+            const uint32_t idx = base + 32u * u + lane;
+            active[u] = idx < n_tails;
+            const uint64_t item = active[u] ? *(q_back - idx) : 0ull;
+            pos[u] = item >> 25;
+            pid[u] = uint32_t(item & 0xFFFFu);
+            k[u] = uint32_t(item >> 16) & 0x1FFu;      // bytes matched so far (the last k bytes of the pattern)
+        }
+#pragma unroll
+        for (int u = 0; u < kB; ++u) {
+            rec[u] = make_uint4(0, 0, 0, 0);
+            if (active[u]) rec[u] = __ldg(p.tail_rec + pid[u]);   // x = text offset, y = length, z = next terminal, w = best at the start
+        }
+#pragma unroll
+        for (int u = 0; u < kB; ++u) {
+            avail[u] = pos[u] + p.hist_valid + 1;
+            lim[u] = uint64_t(rec[u].y) < avail[u] ? rec[u].y : uint32_t(avail[u]);
+            cmp_done[u] = !active[u] || k[u] >= lim[u];
         }
         for (;;) {
-            // issue
+            bool any = false;
 #pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
-                if (st[s] == kIdle) {
-                    const uint32_t q = n_tails ? atomicAdd(&s_next_b, 1u) : 0u;
-                    if (q < n_tails) { a_hi[s] = *(q_back - q); st[s] = kItem; }
-                    else st[s] = kEnd;
-                } else if (st[s] == kRec) {
-                    rec[s] = __ldg(p.tail_rec + pid[s]);   // x = text offset, y = length, z = next terminal, w = best at the start
-                } else if (st[s] == kCmp) {
-                    load8_issue(p.stream + pos[s] - k[s], floor_s, a_hi[s], a_lo[s]);
-                    load8_issue(p.pat_bytes + text_off[s] + (len[s] - 1 - k[s]), p.pat_bytes, b_hi[s], b_lo[s]);
-                } else if (st[s] == kChain) {
-                    ld_len[s] = __ldg(p.pat_len + pid[s] - 1);
-                    ld_par[s] = __ldg(p.parent + pid[s]);
+            for (int u = 0; u < kB; ++u) any = any || !cmp_done[u];
+            if (!__any_sync(kFull, any)) break;
+            uint64_t a[kB], b[kB];
+#pragma unroll
+            for (int u = 0; u < kB; ++u) {
+                a[u] = b[u] = 0;
+                if (!cmp_done[u]) {
+                    a[u] = load8_ending_at(p.stream + pos[u] - k[u], floor_s);
+                    b[u] = load8_ending_at(p.pat_bytes + rec[u].x + (rec[u].y - 1 - k[u]), p.pat_bytes);
                 }
             }
-            bool all_end = true;
 #pragma unroll
-            for (int s = 0; s < kSlots; ++s) all_end = all_end && st[s] == kEnd;
-            if (all_end) break;
-            // consume
-#pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
-                if (st[s] == kItem) {
-                    pos[s] = a_hi[s] >> 25;
-                    pid[s] = uint32_t(a_hi[s] & 0xFFFFu);
-                    k[s] = uint32_t(a_hi[s] >> 16) & 0x1FFu;      // bytes matched so far (the last k bytes of the pattern)
-                    st[s] = kRec;
-                } else if (st[s] == kRec) {
-                    text_off[s] = rec[s].x; len[s] = rec[s].y; next_term[s] = rec[s].z; best_start[s] = rec[s].w;
-                    const uint64_t avail = pos[s] + p.hist_valid + 1;
-                    lim[s] = uint64_t(len[s]) < avail ? len[s] : uint32_t(avail);
-                    st[s] = kCmp;
-                } else if (st[s] == kCmp) {
-                    const uint64_t a = load8_merge(p.stream + pos[s] - k[s], a_hi[s], a_lo[s]);
-                    const uint64_t b = load8_merge(p.pat_bytes + text_off[s] + (len[s] - 1 - k[s]), b_hi[s], b_lo[s]);
-                    const uint64_t x = a ^ b;
+            for (int u = 0; u < kB; ++u) {
+                if (!cmp_done[u]) {
+                    const uint64_t x = a[u] ^ b[u];
                     const uint32_t same = x ? uint32_t(__clzll((long long)x) >> 3) : 8u;   // equal bytes from the top (= backwards)
-                    const uint32_t left = lim[s] - k[s];
-                    k[s] += same < left ? same : left;
-                    if (same < 8 || k[s] >= lim[s]) {
-                        if (k[s] < next_term[s]) { put_result<kFlags>(p, pos[s], best_start[s]); st[s] = kIdle; }       // no further terminal reached
-                        else if (k[s] >= len[s]) { put_result<kFlags>(p, pos[s], pid[s]); st[s] = kIdle; }              // the whole pattern
-                        else st[s] = kChain;   // the longest pattern of the chain with length <= k
-                    }
-                } else if (st[s] == kChain) {
-                    if (ld_len[s] > k[s]) {
-                        pid[s] = ld_par[s];
-                        if (pid[s] == 0) { put_result<kFlags>(p, pos[s], 0); st[s] = kIdle; }
-                    } else {
-                        put_result<kFlags>(p, pos[s], pid[s]);
-                        st[s] = kIdle;
-                    }
+                    const uint32_t left = lim[u] - k[u];
+                    k[u] += same < left ? same : left;
+                    if (same < 8 || k[u] >= lim[u]) cmp_done[u] = true;
                 }
-                // a tail item that cannot advance at all (k already at its limit) is resolved by the same rules
-                if (st[s] == kCmp && k[s] >= lim[s]) {
-                    if (k[s] < next_term[s]) { put_result<kFlags>(p, pos[s], best_start[s]); st[s] = kIdle; }
-                    else if (k[s] >= len[s]) { put_result<kFlags>(p, pos[s], pid[s]); st[s] = kIdle; }
-                    else st[s] = kChain;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kB; ++u) {
+            if (active[u]) {
+                uint32_t res, q = pid[u];
+                if (k[u] < rec[u].z) res = rec[u].w;                  // no further terminal reached: best at the tail start
+                else if (k[u] >= rec[u].y) res = q;                   // the whole pattern
+                else {                                                // the longest pattern of the chain with length <= k
+                    while (q && __ldg(p.pat_len + q - 1) > k[u]) q = __ldg(p.parent + q);
+                    res = q;
                 }
+                put_result<kFlags>(p, pos[u], res);
             }
         }
     }
