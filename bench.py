@@ -347,7 +347,8 @@ def main():
             recv_bytes = 8 * (tot - counts[0])
             sparse["gather"] = {"ms": g_ms, "records_total": int(tot), "bytes_into_rank0": int(recv_bytes),
                                 "effective_GBps_into_rank0": recv_bytes / (g_ms * 1e-3) / 1e9 if g_ms else None,
-                                "share_of_scan_step": g_ms / ms_step, "call": "pm_comm_gather_records (ncclAllGather of counts + grouped ncclSend/ncclRecv)"}
+                                "share_of_scan_step": g_ms / ms_step, "call": "pm_comm_gather_records (ncclAllGather of counts, then one peer-to-peer copy per rank into the root's "
+                                        "IPC-mapped staging buffer; grouped ncclSend/ncclRecv when the GPUs cannot map each other)"}
             if rank == 0:
                 pos = allrec[:tot] >> 24
                 sparse["gather"]["position_sorted"] = bool((pos[1:] > pos[:-1]).all().item()) if tot > 1 else True

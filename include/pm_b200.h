@@ -250,8 +250,9 @@ uint64_t pm_engine_launch_count(const pm_engine* e);
  * Multi-GPU: one process per GPU, the stream cut into contiguous shards that each read max_pat_len-1 bytes of history
  * (hist_valid) -- no exchange step in the scan (Core/src/measure.c:262-306 keeps state across chunks, a
  * warmed-up shard reports the same matches).  The only communication is the gather of the per-rank, position-sorted
- * record lists to one rank, over NCCL (NVLink): all-gather of the counts, then grouped ncclSend / ncclRecv of the
- * variable-length lists; rank order is position order, so the concatenation is sorted.  NCCL is dlopen'ed at first use
+ * record lists to one rank over NVLink: an NCCL all-gather of the counts, then one peer-to-peer copy per rank into the
+ * root's CUDA-IPC-mapped staging buffer (grouped ncclSend / ncclRecv when the GPUs cannot map each other's memory, or with
+ * PM_COMM_NO_P2P=1); rank order is position order, so the concatenation is sorted.  NCCL is dlopen'ed at first use
  * (libnccl.so.2 of the process), the library has no link-time dependency on it.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct pm_comm pm_comm;
